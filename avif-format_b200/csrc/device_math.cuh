@@ -1,0 +1,420 @@
+// device_math.cuh -- float powf / expf / logf whose results are bit-identical to glibc's (>= 2.28).
+//
+// Why this exists: the reference's transfer functions (ColorTransfer.cpp:69-220) are a handful of IEEE float
+// operations around powf / expf / logf, so "identical to the reference's CPU loop" means "identical libm
+// results".  CUDA's own powf (a few ULP) and even a correctly rounded powf would differ from the host on
+// 0.06-0.17 % of inputs, and the PQ curve amplifies a 1-ULP inner difference to hundreds of ULP (SURVEY.md
+// section 7.4).  glibc computes these three functions in binary64 with a small table and a short polynomial
+// and rounds once to binary32; that is cheap on B200 (full-rate FP64 FMA pipe) and reproducible, so the device
+// evaluates the very same operation sequence: same tables (libm_tables.inc, recovered from the installed
+// libm and cross-checked), same association, fused multiply-adds exactly where glibc's x86-64 FMA build has
+// them (the ifunc variant every FMA-capable host selects; the non-FMA variant gives the same float in all
+// ~1.4e9 cases compared).  tests/test_device_math_host.py compiles this header for the HOST and compares with
+// the system libm; tests/test_gpu_primitives.py does the same on the device.
+//
+// The functions are __host__ __device__ so the identical source is what both tests exercise.
+//
+// Compile with -fmad=false: plain a*b+c below must NOT be contracted; every fused operation is an explicit
+// fma().
+#ifndef AVIF_DEVICE_MATH_CUH
+#define AVIF_DEVICE_MATH_CUH
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "libm_tables.inc"
+
+#if defined(__CUDACC__)
+#define AVIF_HD __host__ __device__ __forceinline__
+#else
+#define AVIF_HD inline
+#endif
+
+namespace avifmath
+{
+
+#if defined(__CUDACC__)
+// Device copies live in constant memory and are staged into shared memory by the kernels that index them with
+// a per-lane (divergent) index; see StageLibmTables below.
+__device__ __constant__ const uint64_t kExp2fTableConst[32] = { AVIF_LIBM_EXP2F_TABLE };
+__device__ __constant__ const double kPowfLog2TableConst[32] = { AVIF_LIBM_POWF_LOG2_TABLE };
+__device__ __constant__ const double kLogfTableConst[32] = { AVIF_LIBM_LOGF_TABLE };
+#endif
+
+static const uint64_t kExp2fTableHost[32] = { AVIF_LIBM_EXP2F_TABLE };
+static const double kPowfLog2TableHost[32] = { AVIF_LIBM_POWF_LOG2_TABLE };
+static const double kLogfTableHost[32] = { AVIF_LIBM_LOGF_TABLE };
+
+// Where the three 256-byte tables are read from.  Kernels pass pointers to shared-memory copies (a divergent
+// index into __constant__ memory serialises; shared memory does not); host code passes the static arrays.
+struct LibmTables
+{
+    const uint64_t* exp2f;   // 32 entries
+    const double* powfLog2;  // 16 x { invc, log2 c }
+    const double* logf;      // 16 x { invc, ln c }
+};
+
+inline LibmTables HostLibmTables()
+{
+    LibmTables t;
+    t.exp2f = kExp2fTableHost;
+    t.powfLog2 = kPowfLog2TableHost;
+    t.logf = kLogfTableHost;
+    return t;
+}
+
+#if defined(__CUDACC__)
+// Cooperative copy of the tables into shared memory: `storage` must hold 96 eight-byte words.
+__device__ __forceinline__ LibmTables StageLibmTables(uint64_t* storage, int threadIndex, int threadCount)
+{
+    for (int i = threadIndex; i < 96; i += threadCount)
+    {
+        uint64_t word;
+        if (i < 32)
+        {
+            word = kExp2fTableConst[i];
+        }
+        else if (i < 64)
+        {
+            word = static_cast<uint64_t>(__double_as_longlong(kPowfLog2TableConst[i - 32]));
+        }
+        else
+        {
+            word = static_cast<uint64_t>(__double_as_longlong(kLogfTableConst[i - 64]));
+        }
+        storage[i] = word;
+    }
+    LibmTables t;
+    t.exp2f = storage;
+    t.powfLog2 = reinterpret_cast<const double*>(storage + 32);
+    t.logf = reinterpret_cast<const double*>(storage + 64);
+    return t;
+}
+#endif
+
+AVIF_HD uint32_t AsUint(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, sizeof(u));
+    return u;
+#endif
+}
+
+AVIF_HD float AsFloat(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, sizeof(f));
+    return f;
+#endif
+}
+
+AVIF_HD uint64_t AsUint64(double f)
+{
+#if defined(__CUDA_ARCH__)
+    return static_cast<uint64_t>(__double_as_longlong(f));
+#else
+    uint64_t u;
+    memcpy(&u, &f, sizeof(u));
+    return u;
+#endif
+}
+
+AVIF_HD double AsDouble(uint64_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(static_cast<long long>(u));
+#else
+    double f;
+    memcpy(&f, &u, sizeof(f));
+    return f;
+#endif
+}
+
+// binary32 -> binary64 for a positive NORMAL float given as bits, with integer ops only (the conversion
+// instruction runs on the quarter-rate pipe; this is exact for normal inputs: rebias the exponent by
+// 1023 - 127 = 896 and widen the fraction by 29 zero bits).
+AVIF_HD double NormalFloatBitsToDouble(uint32_t bits)
+{
+#if defined(__CUDA_ARCH__)
+    const uint32_t hi = (bits >> 3) + 0x38000000u;
+    const uint32_t lo = bits << 29;
+    return __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
+#else
+    return static_cast<double>(AsFloat(bits));
+#endif
+}
+
+// (double)k for an int32 k without the integer->double conversion instruction (quarter-rate pipe).
+AVIF_HD double SmallIntToDouble(int32_t k)
+{
+#if defined(__CUDA_ARCH__)
+    // bits(2^52) | (k + 2^31) has the value 2^52 + 2^31 + k exactly.
+    return __hiloint2double(0x43300000, k ^ static_cast<int32_t>(0x80000000u)) - 0x1.000008p+52;
+#else
+    return static_cast<double>(k);
+#endif
+}
+
+// ---- exp2 core shared by powf (glibc e_powf.c exp2_inline) ------------------------------------------------
+
+// 2^xd rounded once to binary32, for |xd| < 126 (callers check).  sign_bias is 0 on every path this library
+// takes (no negative bases), so it is omitted.
+AVIF_HD float Exp2Inline(double xd, const LibmTables& t)
+{
+    const double C[3] = AVIF_LIBM_EXP2F_POLY;
+    // x = k/N + r with r in [-1/(2N), 1/(2N)], N = 32
+    double kd = xd + AVIF_LIBM_EXP2F_SHIFT_SCALED;
+    const uint64_t ki = AsUint64(kd);
+    kd -= AVIF_LIBM_EXP2F_SHIFT_SCALED;
+    const double r = xd - kd;
+    // exp2(x) = 2^(k/N) * 2^r ~= s * (C0*r^3 + C1*r^2 + C2*r + 1)
+    uint64_t bits = t.exp2f[ki % 32];
+    bits += ki << (52 - 5);
+    const double s = AsDouble(bits);
+    const double z = fma(C[0], r, C[1]);
+    const double r2 = r * r;
+    double y = fma(C[2], r, 1.0);
+    y = fma(z, r2, y);
+    y = y * s;
+    return static_cast<float>(y);
+}
+
+// log2 of the positive normal float whose bits are ix (glibc e_powf.c log2_inline), in binary64.
+AVIF_HD double Log2Inline(uint32_t ix, const LibmTables& t)
+{
+    const double A[5] = AVIF_LIBM_POWF_LOG2_POLY;
+    // x = 2^k z; z in [OFF, 2*OFF) with OFF = 0x3f330000; 16 sub-intervals
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = static_cast<int>((tmp >> (23 - 4)) % 16);
+    const uint32_t top = tmp & 0xff800000u;
+    const uint32_t iz = ix - top;
+    const int32_t k = static_cast<int32_t>(top) >> 23; // arithmetic shift
+    const double invc = t.powfLog2[2 * i];
+    const double logc = t.powfLog2[2 * i + 1];
+    const double z = NormalFloatBitsToDouble(iz);
+
+    // log2(x) = log1p(z/c-1)/ln2 + log2(c) + k
+    const double r = fma(z, invc, -1.0);
+    const double y0 = logc + SmallIntToDouble(k);
+
+    const double r2 = r * r;
+    double y = fma(A[0], r, A[1]);
+    const double p = fma(A[2], r, A[3]);
+    const double r4 = r2 * r2;
+    double q = fma(A[4], r, y0);
+    q = fma(p, r2, q);
+    y = fma(y, r4, q);
+    return y;
+}
+
+// Returns 2 if the float with bits iy is an even integer, 1 if odd, 0 if not an integer (glibc checkint).
+AVIF_HD int CheckInt(uint32_t iy)
+{
+    const int e = static_cast<int>((iy >> 23) & 0xff);
+    if (e < 0x7f)
+    {
+        return 0;
+    }
+    if (e > 0x7f + 23)
+    {
+        return 2;
+    }
+    if (iy & ((1u << (0x7f + 23 - e)) - 1))
+    {
+        return 0;
+    }
+    if (iy & (1u << (0x7f + 23 - e)))
+    {
+        return 1;
+    }
+    return 2;
+}
+
+AVIF_HD bool ZeroInfNan(uint32_t ix) { return 2 * ix - 1 >= 2u * 0x7f800000u - 1; }
+
+AVIF_HD bool IsSignaling(uint32_t ix) { return 2 * (ix ^ 0x00400000u) > 2u * 0x7fc00000u; }
+
+// powf(x, y) as glibc computes it (sysdeps/ieee754/flt-32/e_powf.c), errno / exception flags aside.
+AVIF_HD float Powf(float x, float y, const LibmTables& t)
+{
+    uint32_t signBias = 0;
+    uint32_t ix = AsUint(x);
+    const uint32_t iy = AsUint(y);
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u || ZeroInfNan(iy))
+    {
+        // Either (x < 0x1p-126 or inf or nan) or (y is 0 or inf or nan).
+        if (ZeroInfNan(iy))
+        {
+            if (2 * iy == 0)
+            {
+                return IsSignaling(ix) ? x + y : 1.0f;
+            }
+            if (ix == 0x3f800000u)
+            {
+                return IsSignaling(iy) ? x + y : 1.0f;
+            }
+            if (2 * ix > 2u * 0x7f800000u || 2 * iy > 2u * 0x7f800000u)
+            {
+                return x + y;
+            }
+            if (2 * ix == 2 * 0x3f800000u)
+            {
+                return 1.0f;
+            }
+            if ((2 * ix < 2 * 0x3f800000u) == !(iy & 0x80000000u))
+            {
+                return 0.0f; // |x|<1 && y==inf or |x|>1 && y==-inf
+            }
+            return y * y;
+        }
+        if (ZeroInfNan(ix))
+        {
+            float x2 = x * x;
+            if ((ix & 0x80000000u) && CheckInt(iy) == 1)
+            {
+                x2 = -x2;
+            }
+            return (iy & 0x80000000u) ? 1 / x2 : x2;
+        }
+        // x and y are non-zero finite.
+        if (ix & 0x80000000u)
+        {
+            // Finite x < 0.
+            const int yint = CheckInt(iy);
+            if (yint == 0)
+            {
+                return AsFloat(0x7fc00000u); // invalid: NaN
+            }
+            if (yint == 1)
+            {
+                signBias = 1;
+            }
+            ix &= 0x7fffffffu;
+        }
+        if (ix < 0x00800000u)
+        {
+            // Normalize subnormal x so exponent becomes negative.
+            ix = AsUint(AsFloat(ix) * 0x1p23f);
+            ix &= 0x7fffffffu;
+            ix -= 23u << 23;
+        }
+    }
+    const double logx = Log2Inline(ix, t);
+    const double ylogx = static_cast<double>(y) * logx; // cannot overflow, y is single precision
+    if (((AsUint64(ylogx) >> 47) & 0xffff) >= (AsUint64(126.0) >> 47))
+    {
+        // |y*log(x)| >= 126.
+        if (ylogx > 0x1.fffffffd1d571p+6)
+        {
+            const float inf = AsFloat(0x7f800000u);
+            return signBias ? -inf : inf;
+        }
+        if (ylogx <= -150.0)
+        {
+            return signBias ? -0.0f : 0.0f;
+        }
+    }
+    const float result = Exp2Inline(ylogx, t);
+    return signBias ? -result : result;
+}
+
+// expf(x) as glibc computes it (sysdeps/ieee754/flt-32/e_expf.c).
+AVIF_HD float Expf(float x, const LibmTables& t)
+{
+    const double C[3] = AVIF_LIBM_EXP2F_POLY_SCALED;
+    const uint32_t abstop = (AsUint(x) >> 20) & 0x7ff;
+    if (abstop >= (0x42b00000u >> 20)) // |x| >= 88 or x is nan
+    {
+        if (AsUint(x) == 0xff800000u)
+        {
+            return 0.0f;
+        }
+        if (abstop >= (0x7f800000u >> 20))
+        {
+            return x + x;
+        }
+        if (x > 0x1.62e42ep6f)
+        {
+            return AsFloat(0x7f800000u);
+        }
+        if (x < -0x1.9fe368p6f)
+        {
+            return 0.0f;
+        }
+    }
+    const double xd = static_cast<double>(x);
+    // x*N/Ln2 = k + r with r in [-1/2, 1/2] and int k.
+    const double z = AVIF_LIBM_EXP2F_INVLN2_SCALED * xd;
+    double kd = z + AVIF_LIBM_EXP2F_SHIFT;
+    const uint64_t ki = AsUint64(kd);
+    kd -= AVIF_LIBM_EXP2F_SHIFT;
+    const double r = z - kd;
+    // exp(x) = 2^(k/N) * 2^(r/N) ~= s * (C0*r^3 + C1*r^2 + C2*r + 1)
+    uint64_t bits = t.exp2f[ki % 32];
+    bits += ki << (52 - 5);
+    const double s = AsDouble(bits);
+    const double zz = fma(C[0], r, C[1]);
+    const double r2 = r * r;
+    double y = fma(C[2], r, 1.0);
+    y = fma(zz, r2, y);
+    y = y * s;
+    return static_cast<float>(y);
+}
+
+// logf(x) as glibc computes it (sysdeps/ieee754/flt-32/e_logf.c).
+AVIF_HD float Logf(float x, const LibmTables& t)
+{
+    const double A[3] = AVIF_LIBM_LOGF_POLY;
+    uint32_t ix = AsUint(x);
+    if (ix == 0x3f800000u)
+    {
+        return 0.0f;
+    }
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u)
+    {
+        // x < 0x1p-126 or inf or nan.
+        if (ix * 2 == 0)
+        {
+            return AsFloat(0xff800000u); // -inf
+        }
+        if (ix == 0x7f800000u)
+        {
+            return x;
+        }
+        if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u)
+        {
+            return AsFloat(0x7fc00000u);
+        }
+        // x is subnormal, normalize it.
+        ix = AsUint(x * 0x1p23f);
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = static_cast<int>((tmp >> (23 - 4)) % 16);
+    const int32_t k = static_cast<int32_t>(tmp) >> 23; // arithmetic shift
+    const uint32_t iz = ix - (tmp & (0x1ffu << 23));
+    const double invc = t.logf[2 * i];
+    const double logc = t.logf[2 * i + 1];
+    const double z = NormalFloatBitsToDouble(iz);
+
+    // log(x) = log1p(z/c-1) + log(c) + k*Ln2
+    const double r = fma(z, invc, -1.0);
+    const double y0 = fma(SmallIntToDouble(k), AVIF_LIBM_LOGF_LN2, logc);
+
+    const double r2 = r * r;
+    double y = fma(A[1], r, A[2]);
+    y = fma(A[0], r2, y);
+    y = fma(y, r2, y0 + r);
+    return static_cast<float>(y);
+}
+
+} // namespace avifmath
+
+#endif // AVIF_DEVICE_MATH_CUH

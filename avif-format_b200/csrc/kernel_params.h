@@ -1,0 +1,75 @@
+// kernel_params.h -- plain parameter blocks handed to the CUDA kernels (device pointers, block-relative).
+//
+// "Block" = the row block [y0, y0 + rows) one launch converts.  All pointers already point at the first row of
+// the block in their buffer (for sub-sampled chroma planes: at chroma row y0 >> ys), so kernels index rows from
+// zero and never see y0 -- except `yPhase`, the parity of y0 for 4:2:0 decode, where an odd first row shares its
+// chroma row with the row above it (ReadHeifImage.cpp:359 uvJ = y >> yChromaShift).
+#ifndef AVIF_KERNEL_PARAMS_H
+#define AVIF_KERNEL_PARAMS_H
+
+#include <stdint.h>
+
+#include "pixel_math.cuh"
+
+namespace avifgpu
+{
+
+struct EncodeParams
+{
+    const void* rows;      // interleaved host pixels (formatRecord->data layout), device memory
+    int64_t rowStride;     // bytes
+    void* plane[4];        // REFERENCE layout: [0] interleaved or Y, [3] alpha (gray); PLANAR: Y, Cb, Cr, A
+    int64_t planeStride[4];
+    int32_t width;
+    int32_t rowCount;      // rows in this block
+    int32_t channels;      // 1..4
+    int32_t hasAlpha;
+    int32_t premultiply;
+    int32_t imageDepth;    // 8, 10, 12
+    uint32_t maxCode;
+    float maxCodeFloat;
+    int32_t transfer;      // avifgpu_transfer (float hosts)
+    float pqMultiplier;    // peak / 10000.0f
+    int32_t gray16Smpte428;
+    int32_t planar;        // AVIFGPU_LAYOUT_PLANAR_YCBCR
+    int32_t xs, ys;        // chroma shifts
+    int32_t topLeft;       // AVIFGPU_DOWN_FILTER_TOP_LEFT
+    avifpix::ForwardMatrix matrix;
+    float chromaOffset;
+};
+
+struct DecodeParams
+{
+    const void* plane[4];  // YCbCr: Y, Cb, Cr, A; mono: Y, -, -, A; planar RGB: R, G, B, A
+    int64_t planeStride[4];
+    void* rows;            // interleaved host pixels, device memory
+    int64_t rowStride;
+    int32_t width;
+    int32_t rowCount;
+    int32_t yPhase;        // y0 & ys
+    int32_t colorspace;    // avifgpu_colorspace
+    int32_t xs, ys;
+    int32_t hasAlpha;
+    int32_t premultiplied;
+    int32_t bitDepth;
+    uint32_t maxCode;
+    avifpix::RangeParams range;
+    avifpix::InverseMatrix matrix;
+    int32_t hostDepth;     // 8, 16, 32
+    int32_t transfer;      // avifgpu_transfer (host depth 32)
+    float pqMultiplier;    // 10000.0f / peak
+    int32_t applyOotf;
+    float lumaR, lumaG, lumaB;
+    float gammaMinusOne;
+    float hlgPeak;
+};
+
+// Launchers implemented in kernels_*.cu.  They only enqueue work on `stream` and return the number of kernels
+// launched (>= 1) or a negative avifgpu_status.
+int LaunchEncode(const EncodeParams& params, int hostDepth, void* stream);
+int LaunchDecode(const DecodeParams& params, void* stream);
+int LaunchTransfer(int function, float param, const float* in, float* out, size_t count, void* stream);
+
+} // namespace avifgpu
+
+#endif

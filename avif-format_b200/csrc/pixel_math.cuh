@@ -1,0 +1,317 @@
+// pixel_math.cuh -- the per-pixel arithmetic of the avif-format colour path, as __host__ __device__ functions.
+//
+// Each function states the reference lines whose arithmetic it reproduces (paths relative to the reference's
+// src/common/).  The float expressions are written in the reference's association and must be compiled
+// without contraction (nvcc -fmad=false; g++ -ffp-contract=off for the host-side checks): integer outputs are
+// trunc(0.5f + c * max) or trunc(clamp(c * max)) of a float chain, so a single fused multiply-add flips codes.
+// Division and square root are IEEE (nvcc default -prec-div=true -prec-sqrt=true), denormals are kept
+// (-ftz=false).  libm calls go through device_math.cuh (glibc-identical powf / expf / logf).
+#ifndef AVIF_PIXEL_MATH_CUH
+#define AVIF_PIXEL_MATH_CUH
+
+#include "device_math.cuh"
+
+namespace avifpix
+{
+
+using avifmath::LibmTables;
+
+// std::min(a, b) and std::clamp(v, lo, hi) exactly as the reference uses them (NaN behaviour included).
+AVIF_HD float MinF(float a, float b) { return (b < a) ? b : a; }
+AVIF_HD float MaxF(float a, float b) { return (a < b) ? b : a; }
+AVIF_HD float ClampF(float v, float lo, float hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); }
+
+// ---- transfer functions: ColorTransfer.cpp ----------------------------------------------------------------
+
+struct PqConstants
+{
+    // ColorTransfer.cpp:73-77 / 100-104 (constexpr float arithmetic, evaluated here by the host compiler in
+    // binary32 exactly as MSVC / gcc evaluate the reference's constexpr initialisers).
+    static constexpr float m1 = 2610.0f / 16384.0f;
+    static constexpr float m2 = 2523.0f / 4096.0f * 128.0f;
+    static constexpr float c1 = 3424.0f / 4096.0f;
+    static constexpr float c2 = 2413.0f / 4096.0f * 32.0f;
+    static constexpr float c3 = 2392.0f / 4096.0f * 32.0f;
+    static constexpr float inv_m2 = 1.0f / m2;
+    static constexpr float inv_m1 = 1.0f / m1;
+};
+
+// ColorTransfer.cpp:69-92.  luminanceMultiplier = imageMaxLuminanceLevel / 10000.0f (float division, hoisted:
+// it does not depend on the pixel).
+AVIF_HD float LinearToPQ(float value, float luminanceMultiplier, const LibmTables& t)
+{
+    if (value < 0.0f)
+    {
+        return 0.0f;
+    }
+    const float x = avifmath::Powf(value * luminanceMultiplier, PqConstants::m1, t);
+    const float pq = avifmath::Powf((PqConstants::c1 + PqConstants::c2 * x) / (1.0f + PqConstants::c3 * x), PqConstants::m2, t);
+    return pq;
+}
+
+// ColorTransfer.cpp:94-117.  luminanceMultiplier = 10000.0f / imageMaxLuminanceLevel.
+AVIF_HD float PQToLinear(float value, float luminanceMultiplier, const LibmTables& t)
+{
+    if (value < 0.0f)
+    {
+        return 0.0f;
+    }
+    const float x = avifmath::Powf(value, PqConstants::inv_m2, t);
+    const float normalizedLinear =
+        avifmath::Powf(MaxF(x - PqConstants::c1, 0.0f) / (PqConstants::c2 - PqConstants::c3 * x), PqConstants::inv_m1, t);
+    return normalizedLinear * luminanceMultiplier;
+}
+
+// ColorTransfer.cpp:119-127
+AVIF_HD float LinearToSMPTE428(float value, const LibmTables& t)
+{
+    if (value < 0.0f)
+    {
+        return 0.0f;
+    }
+    return avifmath::Powf(value * 48.0f / 52.37f, 1.0f / 2.6f, t);
+}
+
+// ColorTransfer.cpp:129-139
+AVIF_HD float SMPTE428ToLinear(float value, const LibmTables& t)
+{
+    if (value < 0.0f)
+    {
+        return 0.0f;
+    }
+    return avifmath::Powf(value, 2.6f, t) * (52.37f / 48.0f);
+}
+
+// ColorTransfer.cpp:141-164 (no caller in the reference; provided for the HLG-save extension)
+AVIF_HD float LinearToHLG(float value, const LibmTables& t)
+{
+    constexpr float a = 0.17883277f;
+    constexpr float b = 0.28466892f;
+    constexpr float c = 0.55991073f;
+    if (value < 0.0f)
+    {
+        return 0.0f;
+    }
+    if (value > (1.0f / 12.0f))
+    {
+        value = a * avifmath::Logf(value * 12.0f - b, t) + c;
+    }
+    else
+    {
+        value = sqrtf(value * 3.0f);
+    }
+    return value;
+}
+
+// ColorTransfer.cpp:166-190
+AVIF_HD float HLGToLinear(float value, const LibmTables& t)
+{
+    constexpr float a = 0.17883277f;
+    constexpr float b = 0.28466892f;
+    constexpr float c = 0.55991073f;
+    if (value < 0.0f)
+    {
+        return 0.0f;
+    }
+    if (value > 0.5f)
+    {
+        value = (avifmath::Expf((value - c) / a, t) + b) / 12.0f;
+    }
+    else
+    {
+        value = (value * value) * (1.0f / 3.0f);
+    }
+    return value;
+}
+
+// ColorTransfer.cpp:192-205.  gammaMinusOne = displayGamma - 1.0f (float subtraction, hoisted).
+AVIF_HD void ApplyHLGOOTF(float& r, float& g, float& b, float lumaR, float lumaG, float lumaB, float gammaMinusOne,
+                          float nominalPeakBrightness, const LibmTables& t)
+{
+    const float luma = (r * lumaR) + (g * lumaG) + (b * lumaB);
+    const float factor = nominalPeakBrightness * avifmath::Powf(luma, gammaMinusOne, t);
+    r *= factor;
+    g *= factor;
+    b *= factor;
+}
+
+// ---- alpha: PremultipliedAlpha.cpp ------------------------------------------------------------------------
+
+// PremultipliedAlpha.cpp:49-52
+AVIF_HD float PremultiplyColor(float color, float alpha, float maxValue) { return color * alpha / maxValue; }
+
+// PremultipliedAlpha.cpp:54-70 (uint8 and uint16 overloads share this body; maxValue 255 or 2^depth-1)
+AVIF_HD uint32_t PremultiplyCode(uint32_t color, uint32_t alpha, float maxValueFloat)
+{
+    const float value = PremultiplyColor(static_cast<float>(color), static_cast<float>(alpha), maxValueFloat);
+    return static_cast<uint32_t>(MinF(roundf(value), maxValueFloat));
+}
+
+// PremultipliedAlpha.cpp:72-75
+AVIF_HD float UnpremultiplyColor(float color, float alpha, float maxValue) { return MinF(color * maxValue / alpha, maxValue); }
+
+// PremultipliedAlpha.cpp:77-93
+AVIF_HD uint32_t UnpremultiplyCode(uint32_t color, uint32_t alpha, float maxValueFloat)
+{
+    const float value = UnpremultiplyColor(static_cast<float>(color), static_cast<float>(alpha), maxValueFloat);
+    return static_cast<uint32_t>(MinF(roundf(value), maxValueFloat));
+}
+
+// The caller-side guard every integer premultiply site wraps around PremultiplyColor
+// (WriteHeifImage.cpp:238-251, 404-417, 700-718, 760-778, 877-895, 947-965).
+AVIF_HD uint32_t PremultiplyCodeGuarded(uint32_t color, uint32_t alpha, uint32_t maxValue)
+{
+    if (alpha < maxValue)
+    {
+        if (alpha == 0)
+        {
+            return 0;
+        }
+        return PremultiplyCode(color, alpha, static_cast<float>(maxValue));
+    }
+    return color;
+}
+
+// ---- encode side: WriteHeifImage.cpp ----------------------------------------------------------------------
+
+// WriteHeifImage.cpp:87-166: lut[i] = clamp((int)((i / fromMax) * toMax + 0.5f), 0, toMax) evaluated directly
+// (fromMax = 255.0f or 32768.0f).  For 16-bit hosts a sample above 32768 would index past the reference's
+// table (undefined there); the same formula is DEFINED to apply, the clamp then yields toMax.
+AVIF_HD uint32_t DepthLutEntry(uint32_t i, float fromMax, uint32_t toMax)
+{
+    int value = static_cast<int>(((static_cast<float>(i) / fromMax) * static_cast<float>(toMax)) + 0.5f);
+    if (value < 0)
+    {
+        value = 0;
+    }
+    else if (value > static_cast<int>(toMax))
+    {
+        value = static_cast<int>(toMax);
+    }
+    return static_cast<uint32_t>(value);
+}
+
+// WriteHeifImage.cpp:590, 618, 1093-1096, 1128-1130: static_cast<uint16_t>(std::clamp(v * max, 0.0f, max)).
+// NaN survives std::clamp and the cast is undefined in the reference (0 on x86); DEFINED here as 0.
+AVIF_HD uint32_t FloatToCode(float v, float maxValue)
+{
+    const float scaled = ClampF(v * maxValue, 0.0f, maxValue);
+    if (scaled != scaled)
+    {
+        return 0;
+    }
+    return static_cast<uint32_t>(scaled);
+}
+
+// Forward matrix, this project's definition of the stage the reference leaves to libheif (DESIGN.md "Forward
+// matrix"): the algebraic inverse of YuvDecode.cpp:555-557 on integer
+// codes, full range.
+struct ForwardMatrix
+{
+    float kr, kg, kb;
+    float cbDivisor; // 2*(1-kb)
+    float crDivisor; // 2*(1-kr)
+    int identity;    // matrix_coefficients == 0 (GBR)
+};
+
+AVIF_HD void ForwardPixel(const ForwardMatrix& m, uint32_t rc, uint32_t gc, uint32_t bc, float& y, float& cb, float& cr)
+{
+    const float r = static_cast<float>(rc);
+    const float g = static_cast<float>(gc);
+    const float b = static_cast<float>(bc);
+    if (m.identity)
+    {
+        y = g;
+        cb = b;
+        cr = r;
+        return;
+    }
+    y = ((m.kr * r) + (m.kg * g)) + (m.kb * b);
+    cb = (b - y) / m.cbDivisor;
+    cr = (r - y) / m.crDivisor;
+}
+
+AVIF_HD uint32_t QuantiseLuma(float y, int maxCode)
+{
+    int v = static_cast<int>(y + 0.5f);
+    v = (v < 0) ? 0 : ((v > maxCode) ? maxCode : v);
+    return static_cast<uint32_t>(v);
+}
+
+// chromaOffset = (float)(1 << (depth-1)), or 0 for the identity matrix.
+AVIF_HD uint32_t QuantiseChroma(float c, float chromaOffset, int maxCode)
+{
+    int v = static_cast<int>((c + chromaOffset) + 0.5f);
+    v = (v < 0) ? 0 : ((v > maxCode) ? maxCode : v);
+    return static_cast<uint32_t>(v);
+}
+
+// ---- decode side: YuvLookupTables.cpp / YuvDecode.cpp -----------------------------------------------------
+
+// YuvLookupTables.cpp:64-66 with the reference's int arithmetic (the 16-bit case overflows int there; both the
+// oracle (-fwrapv) and this code use two's-complement wrap-around so they agree).
+AVIF_HD int LimitedToFull(int v, int lo, int hi, int full)
+{
+    const uint32_t product = static_cast<uint32_t>(v - lo) * static_cast<uint32_t>(full) + static_cast<uint32_t>((hi - lo) / 2);
+    v = static_cast<int32_t>(product) / (hi - lo);
+    return (v > full) ? full : ((v < 0) ? 0 : v);
+}
+
+struct RangeParams
+{
+    int fullRange;
+    int yLo, yHi;   // limited-range luma foot / head   (YuvLookupTables.cpp:72-83)
+    int uvLo, uvHi; // limited-range chroma foot / head (YuvLookupTables.cpp:93-104)
+    int maxChannel; // (1 << depth) - 1
+    float maxChannelFloat;
+    int identityMatrix;
+};
+
+// unormFloatTableY[i], YuvLookupTables.cpp:157-171
+AVIF_HD float UnormToFloatY(uint32_t code, const RangeParams& p)
+{
+    int v = static_cast<int>(code);
+    if (!p.fullRange)
+    {
+        v = LimitedToFull(v, p.yLo, p.yHi, p.maxChannel);
+    }
+    return static_cast<float>(v) / p.maxChannelFloat;
+}
+
+// unormFloatTableUV[i], YuvLookupTables.cpp:173-184
+AVIF_HD float UnormToFloatUV(uint32_t code, const RangeParams& p)
+{
+    if (p.identityMatrix)
+    {
+        return UnormToFloatY(code, p);
+    }
+    int v = static_cast<int>(code);
+    if (!p.fullRange)
+    {
+        v = LimitedToFull(v, p.uvLo, p.uvHi, p.maxChannel);
+    }
+    return static_cast<float>(v) / p.maxChannelFloat - 0.5f;
+}
+
+// unormFloatTableAlpha[i], YuvLookupTables.cpp:186-189; also BuildUnormToFloatLookupTable, ReadHeifImage.cpp:402-415
+AVIF_HD float UnormToFloatPlain(uint32_t code, float maxChannelFloat) { return static_cast<float>(code) / maxChannelFloat; }
+
+struct InverseMatrix
+{
+    float kr, kg, kb;
+};
+
+// YuvDecode.cpp:306-312 (the same three lines appear in all six colour row decoders).
+AVIF_HD void YuvToRgb(const InverseMatrix& m, float Y, float Cb, float Cr, float& R, float& G, float& B)
+{
+    R = Y + (2 * (1 - m.kr)) * Cr;
+    B = Y + (2 * (1 - m.kb)) * Cb;
+    G = Y - ((2 * ((m.kr * (1 - m.kr) * Cr) + (m.kb * (1 - m.kb) * Cb))) / m.kg);
+    R = ClampF(R, 0.0f, 1.0f);
+    G = ClampF(G, 0.0f, 1.0f);
+    B = ClampF(B, 0.0f, 1.0f);
+}
+
+} // namespace avifpix
+
+#endif // AVIF_PIXEL_MATH_CUH

@@ -1038,21 +1038,63 @@ int avif_oracle_encode_image(const avifgpu_encode_desc* desc, const void* host_r
     return avif_oracle_encode_image_mt(desc, host_rows, row_stride, dst, 1);
 }
 
-int avif_oracle_rgb_codes_to_ycbcr(const avifgpu_encode_desc* desc, const void* interleaved, int64_t interleaved_stride,
-                                   const avifgpu_planes* dst)
+typedef struct codes_job
 {
     encode_job job;
+    const void* interleaved;
+    int64_t interleaved_stride;
+} codes_job;
+
+static void* codes_thread(void* arg)
+{
+    codes_job* c = (codes_job*)arg;
+    c->job.status = encode_rows_planar_ycbcr(&c->job, c->interleaved, c->interleaved_stride);
+    return NULL;
+}
+
+int avif_oracle_rgb_codes_to_ycbcr_mt(const avifgpu_encode_desc* desc, const void* interleaved, int64_t interleaved_stride,
+                                      const avifgpu_planes* dst, int32_t threads)
+{
+    int bounds[AVIF_ORACLE_MAX_THREADS + 2];
+    codes_job jobs[AVIF_ORACLE_MAX_THREADS];
+    pthread_t handles[AVIF_ORACLE_MAX_THREADS];
+    int blocks, i;
     const int status = validate_encode_desc(desc);
     if (status != AVIFGPU_OK) return status;
     if (desc->layout != AVIFGPU_LAYOUT_PLANAR_YCBCR) return fail(AVIFGPU_ERR_BAD_PARAM, "layout must be planar YCbCr");
-    job.desc = desc;
-    job.rows = NULL;
-    job.row_stride = 0;
-    job.dst = *dst;
-    job.y_begin = 0;
-    job.y_end = desc->height;
-    job.status = AVIFGPU_OK;
-    return encode_rows_planar_ycbcr(&job, interleaved, interleaved_stride);
+    if (threads < 1) threads = 1;
+    if (threads > AVIF_ORACLE_MAX_THREADS) threads = AVIF_ORACLE_MAX_THREADS;
+    blocks = split_rows(desc->height, threads, bounds);
+    for (i = 0; i < blocks; ++i)
+    {
+        jobs[i].job.desc = desc;
+        jobs[i].job.rows = NULL;
+        jobs[i].job.row_stride = 0;
+        jobs[i].job.dst = *dst;
+        jobs[i].job.y_begin = bounds[i];
+        jobs[i].job.y_end = bounds[i + 1];
+        jobs[i].job.status = AVIFGPU_OK;
+        jobs[i].interleaved = interleaved;
+        jobs[i].interleaved_stride = interleaved_stride;
+    }
+    if (blocks == 1)
+    {
+        codes_thread(&jobs[0]);
+        return jobs[0].job.status;
+    }
+    for (i = 0; i < blocks; ++i) pthread_create(&handles[i], NULL, codes_thread, &jobs[i]);
+    for (i = 0; i < blocks; ++i) pthread_join(handles[i], NULL);
+    for (i = 0; i < blocks; ++i)
+    {
+        if (jobs[i].job.status != AVIFGPU_OK) return jobs[i].job.status;
+    }
+    return AVIFGPU_OK;
+}
+
+int avif_oracle_rgb_codes_to_ycbcr(const avifgpu_encode_desc* desc, const void* interleaved, int64_t interleaved_stride,
+                                   const avifgpu_planes* dst)
+{
+    return avif_oracle_rgb_codes_to_ycbcr_mt(desc, interleaved, interleaved_stride, dst, 1);
 }
 
 /* ---------------------------------------------------------------------------------------------------- */

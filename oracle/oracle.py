@@ -71,7 +71,7 @@ class CpuChecker:
         f("decode_image_mt", C.c_int, [C.POINTER(abi.DecodeDesc), C.POINTER(abi.Planes), C.c_void_p, C.c_int64, C.c_int32])
         if prefix == "avif_oracle_":
             f("build_depth_lut", C.c_int, [C.c_int32, C.c_int32, C.c_void_p])
-            f("rgb_codes_to_ycbcr", C.c_int, [C.POINTER(abi.EncodeDesc), C.c_void_p, C.c_int64, C.POINTER(abi.Planes)])
+            f("rgb_codes_to_ycbcr_mt", C.c_int, [C.POINTER(abi.EncodeDesc), C.c_void_p, C.c_int64, C.POINTER(abi.Planes), C.c_int32])
 
     def _fn(self, name, restype, argtypes):
         fn = getattr(self.lib, self.prefix + name)
@@ -133,12 +133,13 @@ class CpuChecker:
         return out
 
     # ---- images -----------------------------------------------------------------------------------------
-    def encode(self, desc, rows, threads=1, pad=0):
+    def encode(self, desc, rows, threads=1, pad=0, planes=None):
         """rows: (H, W*channels) host array.  Returns the list of 4 plane arrays (None where absent)."""
         rows = np.ascontiguousarray(rows)
         assert rows.dtype == abi.host_dtype(desc.host_depth)
         assert rows.shape == (desc.height, desc.width * desc.host_channels), rows.shape
-        planes = alloc_planes(abi.encode_plane_shapes(desc), abi.code_dtype(desc.image_bit_depth), pad)
+        if planes is None:
+            planes = alloc_planes(abi.encode_plane_shapes(desc), abi.code_dtype(desc.image_bit_depth), pad)
         p = abi.planes_from_arrays(planes)
         status = self._encode_image_mt(C.byref(desc), rows.ctypes.data, rows.strides[0] if rows.size else 0,
                                        C.byref(p), threads)
@@ -155,11 +156,13 @@ class CpuChecker:
         self._check(status)
         return rows
 
-    def rgb_codes_to_ycbcr(self, desc, interleaved, pad=0):
+    def rgb_codes_to_ycbcr(self, desc, interleaved, pad=0, threads=1, planes=None):
         interleaved = np.ascontiguousarray(interleaved)
-        planes = alloc_planes(abi.encode_plane_shapes(desc), abi.code_dtype(desc.image_bit_depth), pad)
+        if planes is None:
+            planes = alloc_planes(abi.encode_plane_shapes(desc), abi.code_dtype(desc.image_bit_depth), pad)
         p = abi.planes_from_arrays(planes)
-        self._check(self._rgb_codes_to_ycbcr(C.byref(desc), interleaved.ctypes.data, interleaved.strides[0], C.byref(p)))
+        self._check(self._rgb_codes_to_ycbcr_mt(C.byref(desc), interleaved.ctypes.data, interleaved.strides[0], C.byref(p),
+                                                threads))
         return planes
 
 
