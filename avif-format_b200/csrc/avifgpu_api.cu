@@ -3,6 +3,7 @@
 // converts pixels launches a CUDA kernel or fails.
 #include "../../include/avifgpu.h"
 
+#include "curve_tables.h"
 #include "host_params.h"
 #include "kernel_params.h"
 
@@ -77,6 +78,48 @@ struct avifgpu_context
     Buffer pinnedRows[kPipelineStreams];
     Buffer pinnedPlanes[kPipelineStreams][AVIFGPU_MAX_PLANES];
     Buffer transferScratch[2];
+    std::vector<CurveTable*> curveTables; // exact step tables, built on first use per (curve, param, depth)
+
+    // The verified step table for a float-host encode description, or nullptr when the description does not use
+    // one / the table could not be verified (then the generic exact kernel serves the configuration).
+    CurveTable* CurveTableFor(const avifgpu_encode_desc& d)
+    {
+        if (d.host_depth != 32 || d.layout != AVIFGPU_LAYOUT_PLANAR_YCBCR || d.image_bit_depth > 12)
+        {
+            return nullptr;
+        }
+        int curve;
+        int param = 0;
+        if (d.transfer == AVIFGPU_TRANSFER_PQ)
+        {
+            curve = kCurveLinearToPQ;
+            param = d.pq_peak_nits;
+        }
+        else if (d.transfer == AVIFGPU_TRANSFER_SMPTE428)
+        {
+            curve = kCurveLinearToSMPTE428;
+        }
+        else
+        {
+            return nullptr;
+        }
+        for (CurveTable* t : curveTables)
+        {
+            if (t->curve == curve && t->param == param && t->depth == d.image_bit_depth)
+            {
+                return t;
+            }
+        }
+        CurveTable* t = new (std::nothrow) CurveTable();
+        if (t == nullptr)
+        {
+            return nullptr;
+        }
+        BuildCurveTable(curve, param, d.image_bit_depth, streams[0], t);
+        launches += t->stats.sweptInputs ? 2 : 0;
+        curveTables.push_back(t);
+        return t;
+    }
 
     int Fail(int status, const std::string& message)
     {
@@ -296,6 +339,11 @@ AVIFGPU_EXPORT void avifgpu_destroy(avifgpu_context* ctx)
     {
         if (b.ptr) cudaFree(b.ptr);
     }
+    for (CurveTable* t : ctx->curveTables)
+    {
+        FreeCurveTable(t);
+        delete t;
+    }
     delete ctx;
 }
 
@@ -467,6 +515,11 @@ AVIFGPU_EXPORT int avifgpu_encode_rows_device(avifgpu_context* ctx, const avifgp
         p.planeStride[k] = device_dst->stride[k];
     }
     DeviceGuard guard(ctx->device);
+    p.smCount = ctx->smCount;
+    if (CurveTable* table = ctx->CurveTableFor(*desc))
+    {
+        p.curveTable = table->valid ? &table->view : nullptr;
+    }
     const int launched = LaunchEncode(p, desc->host_depth, cuda_stream);
     if (launched < 0)
     {
@@ -587,6 +640,11 @@ AVIFGPU_EXPORT int avifgpu_encode_rows(avifgpu_context* ctx, const avifgpu_encod
     }
 
     DeviceGuard guard(ctx->device);
+    base.smCount = ctx->smCount;
+    if (CurveTable* table = ctx->CurveTableFor(*desc))
+    {
+        base.curveTable = table->valid ? &table->view : nullptr;
+    }
     const int64_t rowPayload = static_cast<int64_t>(desc->width) * EncodeHostColBytes(*desc);
     const int64_t deviceRowStride = (rowPayload + 255) & ~255ll;
     const bool rowsPinned = IsPinned(host_rows);
@@ -825,6 +883,46 @@ AVIFGPU_EXPORT int avifgpu_decode_rows(avifgpu_context* ctx, const avifgpu_decod
     {
         if ((status = drain(i)) != AVIFGPU_OK) return status;
         if ((status = ctx->Cuda(cudaStreamSynchronize(ctx->streams[i]), "cudaStreamSynchronize")) != AVIFGPU_OK) return status;
+    }
+    return AVIFGPU_OK;
+}
+
+// ---- preparation ------------------------------------------------------------------------------------------------
+
+AVIFGPU_EXPORT int avifgpu_prepare_encode(avifgpu_context* ctx, const avifgpu_encode_desc* desc, avifgpu_curve_stats* out_stats)
+{
+    if (ctx == nullptr)
+    {
+        return AVIFGPU_ERR_BAD_PARAM;
+    }
+    std::string error;
+    const int status = ValidateEncodeDesc(desc, &error);
+    if (status != AVIFGPU_OK)
+    {
+        return ctx->Fail(status, error);
+    }
+    DeviceGuard guard(ctx->device);
+    CurveTable* table = ctx->CurveTableFor(*desc);
+    if (out_stats != nullptr)
+    {
+        std::memset(out_stats, 0, sizeof(*out_stats));
+        if (table != nullptr)
+        {
+            out_stats->applicable = 1;
+            out_stats->valid = table->valid ? 1 : 0;
+            out_stats->steps = table->stats.steps;
+            out_stats->bands = table->stats.bands;
+            out_stats->widest_band_ulps = table->stats.widestBand;
+            out_stats->bucket_count = table->view.bucketCount;
+            out_stats->swept_inputs = table->stats.sweptInputs;
+            out_stats->in_band_inputs = table->stats.inBandInputs;
+            out_stats->verify_mismatches = table->stats.verifyMismatches;
+            out_stats->build_ms = table->stats.buildMilliseconds;
+        }
+    }
+    if (table != nullptr && !table->valid)
+    {
+        ctx->lastError = "step table not used (generic exact kernel serves this configuration): " + table->error;
     }
     return AVIFGPU_OK;
 }

@@ -1,0 +1,55 @@
+// curve_lookup.cuh -- device-side use of a CurveTable (see curve_tables.h): the exact curve evaluation and the
+// two-level table look-up, shared by the table verifier and the conversion kernels.
+#ifndef AVIF_CURVE_LOOKUP_CUH
+#define AVIF_CURVE_LOOKUP_CUH
+
+#include "curve_tables.h"
+#include "pixel_math.cuh"
+
+namespace avifgpu
+{
+
+// The exact quantised curve: WriteHeifImage.cpp:1079-1096 for one sample.
+template <int CURVE>
+__device__ __forceinline__ uint32_t ExactCurveCode(float x, float pqMultiplier, float maxCodeFloat, const avifmath::LibmTables& t)
+{
+    float curved;
+    if (CURVE == kCurveLinearToPQ)
+    {
+        curved = avifpix::LinearToPQ(x, pqMultiplier, t);
+    }
+    else
+    {
+        curved = avifpix::LinearToSMPTE428(x, t);
+    }
+    return avifpix::FloatToCode(curved, maxCodeFloat);
+}
+
+// Table look-up for the float with bit pattern `bits`.  Returns the code that is correct whenever `inBand` is
+// false; when `inBand` is true the caller must evaluate ExactCurveCode instead.
+// Negative floats (sign bit set; includes -0 and negative NaNs) map to code 0 like the reference: value < 0
+// returns 0, and -0 / NaN quantise to 0.
+__device__ __forceinline__ uint32_t LookupCurveCode(uint32_t bits, const uint2* __restrict__ octaves,
+                                                    const uint32_t* __restrict__ buckets, bool& inBand)
+{
+    if (bits & 0x80000000u)
+    {
+        inBand = false;
+        return 0;
+    }
+    const uint2 oct = octaves[bits >> 23];
+    const uint32_t shift = oct.y & 0xffu;
+    const uint32_t reduce = (oct.y >> 8) & 0xffu;
+    const uint32_t widthQ = oct.y >> 16;
+    const uint32_t mantissa = bits & 0x7fffffu;
+    const uint32_t word = buckets[oct.x + (mantissa >> shift)];
+    const uint32_t offsetQ = (mantissa & ((1u << shift) - 1u)) >> reduce;
+    const uint32_t stepOffset = word & ((1u << kBucketOffsetBits) - 1u);
+    const uint32_t distance = offsetQ - stepOffset; // wraps to a huge value below the step
+    inBand = distance <= widthQ;
+    return (word >> kBucketOffsetBits) + (offsetQ >= stepOffset ? 1u : 0u);
+}
+
+} // namespace avifgpu
+
+#endif

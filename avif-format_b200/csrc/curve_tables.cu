@@ -1,0 +1,377 @@
+// curve_tables.cu -- builds and verifies the exact float -> code tables described in curve_tables.h.
+#include "curve_tables.h"
+#include "curve_lookup.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <vector>
+
+namespace avifgpu
+{
+
+namespace
+{
+
+constexpr int kSweepThreads = 256;
+constexpr uint32_t kRunLength = 128;               // consecutive floats per thread
+constexpr uint32_t kSweepEnd = 0x7f800000u;        // every non-negative finite float: bits [0, +inf)
+constexpr int kMinShift = 6;                       // smallest bucket: 64 floats
+
+// Pass 1: per code, the smallest and largest input bits that produce it.
+template <int CURVE>
+__global__ void __launch_bounds__(kSweepThreads) SweepKernel(float pqMultiplier, float maxCodeFloat, uint32_t* __restrict__ minBits,
+                                                            uint32_t* __restrict__ maxBits)
+{
+    __shared__ uint64_t libmStorage[96];
+    const avifmath::LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
+    __syncthreads();
+
+    const uint64_t runs = kSweepEnd / kRunLength;
+    for (uint64_t run = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; run < runs;
+         run += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    {
+        const uint32_t begin = static_cast<uint32_t>(run * kRunLength);
+        uint32_t current = ExactCurveCode<CURVE>(__uint_as_float(begin), pqMultiplier, maxCodeFloat, t);
+        uint32_t first = begin;
+        for (uint32_t i = 1; i < kRunLength; ++i)
+        {
+            const uint32_t bits = begin + i;
+            const uint32_t code = ExactCurveCode<CURVE>(__uint_as_float(bits), pqMultiplier, maxCodeFloat, t);
+            if (code != current)
+            {
+                atomicMin(&minBits[current], first);
+                atomicMax(&maxBits[current], bits - 1);
+                current = code;
+                first = bits;
+            }
+        }
+        atomicMin(&minBits[current], first);
+        atomicMax(&maxBits[current], begin + kRunLength - 1);
+    }
+}
+
+// Pass 2: every input again, table against exact.  counters[0] = mismatches outside bands, [1] = inputs in bands.
+template <int CURVE>
+__global__ void __launch_bounds__(kSweepThreads) VerifyKernel(float pqMultiplier, float maxCodeFloat, CurveTableView table,
+                                                             unsigned long long* __restrict__ counters)
+{
+    __shared__ uint64_t libmStorage[96];
+    const avifmath::LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
+    __syncthreads();
+
+    unsigned long long mismatches = 0;
+    unsigned long long inBandCount = 0;
+    // +inf and the positive NaNs are part of the check (bits up to 0x7fffffff): they must come out as code 0.
+    const uint64_t total = 0x80000000ull;
+    for (uint64_t u = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; u < total;
+         u += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    {
+        const uint32_t bits = static_cast<uint32_t>(u);
+        bool inBand;
+        const uint32_t fast = LookupCurveCode(bits, table.octaves, table.buckets, inBand);
+        if (inBand)
+        {
+            ++inBandCount;
+        }
+        else if (fast != ExactCurveCode<CURVE>(__uint_as_float(bits), pqMultiplier, maxCodeFloat, t))
+        {
+            ++mismatches;
+        }
+    }
+    for (int offset = 16; offset > 0; offset >>= 1)
+    {
+        mismatches += __shfl_down_sync(0xffffffffu, mismatches, offset);
+        inBandCount += __shfl_down_sync(0xffffffffu, inBandCount, offset);
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (mismatches) atomicAdd(&counters[0], mismatches);
+        if (inBandCount) atomicAdd(&counters[1], inBandCount);
+    }
+}
+
+struct Step
+{
+    uint32_t first; // min{bits : code >= k}
+    uint32_t end;   // max(first, max{bits : code < k})
+    uint32_t k;
+};
+
+bool Check(cudaError_t e, const char* what, std::string* error)
+{
+    if (e == cudaSuccess)
+    {
+        return true;
+    }
+    *error = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+
+} // namespace
+
+void FreeCurveTable(CurveTable* table)
+{
+    if (table->deviceOctaves) cudaFree(table->deviceOctaves);
+    if (table->deviceBuckets) cudaFree(table->deviceBuckets);
+    table->deviceOctaves = nullptr;
+    table->deviceBuckets = nullptr;
+    table->valid = false;
+}
+
+bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveTable* table)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
+    table->curve = curve;
+    table->param = param;
+    table->depth = depth;
+    table->valid = false;
+    table->error.clear();
+
+    const uint32_t maxCode = (1u << depth) - 1u;
+    const float maxCodeFloat = static_cast<float>(maxCode);
+    const float pqMultiplier = static_cast<float>(param) / 10000.0f; // ColorTransfer.cpp:86
+    const size_t codeCount = static_cast<size_t>(maxCode) + 1;
+
+    int device = 0;
+    cudaDeviceProp prop{};
+    if (!Check(cudaGetDevice(&device), "cudaGetDevice", &table->error) ||
+        !Check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties", &table->error))
+    {
+        return false;
+    }
+    const int grid = prop.multiProcessorCount * 8;
+
+    // ---- pass 1: sweep ----------------------------------------------------------------------------------------
+    uint32_t* dMin = nullptr;
+    uint32_t* dMax = nullptr;
+    if (!Check(cudaMalloc(&dMin, codeCount * sizeof(uint32_t)), "cudaMalloc", &table->error) ||
+        !Check(cudaMalloc(&dMax, codeCount * sizeof(uint32_t)), "cudaMalloc", &table->error))
+    {
+        cudaFree(dMin);
+        return false;
+    }
+    cudaMemsetAsync(dMin, 0xff, codeCount * sizeof(uint32_t), stream);
+    cudaMemsetAsync(dMax, 0x00, codeCount * sizeof(uint32_t), stream);
+    if (curve == kCurveLinearToPQ)
+    {
+        SweepKernel<kCurveLinearToPQ><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, dMin, dMax);
+    }
+    else
+    {
+        SweepKernel<kCurveLinearToSMPTE428><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, dMin, dMax);
+    }
+    std::vector<uint32_t> minBits(codeCount), maxBits(codeCount);
+    bool ok = Check(cudaMemcpyAsync(minBits.data(), dMin, codeCount * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "D2H", &table->error) &&
+              Check(cudaMemcpyAsync(maxBits.data(), dMax, codeCount * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "D2H", &table->error) &&
+              Check(cudaStreamSynchronize(stream), "curve sweep", &table->error);
+    cudaFree(dMin);
+    cudaFree(dMax);
+    if (!ok)
+    {
+        return false;
+    }
+    table->stats.sweptInputs = kSweepEnd;
+
+    // ---- thresholds -------------------------------------------------------------------------------------------
+    // first_k = min over codes >= k of minBits (suffix minimum); last_k = max over codes < k of maxBits (prefix max).
+    std::vector<uint32_t> first(codeCount + 1, 0xffffffffu), last(codeCount + 1, 0u);
+    {
+        uint32_t running = 0xffffffffu;
+        for (size_t c = codeCount; c-- > 0;)
+        {
+            running = std::min(running, minBits[c]);
+            first[c] = running;
+        }
+        uint32_t high = 0;
+        bool any = false;
+        for (size_t k = 1; k <= codeCount; ++k)
+        {
+            if (minBits[k - 1] != 0xffffffffu)
+            {
+                high = any ? std::max(high, maxBits[k - 1]) : maxBits[k - 1];
+                any = true;
+            }
+            last[k] = high;
+        }
+    }
+    if (first[0] != 0)
+    {
+        table->error = "curve sweep: code of +0 is not the minimum";
+        return false;
+    }
+    std::vector<Step> steps;
+    for (uint32_t k = 1; k <= maxCode; ++k)
+    {
+        if (first[k] == 0xffffffffu)
+        {
+            break; // codes >= k are never produced
+        }
+        Step s;
+        s.k = k;
+        s.first = first[k];
+        s.end = std::max(first[k], last[k]);
+        if (!steps.empty() && s.first <= steps.back().end)
+        {
+            table->error = "curve sweep: fuzzy bands of neighbouring codes overlap";
+            return false;
+        }
+        if (last[k] >= first[k])
+        {
+            table->stats.bands++;
+            table->stats.widestBand = std::max(table->stats.widestBand, last[k] - first[k] + 1);
+        }
+        steps.push_back(s);
+    }
+    table->stats.steps = static_cast<int32_t>(steps.size());
+
+    // ---- two-level table --------------------------------------------------------------------------------------
+    std::vector<uint2> octaves(256);
+    std::vector<uint32_t> buckets;
+    size_t cursor = 0; // first step whose end is >= the current octave start
+    for (uint32_t e = 0; e < 256; ++e)
+    {
+        const uint64_t lo = static_cast<uint64_t>(e) << 23;
+        const uint64_t hi = lo + (1u << 23);
+        if (e == 255)
+        {
+            // +inf and NaN do not follow the step structure (LinearToPQ(inf) is NaN -> 0, LinearToSMPTE428(inf) is
+            // inf -> max, NaN -> 0): one bucket whose band covers every offset, so they all take the exact path.
+            octaves[e] = make_uint2(static_cast<uint32_t>(buckets.size()), 23u | (7u << 8) | (0xffffu << 16));
+            buckets.push_back(0u);
+            continue;
+        }
+        while (cursor < steps.size() && steps[cursor].end < lo)
+        {
+            ++cursor;
+        }
+        size_t stop = cursor;
+        while (stop < steps.size() && steps[stop].first < hi)
+        {
+            ++stop;
+        }
+        // steps[cursor, stop) touch this octave (their [first, end] intersects it)
+        int shift = 23;
+        for (; shift >= kMinShift; --shift)
+        {
+            bool separated = true;
+            for (size_t i = cursor; i + 1 < stop && separated; ++i)
+            {
+                const uint64_t endHere = std::min<uint64_t>(steps[i].end, hi - 1);
+                const uint64_t nextFirst = std::max<uint64_t>(steps[i + 1].first, lo);
+                separated = ((endHere - lo) >> shift) < ((nextFirst - lo) >> shift);
+            }
+            if (separated)
+            {
+                break;
+            }
+        }
+        if (shift < kMinShift)
+        {
+            table->error = "curve table: two steps closer than the smallest bucket";
+            return false;
+        }
+        const uint32_t reduce = shift > static_cast<int>(kOffsetResolutionBits) ? static_cast<uint32_t>(shift) - kOffsetResolutionBits : 0u;
+        uint32_t widest = 0;
+        for (size_t i = cursor; i < stop; ++i)
+        {
+            widest = std::max(widest, steps[i].end - steps[i].first);
+        }
+        const uint32_t widthQ = (widest >> reduce) + 2u;
+        if (widthQ > 0xffffu)
+        {
+            table->error = "curve table: band wider than the table format allows";
+            return false;
+        }
+        octaves[e] = make_uint2(static_cast<uint32_t>(buckets.size()), static_cast<uint32_t>(shift) | (reduce << 8) | (widthQ << 16));
+
+        const uint32_t bucketCount = 1u << (23 - shift);
+        size_t next = cursor; // first step with end >= bucket start
+        for (uint32_t b = 0; b < bucketCount; ++b)
+        {
+            const uint64_t bLo = lo + (static_cast<uint64_t>(b) << shift);
+            const uint64_t bHi = bLo + (1ull << shift);
+            while (next < stop && steps[next].end < bLo)
+            {
+                ++next;
+            }
+            uint32_t word;
+            if (next < stop && steps[next].first < bHi)
+            {
+                // this bucket meets step `next` (its start, its band, or the tail of its band)
+                const uint64_t start = std::max<uint64_t>(steps[next].first, bLo);
+                const uint32_t offsetQ = static_cast<uint32_t>((start - bLo) >> reduce);
+                word = ((steps[next].k - 1u) << kBucketOffsetBits) | offsetQ;
+            }
+            else
+            {
+                // no step here: the code is the number of steps below the bucket
+                const uint32_t code = static_cast<uint32_t>(next); // steps[0..next) all end below bLo
+                word = (code << kBucketOffsetBits) | kBucketOffsetNone;
+            }
+            buckets.push_back(word);
+        }
+    }
+    // Bucket words store k-1 in 12 bits: depth <= 12.
+    if (depth > 12)
+    {
+        table->error = "curve table: depth above 12 bits";
+        return false;
+    }
+
+    // ---- upload -----------------------------------------------------------------------------------------------
+    if (!Check(cudaMalloc(&table->deviceOctaves, octaves.size() * sizeof(uint2)), "cudaMalloc", &table->error) ||
+        !Check(cudaMalloc(&table->deviceBuckets, buckets.size() * sizeof(uint32_t)), "cudaMalloc", &table->error))
+    {
+        FreeCurveTable(table);
+        return false;
+    }
+    table->view.octaves = static_cast<const uint2*>(table->deviceOctaves);
+    table->view.buckets = static_cast<const uint32_t*>(table->deviceBuckets);
+    table->view.bucketCount = static_cast<int32_t>(buckets.size());
+    unsigned long long* dCounters = nullptr;
+    ok = Check(cudaMemcpyAsync(table->deviceOctaves, octaves.data(), octaves.size() * sizeof(uint2), cudaMemcpyHostToDevice, stream), "H2D", &table->error) &&
+         Check(cudaMemcpyAsync(table->deviceBuckets, buckets.data(), buckets.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "H2D", &table->error) &&
+         Check(cudaMalloc(&dCounters, 2 * sizeof(unsigned long long)), "cudaMalloc", &table->error);
+    if (!ok)
+    {
+        FreeCurveTable(table);
+        return false;
+    }
+
+    // ---- pass 2: verify every input ---------------------------------------------------------------------------
+    cudaMemsetAsync(dCounters, 0, 2 * sizeof(unsigned long long), stream);
+    if (curve == kCurveLinearToPQ)
+    {
+        VerifyKernel<kCurveLinearToPQ><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, table->view, dCounters);
+    }
+    else
+    {
+        VerifyKernel<kCurveLinearToSMPTE428><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, table->view, dCounters);
+    }
+    unsigned long long counters[2] = { 0, 0 };
+    ok = Check(cudaMemcpyAsync(counters, dCounters, sizeof(counters), cudaMemcpyDeviceToHost, stream), "D2H", &table->error) &&
+         Check(cudaStreamSynchronize(stream), "curve verify", &table->error);
+    cudaFree(dCounters);
+    if (!ok)
+    {
+        FreeCurveTable(table);
+        return false;
+    }
+    table->stats.verifyMismatches = counters[0];
+    table->stats.inBandInputs = counters[1];
+    table->stats.buildMilliseconds = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (counters[0] != 0)
+    {
+        table->error = "curve table: verification found inputs where the table disagrees with the exact curve";
+        FreeCurveTable(table);
+        return false;
+    }
+    table->valid = true;
+    return true;
+}
+
+} // namespace avifgpu

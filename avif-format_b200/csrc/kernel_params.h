@@ -9,6 +9,7 @@
 
 #include <stdint.h>
 
+#include "curve_tables.h"
 #include "pixel_math.cuh"
 
 namespace avifgpu
@@ -36,6 +37,9 @@ struct EncodeParams
     int32_t topLeft;       // AVIFGPU_DOWN_FILTER_TOP_LEFT
     avifpix::ForwardMatrix matrix;
     float chromaOffset;
+    // Host-side extras for the launcher (ignored by the kernels):
+    const CurveTableView* curveTable; // verified exact step table for `transfer`, or nullptr
+    int32_t smCount;
 };
 
 struct DecodeParams

@@ -69,6 +69,7 @@ def library():
     sig("avifgpu_decode_rows_device", C.c_int,
         [ctx_p, C.POINTER(abi.DecodeDesc), C.POINTER(abi.Planes), C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p])
     sig("avifgpu_transfer_f32", C.c_int, [ctx_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t])
+    sig("avifgpu_prepare_encode", C.c_int, [ctx_p, C.POINTER(abi.EncodeDesc), C.POINTER(abi.CurveStats)])
     _lib = lib
     return lib
 
@@ -79,7 +80,7 @@ EXPORTED_SYMBOLS = [
     "avifgpu_encode_host_col_bytes", "avifgpu_decode_host_col_bytes", "avifgpu_encode_plane_geometry",
     "avifgpu_decode_plane_geometry", "avifgpu_get_yuv_coefficients", "avifgpu_get_hlg_luma_coefficients",
     "avifgpu_build_yuv_tables", "avifgpu_encode_rows", "avifgpu_decode_rows", "avifgpu_encode_rows_device",
-    "avifgpu_decode_rows_device", "avifgpu_transfer_f32",
+    "avifgpu_decode_rows_device", "avifgpu_transfer_f32", "avifgpu_prepare_encode",
 ]
 
 
@@ -172,7 +173,8 @@ class Context:
     def encode(self, desc, rows, y0=0, nrows=None, planes=None, pad=0):
         """rows: 2-D host array holding rows [y0, y0+nrows).  Returns the 4 whole-image planes (None where absent)."""
         nrows = desc.height - y0 if nrows is None else nrows
-        assert rows.dtype == abi.host_dtype(desc.host_depth) and rows.ndim == 2 and rows.strides[1] == rows.itemsize
+        assert rows.dtype == abi.host_dtype(desc.host_depth) and rows.ndim == 2
+        assert rows.size == 0 or rows.strides[1] == rows.itemsize
         if planes is None:
             planes = alloc_planes(abi.encode_plane_shapes(desc), abi.code_dtype(desc.image_bit_depth), pad)
         p = abi.planes_from_arrays(planes)
@@ -189,6 +191,12 @@ class Context:
         self._check(self.lib.avifgpu_decode_rows(self.handle, C.byref(desc), C.byref(p), y0, nrows, out.ctypes.data,
                                                  out.strides[0]))
         return out
+
+    def prepare_encode(self, desc):
+        """Builds the device tables `desc` needs and returns their statistics (abi.CurveStats)."""
+        stats = abi.CurveStats()
+        self._check(self.lib.avifgpu_prepare_encode(self.handle, C.byref(desc), C.byref(stats)))
+        return stats
 
     def transfer(self, function, values, param=0.0):
         values = np.ascontiguousarray(values, dtype=np.float32)

@@ -150,6 +150,24 @@ class DecodeDesc(C.Structure):
         return out
 
 
+class CurveStats(C.Structure):
+    _fields_ = [
+        ("applicable", C.c_int32),
+        ("valid", C.c_int32),
+        ("steps", C.c_int32),
+        ("bands", C.c_int32),
+        ("widest_band_ulps", C.c_uint32),
+        ("bucket_count", C.c_int32),
+        ("swept_inputs", C.c_uint64),
+        ("in_band_inputs", C.c_uint64),
+        ("verify_mismatches", C.c_uint64),
+        ("build_ms", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
 # ---- geometry (mirrors avifgpu_*_plane_geometry / *_host_col_bytes) ---------------------------------------
 
 def host_dtype(host_depth):

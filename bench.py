@@ -130,49 +130,73 @@ class Workload:
 # ---- helpers ----------------------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md 'clocks line')."""
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md 'clocks line'), polled through NVML
+    from a thread (nvidia-smi -lms cannot resolve a region of a few milliseconds); nvidia-smi is the fallback."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index = index
-        self.lines = []
-        self.proc = None
+        self.samples = []
+        self.running = False
+        self.nvml = None
+        self.thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            physical = self.index
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    physical = int(ids[self.index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(physical)
+            self.nvml = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+            return
+        self.running = True
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+    def _poll(self):
+        n = self.nvml
+        while self.running:
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    reasons = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((time.perf_counter(), mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            return float(out[0]), float(out[1])
+        except Exception:
+            return None, None
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.06] or [ln for (_, ln) in self.lines[-3:]]
-        sm, smax, reasons = [], [], set()
-        for ln in inside:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                smax.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, flag in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nvml is None:
+            sm, smax = self._smi_once()
+            return {"sm_mhz": sm, "sm_max_mhz": smax, "reasons": ["nvml unavailable: one nvidia-smi sample taken after the timed region"], "samples": 0}
+        self.running = False
+        self.thread.join(timeout=1.0)
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        if not inside:
+            inside = self.samples[-1:]
+        mask = 0
+        for s in inside:
+            mask |= s[2]
+        return {"sm_mhz": statistics.median([s[1] for s in inside]) if inside else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [name for name, bit in self.REASONS if mask & bit], "samples": len(inside)}
 
 
 def measured_peak():
@@ -340,7 +364,6 @@ def run_b200(args, workload, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.15)
     events = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     launches_before = gpu.launch_count()
     barrier()

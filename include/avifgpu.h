@@ -269,6 +269,30 @@ AVIFGPU_EXPORT int avifgpu_decode_rows_device(avifgpu_context* ctx, const avifgp
                                               void* device_rows, int64_t row_stride_bytes,
                                               void* cuda_stream);
 
+/* ---- preparation (optional) --------------------------------------------------------------------------- */
+
+/* Statistics of the exact float->code step table behind a float-host encode configuration
+ * (avif-format_b200/csrc/curve_tables.h).  The table is derived on the device from the exact curve by sweeping
+ * every non-negative float, and verified against it the same way, the first time a configuration is used. */
+typedef struct avifgpu_curve_stats
+{
+    int32_t applicable;          /* 1 if this description uses a step table (float host, PQ or SMPTE 428) */
+    int32_t valid;               /* 1 if the table was built and verified; 0 -> the exact generic kernel is used */
+    int32_t steps;               /* thresholds found */
+    int32_t bands;               /* thresholds with a non-empty fuzzy (non-monotone) band */
+    uint32_t widest_band_ulps;
+    int32_t bucket_count;
+    uint64_t swept_inputs;       /* floats evaluated by the sweep */
+    uint64_t in_band_inputs;     /* floats the kernel hands to the exact path */
+    uint64_t verify_mismatches;  /* must be 0 for valid == 1 */
+    double build_ms;
+} avifgpu_curve_stats;
+
+/* Builds whatever device-side tables `desc` needs so that the first avifgpu_encode_rows* call does not pay for
+ * it (the *_device entry points otherwise build them synchronously on first use).  out_stats may be NULL. */
+AVIFGPU_EXPORT int avifgpu_prepare_encode(avifgpu_context* ctx, const avifgpu_encode_desc* desc,
+                                          avifgpu_curve_stats* out_stats);
+
 /* ---- primitive-level entry points (parity gates G2/G5; not on the plug-in's call path) -------------- */
 
 typedef enum avifgpu_function

@@ -1,0 +1,120 @@
+"""The tuned float-host encode kernel (kernels_fast.cu) and its exact step tables (curve_tables.cu) on a B200:
+table self-verification over every float, inputs aimed at the step thresholds and fuzzy bands, queue overflow,
+edge strips, strides -- all bit-exact against the CPU checker."""
+import numpy as np
+import pytest
+
+import cases
+from avifgpu import abi
+
+pytestmark = pytest.mark.gpu
+
+
+def planar_desc(w, h, depth=12, transfer=abi.TRANSFER_PQ, peak=80, chroma=abi.CHROMA_420, down=abi.DOWN_FILTER_BOX, nclx=None):
+    return abi.EncodeDesc(w, h, 32, 3, abi.ALPHA_NONE, depth, transfer, peak, abi.LAYOUT_PLANAR_YCBCR, chroma, down, abi.GRAY16_LUT,
+                          nclx if nclx is not None else cases.NCLX_2020_PQ())
+
+
+@pytest.mark.parametrize("transfer,peak,depth", [(abi.TRANSFER_PQ, 80, 12), (abi.TRANSFER_PQ, 80, 10), (abi.TRANSFER_PQ, 1000, 12),
+                                                 (abi.TRANSFER_PQ, 10000, 12), (abi.TRANSFER_PQ, 1, 10), (abi.TRANSFER_SMPTE428, 80, 12),
+                                                 (abi.TRANSFER_SMPTE428, 80, 10)])
+def test_step_tables_verify_against_every_float(gpu, transfer, peak, depth):
+    stats = gpu.prepare_encode(planar_desc(8, 8, depth, transfer, peak)).as_dict()
+    print(stats)
+    assert stats["applicable"] == 1 and stats["valid"] == 1, stats
+    assert stats["verify_mismatches"] == 0
+    assert stats["swept_inputs"] == 0x7f800000
+    assert stats["steps"] == (1 << depth) - 1
+    if transfer == abi.TRANSFER_SMPTE428:
+        assert stats["bands"] == 0  # a single powf is monotone: SURVEY.md 7.3
+    assert stats["in_band_inputs"] < 0.02 * stats["swept_inputs"]
+
+
+def threshold_inputs(port, transfer, peak, depth, rng, count_codes=400, window=2600, per_code=48):
+    """Floats around the step thresholds of the quantised curve, located by bisection on the CPU checker."""
+    fn = abi.FN_LINEAR_TO_PQ if transfer == abi.TRANSFER_PQ else abi.FN_LINEAR_TO_SMPTE428
+    maxv = np.float32((1 << depth) - 1)
+
+    def codes(x):
+        v = port.transfer(fn, x, float(peak)) * maxv
+        v = np.where(v < 0, np.float32(0), np.where(v > maxv, maxv, v))
+        return np.nan_to_num(v, nan=0.0).astype(np.uint32)
+
+    ks = np.unique(np.concatenate([rng.integers(1, 1 << depth, count_codes), [1, 2, (1 << depth) - 2, (1 << depth) - 1]]))
+    lo = np.zeros(ks.size, np.uint32)
+    hi = np.full(ks.size, np.float32(3.0e38).view(np.uint32), np.uint32)
+    for _ in range(33):
+        mid = ((lo.astype(np.uint64) + hi.astype(np.uint64)) // 2).astype(np.uint32)
+        c = codes(mid.view(np.float32))
+        below = c < ks
+        lo = np.where(below, mid, lo)
+        hi = np.where(below, hi, mid)
+    offsets = rng.integers(-window, window + 1, (ks.size, per_code))
+    bits = (hi.astype(np.int64)[:, None] + offsets).clip(0, 0x7f7fffff).astype(np.uint32)
+    return bits.reshape(-1).view(np.float32)
+
+
+@pytest.mark.parametrize("transfer,peak,depth", [(abi.TRANSFER_PQ, 80, 12), (abi.TRANSFER_PQ, 1000, 10), (abi.TRANSFER_SMPTE428, 80, 12)])
+def test_inputs_at_the_thresholds(gpu, port, transfer, peak, depth):
+    rng = np.random.default_rng(depth * 1000 + peak)
+    values = threshold_inputs(port, transfer, peak, depth, rng)
+    w = 256
+    h = (values.size // (3 * w)) & ~1
+    rows = np.ascontiguousarray(values[:h * w * 3].reshape(h, w * 3))
+    for chroma in (abi.CHROMA_420, abi.CHROMA_444):
+        desc = planar_desc(w, h, depth, transfer, peak, chroma)
+        assert cases.same_planes(port.encode(desc, rows, threads=8), gpu.encode(desc, rows))
+
+
+def test_all_samples_in_a_band_overflow_the_queue(gpu, port):
+    """A flat image whose value sits inside a fuzzy band sends every sample down the exact path (768 per warp tile,
+    queue capacity 128): the flush-and-continue logic must still give the exact result."""
+    rng = np.random.default_rng(7)
+    near = threshold_inputs(port, abi.TRANSFER_PQ, 80, 12, rng, count_codes=8, window=300, per_code=8)
+    w, h = 512, 8
+    for value in near[:6]:
+        rows = np.full((h, w * 3), value, np.float32)
+        rows[::2, ::7] = np.nextafter(value, np.float32(2.0))
+        desc = planar_desc(w, h)
+        assert cases.same_planes(port.encode(desc, rows), gpu.encode(desc, rows))
+
+
+SHAPES = [(4, 2), (5, 3), (7, 2), (128, 2), (129, 3), (130, 4), (131, 5), (257, 7), (1024, 33), (4, 1)]
+
+
+@pytest.mark.parametrize("w,h", SHAPES)
+@pytest.mark.parametrize("chroma", [abi.CHROMA_420, abi.CHROMA_422, abi.CHROMA_444])
+def test_edges_and_chroma_modes(gpu, port, w, h, chroma):
+    rng = cases.rng_for(f"fast_{w}x{h}_{chroma}")
+    rows = cases.float_host_rows(rng, h, w, 3, specials=True)
+    for transfer, depth, down, nclx in ((abi.TRANSFER_PQ, 12, abi.DOWN_FILTER_BOX, cases.NCLX_2020_PQ()),
+                                        (abi.TRANSFER_PQ, 10, abi.DOWN_FILTER_TOP_LEFT, None),
+                                        (abi.TRANSFER_SMPTE428, 12, abi.DOWN_FILTER_BOX, cases.NCLX_709()),
+                                        (abi.TRANSFER_CLIP, 10, abi.DOWN_FILTER_BOX, cases.NCLX_DERIVED())):
+        desc = planar_desc(w, h, depth, transfer, 80, chroma, down, nclx)
+        got = gpu.encode(desc, rows, pad=5)
+        assert cases.same_planes(port.encode(desc, rows), got), (transfer, depth, down)
+        for g in got:
+            if g is not None:
+                assert (g.base[:, g.shape[1]:] == 0xCDCD).all(), "wrote into the row padding"
+
+
+def test_unaligned_device_buffers_fall_back_correctly(gpu, port):
+    """Odd strides / offsets defeat the 128-bit loads: the launcher must route those calls to the generic kernel."""
+    import torch
+    import avifgpu
+    dev = torch.device("cuda", gpu.device)
+    w, h = 64, 6
+    desc = planar_desc(w, h)
+    rows = cases.float_host_rows(np.random.default_rng(11), h, w, 3)
+    expected = port.encode(desc, rows)
+    backing = torch.zeros((h, w * 3 + 1), dtype=torch.float32, device=dev)  # row stride not a multiple of 16 bytes
+    backing[:, :w * 3] = torch.from_numpy(rows).to(dev)
+    shapes = abi.encode_plane_shapes(desc)
+    planes = [None if s is None else torch.zeros((s[0], s[1] + 1), dtype=torch.int16, device=dev) for s in shapes]
+    views = [None if t is None else t[:, 1:] for t in planes]  # 2-byte aligned plane origins
+    gpu.encode_device(desc, backing.data_ptr(), backing.stride(0) * 4, avifgpu.planes_from_tensors(views))
+    torch.cuda.synchronize(dev)
+    for e, v in zip(expected, views):
+        if e is not None:
+            assert np.array_equal(v.cpu().numpy().view(np.uint16), e)
