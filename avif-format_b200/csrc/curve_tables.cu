@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(kSweepThreads) VerifyKernel(float pqMultiplier
 
     unsigned long long mismatches = 0;
     unsigned long long inBandCount = 0;
+    unsigned long long flatInBand = 0;
     // +inf and the positive NaNs are part of the check (bits up to 0x7fffffff): they must come out as code 0.
     const uint64_t total = 0x80000000ull;
     for (uint64_t u = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; u < total;
@@ -71,7 +72,21 @@ __global__ void __launch_bounds__(kSweepThreads) VerifyKernel(float pqMultiplier
     {
         const uint32_t bits = static_cast<uint32_t>(u);
         bool inBand;
-        const uint32_t fast = LookupCurveCode(bits, table.octaves, table.buckets, inBand);
+        uint32_t fast = LookupCurveCode(bits, table.octaves, table.buckets, inBand);
+        if (table.flat != nullptr)
+        {
+            // the flat variant must agree as well (its bands differ: count the union)
+            bool inBandFlat;
+            const uint32_t fastFlat = LookupCurveCodeFlat(bits, table.flat - table.flatLow, table.flatShift, static_cast<int32_t>(table.flatLow), static_cast<int32_t>(table.flatHigh), inBandFlat);
+            if (!inBandFlat && fastFlat != ExactCurveCode<CURVE>(__uint_as_float(bits), pqMultiplier, maxCodeFloat, t))
+            {
+                ++mismatches;
+            }
+            if (inBandFlat)
+            {
+                ++flatInBand;
+            }
+        }
         if (inBand)
         {
             ++inBandCount;
@@ -85,11 +100,13 @@ __global__ void __launch_bounds__(kSweepThreads) VerifyKernel(float pqMultiplier
     {
         mismatches += __shfl_down_sync(0xffffffffu, mismatches, offset);
         inBandCount += __shfl_down_sync(0xffffffffu, inBandCount, offset);
+        flatInBand += __shfl_down_sync(0xffffffffu, flatInBand, offset);
     }
     if ((threadIdx.x & 31) == 0)
     {
         if (mismatches) atomicAdd(&counters[0], mismatches);
         if (inBandCount) atomicAdd(&counters[1], inBandCount);
+        if (flatInBand) atomicAdd(&counters[2], flatInBand);
     }
 }
 
@@ -116,8 +133,10 @@ void FreeCurveTable(CurveTable* table)
 {
     if (table->deviceOctaves) cudaFree(table->deviceOctaves);
     if (table->deviceBuckets) cudaFree(table->deviceBuckets);
+    if (table->deviceFlat) cudaFree(table->deviceFlat);
     table->deviceOctaves = nullptr;
     table->deviceBuckets = nullptr;
+    table->deviceFlat = nullptr;
     table->valid = false;
 }
 
@@ -322,6 +341,65 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
         return false;
     }
 
+    // ---- flat variant ----------------------------------------------------------------------------------------
+    std::vector<uint2> flat;
+    uint32_t flatShift = 0, flatLow = 0, flatHigh = 0;
+    if (!steps.empty())
+    {
+        int shift = static_cast<int>(kFlatMaxShift);
+        for (; shift >= kMinShift; --shift)
+        {
+            bool separated = true;
+            for (size_t i = 0; i + 1 < steps.size() && separated; ++i)
+            {
+                separated = (steps[i].end >> shift) < (steps[i + 1].first >> shift);
+            }
+            if (separated)
+            {
+                break;
+            }
+        }
+        bool usable = shift >= kMinShift && (steps.front().first >> shift) >= 1;
+        if (usable)
+        {
+            flatShift = static_cast<uint32_t>(shift);
+            flatLow = (steps.front().first >> shift) - 1u;
+            flatHigh = (steps.back().end >> shift) + 1u;
+            const uint64_t count = static_cast<uint64_t>(flatHigh) - flatLow + 1u;
+            usable = count * sizeof(uint2) <= kFlatMaxBytes && (static_cast<uint64_t>(flatHigh + 1u) << shift) <= kSweepEnd;
+            if (usable)
+            {
+                flat.resize(count);
+                size_t next = 0;
+                for (uint64_t b = 0; b < count; ++b)
+                {
+                    const uint64_t bLo = (static_cast<uint64_t>(flatLow) + b) << shift;
+                    const uint64_t bHi = bLo + (1ull << shift);
+                    while (next < steps.size() && steps[next].end < bLo)
+                    {
+                        ++next;
+                    }
+                    if (next < steps.size() && steps[next].first < bHi)
+                    {
+                        // the bucket meets step `next`: its start, its band, or the tail of its band.  Samples in
+                        // [first, end] are in band when the step has a fuzzy band (end > first).
+                        const uint32_t bandWidth = steps[next].end > steps[next].first ? (steps[next].end - steps[next].first + 1u) : 0u;
+                        usable = usable && bandWidth < (1u << 20);
+                        flat[b] = make_uint2(steps[next].first, (steps[next].k << 20) | bandWidth);
+                    }
+                    else
+                    {
+                        flat[b] = make_uint2(0u, static_cast<uint32_t>(next) << 20); // no step: code = steps below
+                    }
+                }
+            }
+        }
+        if (!usable)
+        {
+            flat.clear();
+        }
+    }
+
     // ---- upload -----------------------------------------------------------------------------------------------
     if (!Check(cudaMalloc(&table->deviceOctaves, octaves.size() * sizeof(uint2)), "cudaMalloc", &table->error) ||
         !Check(cudaMalloc(&table->deviceBuckets, buckets.size() * sizeof(uint32_t)), "cudaMalloc", &table->error))
@@ -332,10 +410,26 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     table->view.octaves = static_cast<const uint2*>(table->deviceOctaves);
     table->view.buckets = static_cast<const uint32_t*>(table->deviceBuckets);
     table->view.bucketCount = static_cast<int32_t>(buckets.size());
+    table->view.flat = nullptr;
+    table->view.flatCount = 0;
+    if (!flat.empty())
+    {
+        if (!Check(cudaMalloc(&table->deviceFlat, flat.size() * sizeof(uint2)), "cudaMalloc", &table->error) ||
+            !Check(cudaMemcpyAsync(table->deviceFlat, flat.data(), flat.size() * sizeof(uint2), cudaMemcpyHostToDevice, stream), "H2D", &table->error))
+        {
+            FreeCurveTable(table);
+            return false;
+        }
+        table->view.flat = static_cast<const uint2*>(table->deviceFlat);
+        table->view.flatCount = static_cast<int32_t>(flat.size());
+        table->view.flatShift = flatShift;
+        table->view.flatLow = flatLow;
+        table->view.flatHigh = flatHigh;
+    }
     unsigned long long* dCounters = nullptr;
     ok = Check(cudaMemcpyAsync(table->deviceOctaves, octaves.data(), octaves.size() * sizeof(uint2), cudaMemcpyHostToDevice, stream), "H2D", &table->error) &&
          Check(cudaMemcpyAsync(table->deviceBuckets, buckets.data(), buckets.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "H2D", &table->error) &&
-         Check(cudaMalloc(&dCounters, 2 * sizeof(unsigned long long)), "cudaMalloc", &table->error);
+         Check(cudaMalloc(&dCounters, 3 * sizeof(unsigned long long)), "cudaMalloc", &table->error);
     if (!ok)
     {
         FreeCurveTable(table);
@@ -343,7 +437,7 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     }
 
     // ---- pass 2: verify every input ---------------------------------------------------------------------------
-    cudaMemsetAsync(dCounters, 0, 2 * sizeof(unsigned long long), stream);
+    cudaMemsetAsync(dCounters, 0, 3 * sizeof(unsigned long long), stream);
     if (curve == kCurveLinearToPQ)
     {
         VerifyKernel<kCurveLinearToPQ><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, table->view, dCounters);
@@ -352,7 +446,7 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     {
         VerifyKernel<kCurveLinearToSMPTE428><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, table->view, dCounters);
     }
-    unsigned long long counters[2] = { 0, 0 };
+    unsigned long long counters[3] = { 0, 0, 0 };
     ok = Check(cudaMemcpyAsync(counters, dCounters, sizeof(counters), cudaMemcpyDeviceToHost, stream), "D2H", &table->error) &&
          Check(cudaStreamSynchronize(stream), "curve verify", &table->error);
     cudaFree(dCounters);
@@ -363,6 +457,8 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     }
     table->stats.verifyMismatches = counters[0];
     table->stats.inBandInputs = counters[1];
+    table->stats.flatInBandInputs = counters[2];
+    table->stats.flatBuckets = table->view.flatCount;
     table->stats.buildMilliseconds = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (counters[0] != 0)
     {

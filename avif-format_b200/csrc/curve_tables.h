@@ -43,19 +43,36 @@ constexpr uint32_t kBucketOffsetBits = 20;          // low bits of a bucket word
 constexpr uint32_t kBucketOffsetNone = 1u << 19;    // "no step in this bucket": every offset compares below it
 constexpr uint32_t kOffsetResolutionBits = 19;      // offsets inside a bucket are kept to 19 bits
 
+// Flat (single-level) variant, used when one bucket size separates the steps of every binade and the table
+// still fits in shared memory (true for PQ): buckets of 2^flatShift floats covering bit patterns
+// [flatLow << flatShift, (flatHigh + 1) << flatShift); inputs outside are clamped to the end buckets, which
+// hold no step.  One 64-bit entry per bucket:
+//     .x = bit pattern of the step's band start (first_k), 0 when the bucket meets no step
+//     .y = kUpper << 20 | bandWidth   (bandWidth = number of in-band floats from first_k on, < 2^20)
+// code = kUpper - (bits < .x); the sample is in band iff 0 <= bits - .x < bandWidth.
+constexpr uint32_t kFlatMaxShift = 14;
+constexpr uint32_t kFlatMaxBytes = 132 * 1024;
+
 // Device-resident table (global memory; kernels stage it into shared memory).
 struct CurveTableView
 {
     const uint2* octaves;     // 256 entries: .x = first bucket index, .y = S | r << 8 | wq << 16
     const uint32_t* buckets;  // bucketCount words: (k-1) << 20 | offset
     int32_t bucketCount;
+    const uint2* flat;        // flatCount entries, or nullptr when the flat variant does not apply
+    int32_t flatCount;
+    uint32_t flatShift;
+    uint32_t flatLow;         // bucket number (bits >> flatShift) of flat[0]
+    uint32_t flatHigh;        // bucket number of flat[flatCount - 1]
 };
 
 struct CurveTableStats
 {
     double buildMilliseconds = 0.0;
     uint64_t sweptInputs = 0;
-    uint64_t inBandInputs = 0;     // inputs the kernel sends to the exact path
+    uint64_t inBandInputs = 0;     // inputs the kernel sends to the exact path (two-level table)
+    uint64_t flatInBandInputs = 0; // same for the flat variant (exact per-bucket band widths)
+    int32_t flatBuckets = 0;       // 0 when the flat variant does not apply
     uint64_t verifyMismatches = 0; // must be 0
     int32_t steps = 0;             // thresholds found
     int32_t bands = 0;             // thresholds with a non-empty fuzzy band
@@ -73,6 +90,7 @@ struct CurveTable
     std::string error;
     void* deviceOctaves = nullptr;
     void* deviceBuckets = nullptr;
+    void* deviceFlat = nullptr;
 };
 
 // Builds (sweeps, assembles, uploads, verifies) the table on the current device.  Synchronous; uses `stream`.

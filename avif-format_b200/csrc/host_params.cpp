@@ -345,8 +345,8 @@ void FillEncodeParams(const avifgpu_encode_desc& d, EncodeParams* p)
         p->matrix.kr = k[0];
         p->matrix.kg = k[1];
         p->matrix.kb = k[2];
-        p->matrix.cbDivisor = 2 * (1 - k[2]);
-        p->matrix.crDivisor = 2 * (1 - k[0]);
+        p->matrix.cbScale = 0.5f / (1.0f - k[2]);
+        p->matrix.crScale = 0.5f / (1.0f - k[0]);
         p->matrix.identity = (d.nclx.present && d.nclx.matrix_coefficients == 0) ? 1 : 0;
         p->chromaOffset = p->matrix.identity ? 0.0f : static_cast<float>(1 << (d.image_bit_depth - 1));
     }

@@ -27,12 +27,12 @@ using avifmath::LibmTables;
 namespace
 {
 
-constexpr int kFastThreads = 256;
-constexpr int kFastWarps = kFastThreads / 32;
-constexpr int kTilePixels = 128;    // per row
-constexpr int kValuesPerLane = 24;  // 2 rows x 4 pixels x 3 channels
-constexpr int kQueueCapacity = 128; // entries per warp between flushes
-constexpr int kCurveClip = 2;       // no transfer curve: code = trunc(clamp(v * max))
+constexpr int kTilePixels = 128;     // per row
+constexpr int kValuesPerLane = 24;   // 2 rows x 4 pixels x 3 channels
+constexpr int kLaneStrideWords = 28; // staging stride per lane (16-byte aligned, conflict-free for STS.128)
+constexpr int kCurveClip = 2;        // no transfer curve: code = trunc(clamp(v * max))
+constexpr int kTableTwoLevel = 0;
+constexpr int kTableFlat = 1;
 
 struct FastEncodeParams
 {
@@ -55,157 +55,184 @@ struct FastEncodeParams
     CurveTableView table;
 };
 
-struct QueueEntry
+// Shared-memory carve-up (bytes).
+constexpr int kSharedLibm = 768;
+constexpr int kSharedOctaves = 2048;
+constexpr int kSharedStagePerWarp = 32 * kLaneStrideWords * 4;   // sample bits, later the exact codes
+constexpr int kSharedQueuePerWarp = 32 * kValuesPerLane * 2;     // uint16 slots; every sample fits
+__host__ __device__ constexpr int SharedFixedBytes(int warps) { return kSharedLibm + kSharedOctaves + warps * (kSharedStagePerWarp + kSharedQueuePerWarp); }
+
+// The flat table (128 KB for 12-bit PQ) leaves room for one CTA per SM: 16 warps; the two-level table is small
+// enough for two CTAs of 8 warps.  Either way 16 warps are resident per SM.
+template <int TABLE>
+struct FastConfig
 {
-    uint32_t bits;
-    uint32_t slot;
+    static constexpr int threads = TABLE == kTableFlat ? 512 : 256;
+    static constexpr int warps = threads / 32;
+    static constexpr int blocksPerSm = TABLE == kTableFlat ? 1 : 2;
+    static constexpr int sharedLimit = TABLE == kTableFlat ? 224 * 1024 : 112 * 1024;
 };
 
-__device__ __forceinline__ float4 LoadRow4(const uint8_t* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
-template <int CURVE, int XS, int YS>
-__global__ void __launch_bounds__(kFastThreads, 2) EncodeRgbF32PlanarKernel(const FastEncodeParams p)
+template <int CURVE, int XS, int YS, int TABLE>
+__global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>::blocksPerSm) EncodeRgbF32PlanarKernel(const FastEncodeParams p)
 {
+    constexpr int kFastWarps = FastConfig<TABLE>::warps;
+    constexpr int kSharedFixed = SharedFixedBytes(kFastWarps);
     extern __shared__ __align__(16) uint8_t sharedBytes[];
-    // layout: libm tables (768 B) | octaves (2048 B) | per-warp queues | per-warp results | buckets
     uint64_t* libmStorage = reinterpret_cast<uint64_t*>(sharedBytes);
-    uint2* octaves = reinterpret_cast<uint2*>(sharedBytes + 768);
-    QueueEntry* queues = reinterpret_cast<QueueEntry*>(sharedBytes + 768 + 2048);
-    uint16_t* results = reinterpret_cast<uint16_t*>(sharedBytes + 768 + 2048 + kFastWarps * kQueueCapacity * sizeof(QueueEntry));
-    uint32_t* buckets = reinterpret_cast<uint32_t*>(sharedBytes + 768 + 2048 + kFastWarps * kQueueCapacity * sizeof(QueueEntry) +
-                                                    kFastWarps * 32 * kValuesPerLane * sizeof(uint16_t));
+    uint2* octaves = reinterpret_cast<uint2*>(sharedBytes + kSharedLibm);
+    uint32_t* stageAll = reinterpret_cast<uint32_t*>(sharedBytes + kSharedLibm + kSharedOctaves);
+    uint16_t* queueAll = reinterpret_cast<uint16_t*>(sharedBytes + kSharedLibm + kSharedOctaves + kFastWarps * kSharedStagePerWarp);
+    uint32_t* tableWords = reinterpret_cast<uint32_t*>(sharedBytes + kSharedFixed);
+    uint2* flatEntries = reinterpret_cast<uint2*>(sharedBytes + kSharedFixed);
 
     const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
     if (CURVE != kCurveClip)
     {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (TABLE == kTableFlat)
         {
-            octaves[i] = p.table.octaves[i];
+            for (int i = threadIdx.x; i < p.table.flatCount; i += blockDim.x)
+            {
+                flatEntries[i] = p.table.flat[i];
+            }
         }
-        for (int i = threadIdx.x; i < p.table.bucketCount; i += blockDim.x)
+        else
         {
-            buckets[i] = p.table.buckets[i];
+            for (int i = threadIdx.x; i < 256; i += blockDim.x)
+            {
+                octaves[i] = p.table.octaves[i];
+            }
+            for (int i = threadIdx.x; i < p.table.bucketCount; i += blockDim.x)
+            {
+                tableWords[i] = p.table.buckets[i];
+            }
         }
     }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int warpInBlock = threadIdx.x >> 5;
-    QueueEntry* queue = queues + warpInBlock * kQueueCapacity;
-    uint16_t* result = results + warpInBlock * 32 * kValuesPerLane;
+    uint32_t* stage = stageAll + warpInBlock * (32 * kLaneStrideWords);
+    uint32_t* myStage = stage + lane * kLaneStrideWords;
+    uint16_t* queue = queueAll + warpInBlock * (32 * kValuesPerLane);
+    const uint2* flatBiased = flatEntries - p.table.flatLow;
+    const uint32_t flatShift = p.table.flatShift;
+    const int32_t flatLow = static_cast<int32_t>(p.table.flatLow);
+    const int32_t flatHigh = static_cast<int32_t>(p.table.flatHigh);
 
     const int tilesX = (p.width + kTilePixels - 1) / kTilePixels;
     const int tileRows = (p.rowCount + 1) / 2;
-    const long long tileCount = static_cast<long long>(tilesX) * tileRows;
-    const long long warpCount = static_cast<long long>(gridDim.x) * kFastWarps;
+    const int tileCount = tilesX * tileRows;
+    const int warpCount = static_cast<int>(gridDim.x) * kFastWarps;
 
-    for (long long tile = static_cast<long long>(blockIdx.x) * kFastWarps + warpInBlock; tile < tileCount; tile += warpCount)
+    for (int tile = static_cast<int>(blockIdx.x) * kFastWarps + warpInBlock; tile < tileCount; tile += warpCount)
     {
-        const int tileRow = static_cast<int>(tile / tilesX);
-        const int tileX = static_cast<int>(tile - static_cast<long long>(tileRow) * tilesX);
+        const int tileRow = tile / tilesX;
+        const int tileX = tile - tileRow * tilesX;
         const int x0 = tileX * kTilePixels + lane * 4;
         const int y0 = tileRow * 2;
         const bool laneActive = x0 < p.width;
         const bool secondRow = (y0 + 1) < p.rowCount;
 
-        // ---- load 2 rows x 4 pixels x RGB ------------------------------------------------------------------
-        float v[kValuesPerLane];
-        if (laneActive)
+        // ---- load 2 rows x 4 pixels x RGB as six 128-bit words ---------------------------------------------
+        uint4 raw[6];
         {
             const uint8_t* r0 = p.rows + static_cast<int64_t>(y0) * p.rowStride + static_cast<int64_t>(x0) * 12;
-            const float4 a0 = LoadRow4(r0), a1 = LoadRow4(r0 + 16), a2 = LoadRow4(r0 + 32);
-            v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-            v[8] = a2.x; v[9] = a2.y; v[10] = a2.z; v[11] = a2.w;
-            if (secondRow)
-            {
-                const uint8_t* r1 = r0 + p.rowStride;
-                const float4 b0 = LoadRow4(r1), b1 = LoadRow4(r1 + 16), b2 = LoadRow4(r1 + 32);
-                v[12] = b0.x; v[13] = b0.y; v[14] = b0.z; v[15] = b0.w; v[16] = b1.x; v[17] = b1.y; v[18] = b1.z; v[19] = b1.w;
-                v[20] = b2.x; v[21] = b2.y; v[22] = b2.z; v[23] = b2.w;
-            }
-            else
-            {
+            const uint8_t* r1 = r0 + p.rowStride;
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                for (int j = 12; j < 24; ++j) v[j] = 0.0f;
+            for (int q = 0; q < 3; ++q)
+            {
+                raw[q] = laneActive ? __ldg(reinterpret_cast<const uint4*>(r0 + 16 * q)) : zero;
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+            {
+                raw[3 + q] = (laneActive && secondRow) ? __ldg(reinterpret_cast<const uint4*>(r1 + 16 * q)) : zero;
+            }
+        }
+        uint32_t code[kValuesPerLane];
+
+        if (CURVE == kCurveClip)
+        {
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+            {
+                code[4 * q + 0] = FloatToCode(__uint_as_float(raw[q].x), p.maxCodeFloat);
+                code[4 * q + 1] = FloatToCode(__uint_as_float(raw[q].y), p.maxCodeFloat);
+                code[4 * q + 2] = FloatToCode(__uint_as_float(raw[q].z), p.maxCodeFloat);
+                code[4 * q + 3] = FloatToCode(__uint_as_float(raw[q].w), p.maxCodeFloat);
             }
         }
         else
         {
+            // ---- float -> code through the exact step table; in-band samples go to the exact path ------------
+            // Stage the raw sample bits where any lane can fetch them (the exact path runs compacted).
 #pragma unroll
-            for (int j = 0; j < 24; ++j) v[j] = 0.0f;
-        }
-
-        // ---- float -> code: table, with in-band samples queued for the exact path ---------------------------
-        uint32_t code[kValuesPerLane];
-        uint32_t bandMask = 0;
-        int queued = 0; // warp-uniform
-#pragma unroll
-        for (int j = 0; j < kValuesPerLane; ++j)
-        {
-            if (CURVE == kCurveClip)
+            for (int q = 0; q < 6; ++q)
             {
-                code[j] = FloatToCode(v[j], p.maxCodeFloat);
+                *reinterpret_cast<uint4*>(myStage + 4 * q) = raw[q];
             }
-            else
+            uint32_t bandMask = 0;
+#pragma unroll
+            for (int j = 0; j < kValuesPerLane; ++j)
             {
-                const uint32_t bits = __float_as_uint(v[j]);
+                const uint4 w = raw[j >> 2];
+                const uint32_t bits = (j & 3) == 0 ? w.x : (j & 3) == 1 ? w.y : (j & 3) == 2 ? w.z : w.w;
                 bool inBand;
-                code[j] = LookupCurveCode(bits, octaves, buckets, inBand);
-                const uint32_t ballot = __ballot_sync(0xffffffffu, inBand);
-                if (ballot != 0)
+                if (TABLE == kTableFlat)
                 {
-                    const int count = __popc(ballot);
-                    if (queued + count > kQueueCapacity)
-                    {
-                        // flush: evaluate what is queued with all lanes busy
-                        __syncwarp();
-                        for (int q = lane; q < queued; q += 32)
-                        {
-                            const QueueEntry entry = queue[q];
-                            result[entry.slot] = static_cast<uint16_t>(
-                                ExactCurveCode<CURVE == kCurveClip ? kCurveLinearToPQ : CURVE>(__uint_as_float(entry.bits), p.pqMultiplier, p.maxCodeFloat, t));
-                        }
-                        __syncwarp();
-                        queued = 0;
-                    }
-                    if (inBand)
-                    {
-                        const int position = queued + __popc(ballot & ((1u << lane) - 1u));
-                        QueueEntry entry;
-                        entry.bits = bits;
-                        entry.slot = static_cast<uint32_t>(lane * kValuesPerLane + j);
-                        queue[position] = entry;
-                        bandMask |= 1u << j;
-                    }
-                    queued += count;
+                    code[j] = LookupCurveCodeFlat(bits, flatBiased, flatShift, flatLow, flatHigh, inBand);
                 }
-            }
-        }
-        if (CURVE != kCurveClip)
-        {
-            if (queued > 0)
-            {
-                __syncwarp();
-                for (int q = lane; q < queued; q += 32)
+                else
                 {
-                    const QueueEntry entry = queue[q];
-                    result[entry.slot] = static_cast<uint16_t>(
-                        ExactCurveCode<CURVE == kCurveClip ? kCurveLinearToPQ : CURVE>(__uint_as_float(entry.bits), p.pqMultiplier, p.maxCodeFloat, t));
+                    code[j] = LookupCurveCode(bits, octaves, tableWords, inBand);
                 }
-                __syncwarp();
+                bandMask |= inBand ? (1u << j) : 0u;
             }
-            if (bandMask != 0)
-            {
+
+            // Warp-level compaction: exclusive prefix sum of the per-lane counts gives every lane its queue range.
+            const int mine = __popc(bandMask);
+            int inclusive = mine;
 #pragma unroll
-                for (int j = 0; j < kValuesPerLane; ++j)
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const int up = __shfl_up_sync(0xffffffffu, inclusive, d);
+                inclusive += (lane >= d) ? up : 0;
+            }
+            const int total = __shfl_sync(0xffffffffu, inclusive, 31);
+            if (total > 0)
+            {
+                int position = inclusive - mine;
+                uint32_t pending = bandMask;
+                while (pending != 0)
                 {
-                    if (bandMask & (1u << j))
+                    const int j = __ffs(static_cast<int>(pending)) - 1;
+                    pending &= pending - 1;
+                    queue[position++] = static_cast<uint16_t>(lane * kLaneStrideWords + j);
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int q = lane; q < total; q += 32)
+                {
+                    const uint32_t slot = queue[q];
+                    stage[slot] = ExactCurveCode<CURVE == kCurveClip ? kCurveLinearToPQ : CURVE>(__uint_as_float(stage[slot]), p.pqMultiplier,
+                                                                                              p.maxCodeFloat, t);
+                }
+                __syncwarp();
+                if (bandMask != 0)
+                {
+#pragma unroll
+                    for (int j = 0; j < kValuesPerLane; ++j)
                     {
-                        code[j] = result[lane * kValuesPerLane + j];
+                        if (bandMask & (1u << j))
+                        {
+                            code[j] = myStage[j];
+                        }
                     }
                 }
+                __syncwarp(); // the staging area is rewritten by the next tile
             }
-            __syncwarp(); // results are rewritten by the next tile
         }
 
         if (!laneActive)
@@ -258,10 +285,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) EncodeRgbF32PlanarKernel(cons
                 cbCode[s] = QuantiseChroma(cbv, p.chromaOffset, p.maxCode);
                 crCode[s] = QuantiseChroma(crv, p.chromaOffset, p.maxCode);
             }
-            const int64_t chromaOffsetBytes = static_cast<int64_t>(tileRow) * p.strideCb + static_cast<int64_t>(x0 >> 1) * 2;
-            __stcs(reinterpret_cast<uint32_t*>(p.planeCb + chromaOffsetBytes), cbCode[0] | (cbCode[1] << 16));
-            __stcs(reinterpret_cast<uint32_t*>(p.planeCr + static_cast<int64_t>(tileRow) * p.strideCr + static_cast<int64_t>(x0 >> 1) * 2),
-                   crCode[0] | (crCode[1] << 16));
+            const int64_t column = static_cast<int64_t>(x0 >> 1) * 2;
+            __stcs(reinterpret_cast<uint32_t*>(p.planeCb + static_cast<int64_t>(tileRow) * p.strideCb + column), cbCode[0] | (cbCode[1] << 16));
+            __stcs(reinterpret_cast<uint32_t*>(p.planeCr + static_cast<int64_t>(tileRow) * p.strideCr + column), crCode[0] | (crCode[1] << 16));
         }
         else if (XS == 1)
         {
@@ -278,10 +304,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) EncodeRgbF32PlanarKernel(cons
                     cbCode[s] = QuantiseChroma(cbv, p.chromaOffset, p.maxCode);
                     crCode[s] = QuantiseChroma(crv, p.chromaOffset, p.maxCode);
                 }
-                __stcs(reinterpret_cast<uint32_t*>(p.planeCb + static_cast<int64_t>(y0 + r) * p.strideCb + static_cast<int64_t>(x0 >> 1) * 2),
-                       cbCode[0] | (cbCode[1] << 16));
-                __stcs(reinterpret_cast<uint32_t*>(p.planeCr + static_cast<int64_t>(y0 + r) * p.strideCr + static_cast<int64_t>(x0 >> 1) * 2),
-                       crCode[0] | (crCode[1] << 16));
+                const int64_t column = static_cast<int64_t>(x0 >> 1) * 2;
+                __stcs(reinterpret_cast<uint32_t*>(p.planeCb + static_cast<int64_t>(y0 + r) * p.strideCb + column), cbCode[0] | (cbCode[1] << 16));
+                __stcs(reinterpret_cast<uint32_t*>(p.planeCr + static_cast<int64_t>(y0 + r) * p.strideCr + column), crCode[0] | (crCode[1] << 16));
             }
         }
         else
@@ -297,56 +322,78 @@ __global__ void __launch_bounds__(kFastThreads, 2) EncodeRgbF32PlanarKernel(cons
                     cbCode[i] = QuantiseChroma(cb[r][i], p.chromaOffset, p.maxCode);
                     crCode[i] = QuantiseChroma(cr[r][i], p.chromaOffset, p.maxCode);
                 }
-                __stcs(reinterpret_cast<uint2*>(p.planeCb + static_cast<int64_t>(y0 + r) * p.strideCb + static_cast<int64_t>(x0) * 2),
+                const int64_t column = static_cast<int64_t>(x0) * 2;
+                __stcs(reinterpret_cast<uint2*>(p.planeCb + static_cast<int64_t>(y0 + r) * p.strideCb + column),
                        make_uint2(cbCode[0] | (cbCode[1] << 16), cbCode[2] | (cbCode[3] << 16)));
-                __stcs(reinterpret_cast<uint2*>(p.planeCr + static_cast<int64_t>(y0 + r) * p.strideCr + static_cast<int64_t>(x0) * 2),
+                __stcs(reinterpret_cast<uint2*>(p.planeCr + static_cast<int64_t>(y0 + r) * p.strideCr + column),
                        make_uint2(crCode[0] | (crCode[1] << 16), crCode[2] | (crCode[3] << 16)));
             }
         }
     }
 }
 
-size_t FastEncodeSharedBytes(int bucketCount)
+template <int CURVE, int XS, int YS, int TABLE>
+size_t FastEncodeSharedBytes(const FastEncodeParams& fp)
 {
-    return 768 + 2048 + kFastWarps * kQueueCapacity * sizeof(QueueEntry) + kFastWarps * 32 * kValuesPerLane * sizeof(uint16_t) +
-           static_cast<size_t>(bucketCount) * sizeof(uint32_t);
+    const size_t tableBytes = CURVE == kCurveClip ? 0
+                              : (TABLE == kTableFlat ? static_cast<size_t>(fp.table.flatCount) * sizeof(uint2)
+                                                     : static_cast<size_t>(fp.table.bucketCount) * sizeof(uint32_t));
+    return static_cast<size_t>(SharedFixedBytes(FastConfig<TABLE>::warps)) + tableBytes;
 }
 
-template <int CURVE, int XS, int YS>
+template <int CURVE, int XS, int YS, int TABLE>
 cudaError_t LaunchFastEncodeKernel(const FastEncodeParams& fp, int smCount, cudaStream_t stream)
 {
-    const size_t shared = FastEncodeSharedBytes(CURVE == kCurveClip ? 0 : fp.table.bucketCount);
+    using Config = FastConfig<TABLE>;
+    const size_t shared = FastEncodeSharedBytes<CURVE, XS, YS, TABLE>(fp);
     static bool configured = false; // per instantiation
     if (!configured)
     {
-        const cudaError_t e = cudaFuncSetAttribute(EncodeRgbF32PlanarKernel<CURVE, XS, YS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        const cudaError_t e = cudaFuncSetAttribute(EncodeRgbF32PlanarKernel<CURVE, XS, YS, TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   Config::sharedLimit);
         if (e != cudaSuccess)
         {
             return e;
         }
         configured = true;
     }
-    if (shared > 110 * 1024)
+    if (shared > static_cast<size_t>(Config::sharedLimit))
     {
         return cudaErrorInvalidValue;
     }
     const long long tiles = static_cast<long long>((fp.width + kTilePixels - 1) / kTilePixels) * ((fp.rowCount + 1) / 2);
-    long long blocks = (tiles + kFastWarps - 1) / kFastWarps;
-    const long long resident = static_cast<long long>(smCount) * 2;
+    if (tiles > 0x7fffffffll)
+    {
+        return cudaErrorInvalidValue;
+    }
+    long long blocks = (tiles + Config::warps - 1) / Config::warps;
+    const long long resident = static_cast<long long>(smCount) * Config::blocksPerSm;
     if (blocks > resident)
     {
         blocks = resident;
     }
-    EncodeRgbF32PlanarKernel<CURVE, XS, YS><<<static_cast<unsigned>(blocks), kFastThreads, shared, stream>>>(fp);
+    EncodeRgbF32PlanarKernel<CURVE, XS, YS, TABLE><<<static_cast<unsigned>(blocks), Config::threads, shared, stream>>>(fp);
     return cudaGetLastError();
 }
 
-template <int CURVE>
+template <int CURVE, int TABLE>
 cudaError_t DispatchChroma(const FastEncodeParams& fp, int xs, int ys, int smCount, cudaStream_t stream)
 {
-    if (xs == 1 && ys == 1) return LaunchFastEncodeKernel<CURVE, 1, 1>(fp, smCount, stream);
-    if (xs == 1) return LaunchFastEncodeKernel<CURVE, 1, 0>(fp, smCount, stream);
-    return LaunchFastEncodeKernel<CURVE, 0, 0>(fp, smCount, stream);
+    if (xs == 1 && ys == 1) return LaunchFastEncodeKernel<CURVE, 1, 1, TABLE>(fp, smCount, stream);
+    if (xs == 1) return LaunchFastEncodeKernel<CURVE, 1, 0, TABLE>(fp, smCount, stream);
+    return LaunchFastEncodeKernel<CURVE, 0, 0, TABLE>(fp, smCount, stream);
+}
+
+template <int CURVE>
+cudaError_t DispatchTable(const FastEncodeParams& fp, int xs, int ys, int smCount, cudaStream_t stream)
+{
+    if (fp.table.flat != nullptr &&
+        static_cast<size_t>(SharedFixedBytes(FastConfig<kTableFlat>::warps)) + static_cast<size_t>(fp.table.flatCount) * sizeof(uint2) <=
+            static_cast<size_t>(FastConfig<kTableFlat>::sharedLimit))
+    {
+        return DispatchChroma<CURVE, kTableFlat>(fp, xs, ys, smCount, stream);
+    }
+    return DispatchChroma<CURVE, kTableTwoLevel>(fp, xs, ys, smCount, stream);
 }
 
 bool Aligned(const void* p, int64_t stride, int alignment)
@@ -410,9 +457,9 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
 
     const int smCount = p.smCount > 0 ? p.smCount : 148;
     cudaError_t e;
-    if (curve == kCurveLinearToPQ) e = DispatchChroma<kCurveLinearToPQ>(fp, p.xs, p.ys, smCount, stream);
-    else if (curve == kCurveLinearToSMPTE428) e = DispatchChroma<kCurveLinearToSMPTE428>(fp, p.xs, p.ys, smCount, stream);
-    else e = DispatchChroma<kCurveClip>(fp, p.xs, p.ys, smCount, stream);
+    if (curve == kCurveLinearToPQ) e = DispatchTable<kCurveLinearToPQ>(fp, p.xs, p.ys, smCount, stream);
+    else if (curve == kCurveLinearToSMPTE428) e = DispatchTable<kCurveLinearToSMPTE428>(fp, p.xs, p.ys, smCount, stream);
+    else e = DispatchChroma<kCurveClip, kTableTwoLevel>(fp, p.xs, p.ys, smCount, stream);
     if (e != cudaSuccess)
     {
         return AVIFGPU_ERR_CUDA;

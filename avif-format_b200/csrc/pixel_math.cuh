@@ -205,20 +205,24 @@ AVIF_HD uint32_t FloatToCode(float v, float maxValue)
 
 // Forward matrix, this project's definition of the stage the reference leaves to libheif (DESIGN.md "Forward
 // matrix"): the algebraic inverse of YuvDecode.cpp:555-557 on integer
-// codes, full range.
+// codes, full range: Y = (kr R + kg G) + kb B, Cb = (B - Y) * 0.5f/(1-kb), Cr = (R - Y) * 0.5f/(1-kr).
 struct ForwardMatrix
 {
     float kr, kg, kb;
-    float cbDivisor; // 2*(1-kb)
-    float crDivisor; // 2*(1-kr)
+    float cbScale; // 0.5f / (1-kb)
+    float crScale; // 0.5f / (1-kr)
     int identity;    // matrix_coefficients == 0 (GBR)
 };
 
+// (float)code.  The conversion instruction issues on the quarter-rate pipe, which this path otherwise leaves idle;
+// the integer pipe is the busy one, so the conversion is cheaper here than the usual 2^23 bit trick.
+AVIF_HD float CodeToFloat(uint32_t code) { return static_cast<float>(code); }
+
 AVIF_HD void ForwardPixel(const ForwardMatrix& m, uint32_t rc, uint32_t gc, uint32_t bc, float& y, float& cb, float& cr)
 {
-    const float r = static_cast<float>(rc);
-    const float g = static_cast<float>(gc);
-    const float b = static_cast<float>(bc);
+    const float r = CodeToFloat(rc);
+    const float g = CodeToFloat(gc);
+    const float b = CodeToFloat(bc);
     if (m.identity)
     {
         y = g;
@@ -227,8 +231,8 @@ AVIF_HD void ForwardPixel(const ForwardMatrix& m, uint32_t rc, uint32_t gc, uint
         return;
     }
     y = ((m.kr * r) + (m.kg * g)) + (m.kb * b);
-    cb = (b - y) / m.cbDivisor;
-    cr = (r - y) / m.crDivisor;
+    cb = (b - y) * m.cbScale;
+    cr = (r - y) * m.crScale;
 }
 
 AVIF_HD uint32_t QuantiseLuma(float y, int maxCode)

@@ -238,7 +238,7 @@ def planes_from_arrays(arrays):
             planes.data[i] = None
             planes.stride[i] = 0
         else:
-            assert a.ndim == 2 and a.strides[1] == a.itemsize
+            assert a.ndim == 2 and (a.size == 0 or a.strides[1] == a.itemsize)
             planes.data[i] = a.ctypes.data
             planes.stride[i] = a.strides[0]
     return planes

@@ -720,17 +720,20 @@ static void store_code(void* row, int index, int bytes_per_sample, uint16_t code
 }
 
 /*
- * Forward matrix (PARITY UNPINNED, see avif_oracle.h): the exact algebraic inverse of the reference decoder
- * (YuvDecode.cpp:555-557) on integer codes, full range (WriteMetadata.cpp:46), float32, no contraction:
+ * Forward matrix (PARITY UNPINNED, see avif_oracle.h): the algebraic inverse of the reference decoder
+ * (YuvDecode.cpp:555-557: R = Y + 2(1-kr)Cr, B = Y + 2(1-kb)Cb) on integer codes, full range
+ * (WriteMetadata.cpp:46), float32, no contraction, with the two chroma gains as float constants (the way
+ * libheif holds its RGB->YCbCr coefficients):
  *     Y  = (kr*R + kg*G) + kb*B
- *     Cb = (B - Y) / (2*(1-kb))          Cr = (R - Y) / (2*(1-kr))
+ *     Cb = (B - Y) * cb_scale,  cb_scale = 0.5f / (1 - kb)
+ *     Cr = (R - Y) * cr_scale,  cr_scale = 0.5f / (1 - kr)
  * Identity matrix (lossless GBR, WriteMetadata.cpp:143-146): Y = G, Cb = B, Cr = R.
  */
 typedef struct forward_matrix
 {
     float kr, kg, kb;
-    float cb_divisor; /* 2*(1-kb) */
-    float cr_divisor; /* 2*(1-kr) */
+    float cb_scale; /* 0.5f / (1-kb) */
+    float cr_scale; /* 0.5f / (1-kr) */
     int identity;
 } forward_matrix;
 
@@ -741,8 +744,8 @@ static void forward_matrix_init(forward_matrix* m, const avifgpu_nclx* nclx)
     m->kr = k[0];
     m->kg = k[1];
     m->kb = k[2];
-    m->cb_divisor = 2 * (1 - m->kb);
-    m->cr_divisor = 2 * (1 - m->kr);
+    m->cb_scale = 0.5f / (1.0f - m->kb);
+    m->cr_scale = 0.5f / (1.0f - m->kr);
     m->identity = nclx != NULL && nclx->present && nclx->matrix_coefficients == 0;
 }
 
@@ -759,8 +762,8 @@ static void forward_pixel(const forward_matrix* m, const uint16_t rgb[3], float*
         return;
     }
     *y = ((m->kr * r) + (m->kg * g)) + (m->kb * b);
-    *cb = (b - *y) / m->cb_divisor;
-    *cr = (r - *y) / m->cr_divisor;
+    *cb = (b - *y) * m->cb_scale;
+    *cr = (r - *y) * m->cr_scale;
 }
 
 static uint16_t quantise_luma(float y, int max_code)

@@ -1,0 +1,74 @@
+"""Golden vectors (tests/golden/*.npz, produced by tests/golden/make_golden.py from the compiled reference):
+the C restatement must reproduce them on any machine (CPU test), and so must the GPU (marked gpu)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from avifgpu import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load(file_name):
+    data = np.load(os.path.join(HERE, "golden", file_name))
+    index = json.loads(bytes(data["__index__"]).decode())
+    return data, index
+
+
+def make_desc(kind, fields):
+    fields = dict(fields)
+    nclx = abi.Nclx(**fields.pop("nclx"))
+    fields.pop("struct_size")
+    desc = abi.EncodeDesc(1, 1, 8, 1) if kind == "encode" else abi.DecodeDesc(1, 1)
+    for key, value in fields.items():
+        setattr(desc, key, value)
+    desc.nclx = nclx
+    return desc
+
+
+def check(file_name, runner_encode, runner_decode, libm_now):
+    data, index = load(file_name)
+    float_outputs_comparable = index["meta"]["libm"] == libm_now
+    failures = []
+    for entry in index["cases"]:
+        name, desc = entry["name"], make_desc(entry["kind"], entry["desc"])
+        if entry["kind"] == "encode":
+            got = runner_encode(desc, data[name + "/in"])
+            for k, plane in enumerate(got):
+                key = f"{name}/out{k}"
+                assert (plane is None) == (key not in data.files), name
+                if plane is not None and not np.array_equal(plane, data[key]):
+                    # codes behind a float transfer curve depend on libm only through rare 1-code flips
+                    failures.append(name)
+        else:
+            planes = [data[f"{name}/in{k}"] if f"{name}/in{k}" in data.files else None for k in range(4)]
+            got = runner_decode(desc, planes)
+            if not cases.same_bits(got, data[name + "/out"]):
+                if got.dtype == np.float32 and not float_outputs_comparable:
+                    continue  # float outputs are defined by the generating libm
+                failures.append(name)
+    assert not failures, failures[:10]
+    return len(index["cases"])
+
+
+def test_restatement_reproduces_reference_vectors(port):
+    n = check("reference_vectors.npz", lambda d, rows: port.encode(d, rows), lambda d, planes: port.decode(d, planes), port.libm_version())
+    assert n > 300
+
+
+def test_restatement_reproduces_forward_vectors(port):
+    n = check("forward_vectors.npz", lambda d, rows: port.encode(d, rows), None, port.libm_version())
+    assert n > 100
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_reference_vectors(gpu, port):
+    check("reference_vectors.npz", lambda d, rows: gpu.encode(d, rows), lambda d, planes: gpu.decode(d, planes), port.libm_version())
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_forward_vectors(gpu, port):
+    check("forward_vectors.npz", lambda d, rows: gpu.encode(d, rows), None, port.libm_version())
