@@ -50,19 +50,23 @@ __device__ __forceinline__ uint32_t LookupCurveCode(uint32_t bits, const uint2* 
     return (word >> kBucketOffsetBits) + (offsetQ >= stepOffset ? 1u : 0u);
 }
 
-// Flat-table look-up (see CurveTableView::flat).  `flatBiased` points at flat - flatLow (so it is indexed by the
-// bucket number itself).  Branch-free.  The bucket number is taken with an ARITHMETIC shift and clamped as a
-// signed integer, so every float with the sign bit set (negative values, -0, negative NaNs) lands in the lowest
-// bucket, which holds no step (.x = 0, so `bits < .x` is false) and decodes to code 0 exactly as the reference's
-// `value < 0 -> 0` / NaN -> 0 does; +inf and positive NaNs are reported in band (they do not follow the steps).
-__device__ __forceinline__ uint32_t LookupCurveCodeFlat(uint32_t bits, const uint2* __restrict__ flatBiased, uint32_t shift,
-                                                        int32_t low, int32_t high, bool& inBand)
+// Flat-table look-up (see CurveTableView::flat): `flat` is indexed by (bucket number - low), `span` = high - low.
+// Branch-free, 12 integer instructions + one 64-bit shared-memory load.  The bucket number is taken with an
+// ARITHMETIC shift, so every float with the sign bit set (negative values, -0, negative NaNs) yields a negative
+// index that the single clamp-to-[0, span] instruction (DPX min + relu) sends to the lowest bucket; that bucket
+// holds no step (.x = 0, so `bits < .x` is false) and decodes to code 0 exactly as the reference's
+// `value < 0 -> 0` / NaN -> 0 does.  +inf and positive NaNs are reported in band (they do not follow the steps).
+__device__ __forceinline__ uint32_t LookupCurveCodeFlat(uint32_t bits, const uint2* __restrict__ flat, uint32_t shift, int32_t low,
+                                                        int32_t span, bool& inBand)
 {
-    const int32_t bucket = min(max(static_cast<int32_t>(bits) >> shift, low), high);
-    const uint2 entry = flatBiased[bucket];
+    const int32_t index = __vimin_s32_relu((static_cast<int32_t>(bits) >> shift) - low, span);
+    const uint2 entry = flat[index];
     const uint32_t distance = bits - entry.x;
     inBand = (distance < (entry.y & 0xfffffu)) || (static_cast<int32_t>(bits) > 0x7f7fffff);
-    return (entry.y >> 20) - (bits < entry.x ? 1u : 0u);
+    uint32_t code;
+    asm("{ .reg .pred below; setp.lt.u32 below, %1, %2; shr.u32 %0, %3, 20; @below sub.u32 %0, %0, 1; }"
+        : "=r"(code) : "r"(bits), "r"(entry.x), "r"(entry.y));
+    return code;
 }
 
 } // namespace avifgpu

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kSweepThreads) VerifyKernel(float pqMultiplier
         {
             // the flat variant must agree as well (its bands differ: count the union)
             bool inBandFlat;
-            const uint32_t fastFlat = LookupCurveCodeFlat(bits, table.flat - table.flatLow, table.flatShift, static_cast<int32_t>(table.flatLow), static_cast<int32_t>(table.flatHigh), inBandFlat);
+            const uint32_t fastFlat = LookupCurveCodeFlat(bits, table.flat, table.flatShift, static_cast<int32_t>(table.flatLow), static_cast<int32_t>(table.flatHigh - table.flatLow), inBandFlat);
             if (!inBandFlat && fastFlat != ExactCurveCode<CURVE>(__uint_as_float(bits), pqMultiplier, maxCodeFloat, t))
             {
                 ++mismatches;

@@ -59,18 +59,20 @@ struct FastEncodeParams
 constexpr int kSharedLibm = 768;
 constexpr int kSharedOctaves = 2048;
 constexpr int kSharedStagePerWarp = 32 * kLaneStrideWords * 4;   // sample bits, later the exact codes
-constexpr int kSharedQueuePerWarp = 32 * kValuesPerLane * 2;     // uint16 slots; every sample fits
+constexpr int kQueueCapacity = 256;                              // in-band samples per exact-path round (uint16 slots)
+constexpr int kSharedQueuePerWarp = kQueueCapacity * 2;
 __host__ __device__ constexpr int SharedFixedBytes(int warps) { return kSharedLibm + kSharedOctaves + warps * (kSharedStagePerWarp + kSharedQueuePerWarp); }
 
-// The flat table (128 KB for 12-bit PQ) leaves room for one CTA per SM: 16 warps; the two-level table is small
-// enough for two CTAs of 8 warps.  Either way 16 warps are resident per SM.
+// The flat table (128 KB for 12-bit PQ) leaves room for one CTA per SM: 16 warps (measured: 24 warps at 58
+// registers were slower -- the compiler serialises the 24 independent look-ups of a lane when registers are
+// short).  The two-level table is small enough for two CTAs of 8 warps.
 template <int TABLE>
 struct FastConfig
 {
     static constexpr int threads = TABLE == kTableFlat ? 512 : 256;
     static constexpr int warps = threads / 32;
     static constexpr int blocksPerSm = TABLE == kTableFlat ? 1 : 2;
-    static constexpr int sharedLimit = TABLE == kTableFlat ? 224 * 1024 : 112 * 1024;
+    static constexpr int sharedLimit = TABLE == kTableFlat ? 227 * 1024 : 112 * 1024;
 };
 
 template <int CURVE, int XS, int YS, int TABLE>
@@ -114,8 +116,8 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
     const int warpInBlock = threadIdx.x >> 5;
     uint32_t* stage = stageAll + warpInBlock * (32 * kLaneStrideWords);
     uint32_t* myStage = stage + lane * kLaneStrideWords;
-    uint16_t* queue = queueAll + warpInBlock * (32 * kValuesPerLane);
-    const uint2* flatBiased = flatEntries - p.table.flatLow;
+    uint16_t* queue = queueAll + warpInBlock * kQueueCapacity;
+    const uint2* flatBiased = flatEntries; // indexed by bucket - flatLow (the look-up applies the bias)
     const uint32_t flatShift = p.table.flatShift;
     const int32_t flatLow = static_cast<int32_t>(p.table.flatLow);
     const int32_t flatHigh = static_cast<int32_t>(p.table.flatHigh);
@@ -125,10 +127,19 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
     const int tileCount = tilesX * tileRows;
     const int warpCount = static_cast<int>(gridDim.x) * kFastWarps;
 
-    for (int tile = static_cast<int>(blockIdx.x) * kFastWarps + warpInBlock; tile < tileCount; tile += warpCount)
+    // Tile coordinates advance incrementally (an integer division per tile costs ~24 instructions).
+    const int firstTile = static_cast<int>(blockIdx.x) * kFastWarps + warpInBlock;
+    const int stepRows = warpCount / tilesX;
+    const int stepX = warpCount - stepRows * tilesX;
+    int tileRow = firstTile / tilesX;
+    int tileX = firstTile - tileRow * tilesX;
+    for (int tile = firstTile; tile < tileCount; tile += warpCount, tileRow += stepRows, tileX += stepX)
     {
-        const int tileRow = tile / tilesX;
-        const int tileX = tile - tileRow * tilesX;
+        if (tileX >= tilesX)
+        {
+            tileX -= tilesX;
+            ++tileRow;
+        }
         const int x0 = tileX * kTilePixels + lane * 4;
         const int y0 = tileRow * 2;
         const bool laneActive = x0 < p.width;
@@ -182,13 +193,13 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
                 bool inBand;
                 if (TABLE == kTableFlat)
                 {
-                    code[j] = LookupCurveCodeFlat(bits, flatBiased, flatShift, flatLow, flatHigh, inBand);
+                    code[j] = LookupCurveCodeFlat(bits, flatBiased, flatShift, flatLow, flatHigh - flatLow, inBand);
                 }
                 else
                 {
                     code[j] = LookupCurveCode(bits, octaves, tableWords, inBand);
                 }
-                bandMask |= inBand ? (1u << j) : 0u;
+                asm("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p or.b32 %0, %0, %2; }" : "+r"(bandMask) : "r"(static_cast<uint32_t>(inBand)), "r"(1u << j));
             }
 
             // Warp-level compaction: exclusive prefix sum of the per-lane counts gives every lane its queue range.
@@ -203,23 +214,32 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
             const int total = __shfl_sync(0xffffffffu, inclusive, 31);
             if (total > 0)
             {
-                int position = inclusive - mine;
-                uint32_t pending = bandMask;
-                while (pending != 0)
+                // Rounds of at most kQueueCapacity samples (one round unless a whole tile sits inside fuzzy bands).
+                for (int roundStart = 0; roundStart < total; roundStart += kQueueCapacity)
                 {
-                    const int j = __ffs(static_cast<int>(pending)) - 1;
-                    pending &= pending - 1;
-                    queue[position++] = static_cast<uint16_t>(lane * kLaneStrideWords + j);
-                }
-                __syncwarp();
+                    int position = inclusive - mine - roundStart;
+                    uint32_t pending = bandMask;
+                    while (pending != 0)
+                    {
+                        const int j = __ffs(static_cast<int>(pending)) - 1;
+                        pending &= pending - 1;
+                        if (position >= 0 && position < kQueueCapacity)
+                        {
+                            queue[position] = static_cast<uint16_t>(lane * kLaneStrideWords + j);
+                        }
+                        ++position;
+                    }
+                    __syncwarp();
+                    const int count = min(total - roundStart, kQueueCapacity);
 #pragma unroll 1
-                for (int q = lane; q < total; q += 32)
-                {
-                    const uint32_t slot = queue[q];
-                    stage[slot] = ExactCurveCode<CURVE == kCurveClip ? kCurveLinearToPQ : CURVE>(__uint_as_float(stage[slot]), p.pqMultiplier,
-                                                                                              p.maxCodeFloat, t);
+                    for (int q = lane; q < count; q += 32)
+                    {
+                        const uint32_t slot = queue[q];
+                        stage[slot] = ExactCurveCode<CURVE == kCurveClip ? kCurveLinearToPQ : CURVE>(__uint_as_float(stage[slot]), p.pqMultiplier,
+                                                                                                  p.maxCodeFloat, t);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
                 if (bandMask != 0)
                 {
 #pragma unroll

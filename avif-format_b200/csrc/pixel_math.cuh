@@ -235,20 +235,23 @@ AVIF_HD void ForwardPixel(const ForwardMatrix& m, uint32_t rc, uint32_t gc, uint
     cr = (r - y) * m.crScale;
 }
 
-AVIF_HD uint32_t QuantiseLuma(float y, int maxCode)
+// clamp((int)(v), 0, maxCode).  On the device the float -> unsigned conversion saturates negatives (and NaN) to
+// 0 -- the same value the signed conversion + lower clamp gives -- so one min() finishes the job.
+AVIF_HD uint32_t TruncateToCode(float v, int maxCode)
 {
-    int v = static_cast<int>(y + 0.5f);
-    v = (v < 0) ? 0 : ((v > maxCode) ? maxCode : v);
-    return static_cast<uint32_t>(v);
+#if defined(__CUDA_ARCH__)
+    return min(__float2uint_rz(v), static_cast<uint32_t>(maxCode));
+#else
+    int i = static_cast<int>(v);
+    i = (i < 0) ? 0 : ((i > maxCode) ? maxCode : i);
+    return static_cast<uint32_t>(i);
+#endif
 }
 
+AVIF_HD uint32_t QuantiseLuma(float y, int maxCode) { return TruncateToCode(y + 0.5f, maxCode); }
+
 // chromaOffset = (float)(1 << (depth-1)), or 0 for the identity matrix.
-AVIF_HD uint32_t QuantiseChroma(float c, float chromaOffset, int maxCode)
-{
-    int v = static_cast<int>((c + chromaOffset) + 0.5f);
-    v = (v < 0) ? 0 : ((v > maxCode) ? maxCode : v);
-    return static_cast<uint32_t>(v);
-}
+AVIF_HD uint32_t QuantiseChroma(float c, float chromaOffset, int maxCode) { return TruncateToCode((c + chromaOffset) + 0.5f, maxCode); }
 
 // ---- decode side: YuvLookupTables.cpp / YuvDecode.cpp -----------------------------------------------------
 

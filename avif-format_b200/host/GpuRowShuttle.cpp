@@ -1,0 +1,492 @@
+// GpuRowShuttle.cpp -- see GpuRowShuttle.h.  Host-side C++ only: every pixel goes through the C ABI of
+// libavifgpu.so (include/avifgpu.h); this file owns the FormatRecord protocol, the heif_image plumbing and the
+// translation of status codes back into the exceptions the plug-in's session functions catch
+// (Write.cpp:345-364, Read.cpp:659-678).
+#include "GpuRowShuttle.h"
+
+#include "../../include/avifgpu.h"
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+
+namespace
+{
+    avifgpu_context* g_context = nullptr;
+    int32 g_rowsPerBlock = 512;
+
+    // avifgpu status -> the exception the reference would have thrown for the same condition.
+    void ThrowIfFailed(avifgpu_context* ctx, int status)
+    {
+        if (status == AVIFGPU_OK)
+        {
+            return;
+        }
+        const std::string message = avifgpu_last_error(ctx);
+        switch (status)
+        {
+        case AVIFGPU_ERR_BAD_PARAM: throw OSErrException(formatBadParameters);
+        case AVIFGPU_ERR_NO_DEVICE: throw OSErrException(errPlugInHostInsufficient);
+        case AVIFGPU_ERR_OOM: throw std::bad_alloc();
+        case AVIFGPU_ERR_CANCELED: throw OSErrException(userCanceledErr);
+        default: throw std::runtime_error(message.empty() ? avifgpu_status_string(status) : message);
+        }
+    }
+
+    // Utilities.cpp:382-416
+    VPoint GetImageSizeOf(const FormatRecordPtr formatRecord)
+    {
+        VPoint size;
+        if (formatRecord->HostSupports32BitCoordinates && formatRecord->PluginUsing32BitCoordinates)
+        {
+            size.h = formatRecord->imageSize32.h;
+            size.v = formatRecord->imageSize32.v;
+        }
+        else
+        {
+            size.h = formatRecord->imageSize.h;
+            size.v = formatRecord->imageSize.v;
+        }
+        return size;
+    }
+
+    void SetRectOf(FormatRecordPtr formatRecord, int32 top, int32 left, int32 bottom, int32 right)
+    {
+        if (formatRecord->HostSupports32BitCoordinates && formatRecord->PluginUsing32BitCoordinates)
+        {
+            formatRecord->theRect32.top = top;
+            formatRecord->theRect32.left = left;
+            formatRecord->theRect32.bottom = bottom;
+            formatRecord->theRect32.right = right;
+        }
+        else
+        {
+            formatRecord->theRect.top = static_cast<int16>(top);
+            formatRecord->theRect.left = static_cast<int16>(left);
+            formatRecord->theRect.bottom = static_cast<int16>(bottom);
+            formatRecord->theRect.right = static_cast<int16>(right);
+        }
+    }
+
+    int HeifBitDepth(ImageBitDepth depth)
+    {
+        // WriteHeifImage.cpp:41-61
+        switch (depth)
+        {
+        case ImageBitDepth::Eight: return 8;
+        case ImageBitDepth::Ten: return 10;
+        case ImageBitDepth::Twelve: return 12;
+        default: throw OSErrException(formatCannotRead);
+        }
+    }
+
+    // Pinned staging rows owned by the library; replaces the plug-in's one-row ScopedBufferSuiteBuffer.
+    class PinnedRows
+    {
+    public:
+        PinnedRows(avifgpu_context* ctx, size_t bytes) : context(ctx)
+        {
+            ThrowIfFailed(ctx, avifgpu_host_alloc(ctx, bytes, &memory));
+        }
+        ~PinnedRows() { avifgpu_host_free(context, memory); }
+        PinnedRows(const PinnedRows&) = delete;
+        PinnedRows& operator=(const PinnedRows&) = delete;
+        void* get() const { return memory; }
+
+    private:
+        avifgpu_context* context;
+        void* memory = nullptr;
+    };
+
+    int32 BlockRows(int32 height)
+    {
+        int32 rows = std::max<int32>(g_rowsPerBlock & ~1, 2);
+        return std::min(rows, std::max<int32>(height, 1));
+    }
+
+    // Restores the caller's formatRecord->data / rowBytes when the shuttle leaves (normally or by exception).
+    struct RecordDataGuard
+    {
+        FormatRecordPtr record;
+        void* data;
+        int32 rowBytes;
+        explicit RecordDataGuard(FormatRecordPtr r) : record(r), data(r->data), rowBytes(r->rowBytes) {}
+        ~RecordDataGuard()
+        {
+            record->data = data;
+            record->rowBytes = rowBytes;
+        }
+    };
+
+    avifgpu_nclx ToNclx(const heif_color_profile_nclx* profile)
+    {
+        avifgpu_nclx out{};
+        if (profile != nullptr)
+        {
+            out.present = 1;
+            out.color_primaries = static_cast<int32_t>(profile->color_primaries);
+            out.transfer_characteristics = static_cast<int32_t>(profile->transfer_characteristics);
+            out.matrix_coefficients = static_cast<int32_t>(profile->matrix_coefficients);
+            out.full_range_flag = profile->full_range_flag ? 1 : 0;
+        }
+        return out;
+    }
+
+    // ---- encode --------------------------------------------------------------------------------------------------
+
+    ScopedHeifImage EncodeThroughGpu(FormatRecordPtr formatRecord, AlphaState alphaState, const VPoint& imageSize,
+                                     const SaveUIOptions& saveOptions, int hostDepth, bool gray)
+    {
+        avifgpu_context* ctx = avifgpu_host::SharedContext();
+        const bool hasAlpha = alphaState != AlphaState::None;
+        const int bitDepth = HeifBitDepth(saveOptions.imageBitDepth);
+        const int channels = (gray ? 1 : 3) + (hasAlpha ? 1 : 0);
+
+        avifgpu_encode_desc desc{};
+        desc.struct_size = sizeof(desc);
+        desc.width = imageSize.h;
+        desc.height = imageSize.v;
+        desc.host_depth = hostDepth;
+        desc.host_channels = channels;
+        desc.alpha_state = static_cast<int32_t>(alphaState);
+        desc.image_bit_depth = bitDepth;
+        desc.transfer = static_cast<int32_t>(saveOptions.hdrTransferFunction);
+        desc.pq_peak_nits = saveOptions.pq.nominalPeakBrightness;
+        desc.down_filter = AVIFGPU_DOWN_FILTER_BOX;
+        desc.gray16_curve = AVIFGPU_GRAY16_LUT;
+
+        heif_image* raw = nullptr;
+        heif_chroma chroma = heif_chroma_monochrome;
+        if (gray)
+        {
+            desc.layout = AVIFGPU_LAYOUT_REFERENCE; // Y (+ Alpha) planes, WriteHeifImage.cpp:175-194
+            LibHeifException::ThrowIfError(heif_image_create(imageSize.h, imageSize.v, heif_colorspace_monochrome, heif_chroma_monochrome, &raw));
+        }
+        else
+        {
+            desc.layout = AVIFGPU_LAYOUT_PLANAR_YCBCR;
+            // Write.cpp:96-120: lossless forces 4:4:4; otherwise the save option picks the encoder's chroma format.
+            if (saveOptions.lossless)
+            {
+                chroma = heif_chroma_444;
+            }
+            else
+            {
+                switch (saveOptions.chromaSubsampling)
+                {
+                case ChromaSubsampling::Yuv420: chroma = heif_chroma_420; break;
+                case ChromaSubsampling::Yuv422: chroma = heif_chroma_422; break;
+                case ChromaSubsampling::Yuv444: chroma = heif_chroma_444; break;
+                default: throw OSErrException(formatBadParameters);
+                }
+            }
+            desc.chroma = static_cast<int32_t>(chroma);
+            // WriteMetadata.cpp:107-149: the matrix the file will be tagged with
+            desc.nclx.present = 1;
+            desc.nclx.full_range_flag = 1;
+            if (hostDepth == 32 && saveOptions.hdrTransferFunction != ColorTransferFunction::Clip)
+            {
+                desc.nclx.color_primaries = 9;
+                desc.nclx.transfer_characteristics = saveOptions.hdrTransferFunction == ColorTransferFunction::PQ ? 16 : 17;
+                desc.nclx.matrix_coefficients = 9;
+            }
+            else
+            {
+                desc.nclx.color_primaries = 1;
+                desc.nclx.transfer_characteristics = 13;
+                desc.nclx.matrix_coefficients = 6;
+            }
+            if (saveOptions.lossless)
+            {
+                desc.nclx.matrix_coefficients = 0;
+            }
+            LibHeifException::ThrowIfError(heif_image_create(imageSize.h, imageSize.v, heif_colorspace_YCbCr, chroma, &raw));
+        }
+        ScopedHeifImage image(raw);
+
+        avifgpu_planes planes{};
+        auto addPlane = [&](heif_channel channel, int index, int width, int height)
+        {
+            LibHeifException::ThrowIfError(heif_image_add_plane(image.get(), channel, width, height, bitDepth));
+            int stride = 0;
+            planes.data[index] = heif_image_get_plane(image.get(), channel, &stride);
+            planes.stride[index] = stride;
+        };
+        addPlane(heif_channel_Y, 0, imageSize.h, imageSize.v);
+        if (!gray)
+        {
+            const int cw = (chroma == heif_chroma_444) ? imageSize.h : (imageSize.h + 1) / 2;
+            const int ch = (chroma == heif_chroma_420) ? (imageSize.v + 1) / 2 : imageSize.v;
+            addPlane(heif_channel_Cb, 1, cw, ch);
+            addPlane(heif_channel_Cr, 2, cw, ch);
+        }
+        if (hasAlpha)
+        {
+            addPlane(heif_channel_Alpha, 3, imageSize.h, imageSize.v);
+        }
+
+        ThrowIfFailed(ctx, avifgpu_prepare_encode(ctx, &desc, nullptr));
+
+        const int64_t rowBytes = static_cast<int64_t>(imageSize.h) * avifgpu_encode_host_col_bytes(&desc);
+        if (rowBytes > std::numeric_limits<int32>::max())
+        {
+            throw std::bad_alloc(); // Write.cpp:286-295
+        }
+        const int32 blockRows = BlockRows(imageSize.v);
+        PinnedRows staging(ctx, static_cast<size_t>(std::max<int64_t>(rowBytes, 1)) * blockRows);
+        RecordDataGuard guard(formatRecord);
+        formatRecord->data = staging.get();
+        formatRecord->rowBytes = static_cast<int32>(rowBytes);
+
+        for (int32 top = 0; top < imageSize.v; top += blockRows)
+        {
+            if (formatRecord->abortProc())
+            {
+                throw OSErrException(userCanceledErr); // WriteHeifImage.cpp:208-211, once per block here
+            }
+            const int32 bottom = std::min(top + blockRows, imageSize.v);
+            SetRectOf(formatRecord, top, 0, bottom, imageSize.h);
+            OSErrException::ThrowIfError(formatRecord->advanceState()); // the host fills rows [top, bottom)
+            ThrowIfFailed(ctx, avifgpu_encode_rows(ctx, &desc, staging.get(), rowBytes, top, bottom - top, &planes));
+        }
+        return image;
+    }
+
+    // ---- decode --------------------------------------------------------------------------------------------------
+
+    void DecodeThroughGpu(const heif_image* image, AlphaState alphaState, const heif_color_profile_nclx* nclxProfile,
+                          const LoadUIOptions* loadOptions, FormatRecordPtr formatRecord, int hostDepth, bool gray)
+    {
+        avifgpu_context* ctx = avifgpu_host::SharedContext();
+        const VPoint imageSize = GetImageSizeOf(formatRecord);
+        const bool hasAlpha = alphaState != AlphaState::None;
+
+        avifgpu_decode_desc desc{};
+        desc.struct_size = sizeof(desc);
+        desc.width = imageSize.h;
+        desc.height = imageSize.v;
+        desc.alpha_state = static_cast<int32_t>(alphaState);
+        desc.host_depth = hostDepth;
+        desc.nclx = ToNclx(nclxProfile);
+        if (loadOptions != nullptr)
+        {
+            desc.hlg_apply_ootf = loadOptions->hlg.applyOOTF ? 1 : 0;
+            desc.hlg_display_gamma = loadOptions->hlg.displayGamma;
+            desc.hlg_peak_nits = loadOptions->hlg.nominalPeakBrightness;
+            desc.pq_peak_nits = loadOptions->pq.nominalPeakBrightness;
+        }
+        else
+        {
+            desc.hlg_display_gamma = 1.2f;
+            desc.hlg_peak_nits = 1000;
+            desc.pq_peak_nits = 80;
+        }
+
+        avifgpu_planes planes{};
+        auto plane = [&](heif_channel channel, int index)
+        {
+            int stride = 0;
+            planes.data[index] = const_cast<uint8_t*>(heif_image_get_plane_readonly(image, channel, &stride));
+            planes.stride[index] = stride;
+            if (planes.data[index] == nullptr)
+            {
+                throw std::runtime_error("The image is missing a channel.");
+            }
+        };
+        heif_channel first = heif_channel_Y;
+        if (gray)
+        {
+            desc.colorspace = AVIFGPU_COLORSPACE_MONOCHROME;
+            desc.chroma = AVIFGPU_CHROMA_MONOCHROME;
+            plane(heif_channel_Y, 0);
+        }
+        else
+        {
+            const heif_colorspace colorspace = heif_image_get_colorspace(image);
+            if (colorspace == heif_colorspace_YCbCr)
+            {
+                desc.colorspace = AVIFGPU_COLORSPACE_YCBCR;
+                desc.chroma = static_cast<int32_t>(heif_image_get_chroma_format(image));
+                plane(heif_channel_Y, 0);
+                plane(heif_channel_Cb, 1);
+                plane(heif_channel_Cr, 2);
+                const int luma = heif_image_get_bits_per_pixel_range(image, heif_channel_Y);
+                if (heif_image_get_bits_per_pixel_range(image, heif_channel_Cb) != luma ||
+                    heif_image_get_bits_per_pixel_range(image, heif_channel_Cr) != luma)
+                {
+                    throw std::runtime_error("The chroma channel bit depth does not match the main image."); // ReadHeifImage.cpp:93-97
+                }
+            }
+            else if (colorspace == heif_colorspace_RGB)
+            {
+                desc.colorspace = AVIFGPU_COLORSPACE_RGB;
+                desc.chroma = AVIFGPU_CHROMA_444;
+                first = heif_channel_R;
+                plane(heif_channel_R, 0);
+                plane(heif_channel_G, 1);
+                plane(heif_channel_B, 2);
+                const int red = heif_image_get_bits_per_pixel_range(image, heif_channel_R);
+                if (heif_image_get_bits_per_pixel_range(image, heif_channel_G) != red ||
+                    heif_image_get_bits_per_pixel_range(image, heif_channel_B) != red)
+                {
+                    throw std::runtime_error("The color channel bit depths do not match."); // ReadHeifImage.cpp:591-595
+                }
+            }
+            else
+            {
+                throw std::runtime_error("Unsupported image color space, expected RGB."); // ReadHeifImage.cpp:575-578
+            }
+        }
+        desc.bit_depth = heif_image_get_bits_per_pixel_range(image, first);
+        if (hasAlpha)
+        {
+            plane(heif_channel_Alpha, 3);
+            if (heif_image_get_bits_per_pixel_range(image, heif_channel_Alpha) != desc.bit_depth)
+            {
+                throw std::runtime_error("The alpha channel bit depth does not match the main image channels.");
+            }
+        }
+
+        // SetupFormatRecord, ReadHeifImage.cpp:31-50
+        formatRecord->loPlane = 0;
+        formatRecord->hiPlane = static_cast<int16>(formatRecord->planes - 1);
+        formatRecord->planeBytes = static_cast<int16>((formatRecord->depth + 7) / 8);
+        formatRecord->colBytes = static_cast<int16>(formatRecord->planes * formatRecord->planeBytes);
+        const int64_t rowBytes = static_cast<int64_t>(imageSize.h) * formatRecord->colBytes;
+        if (rowBytes > std::numeric_limits<int32>::max())
+        {
+            throw std::bad_alloc();
+        }
+        if (hostDepth == 16)
+        {
+            // ReadHeifImage.cpp:206 (YCbCr: maxData, sic), :499 (gray), :744 (planar RGB: the source range)
+            if (gray)
+            {
+                formatRecord->maxValue = 32768;
+            }
+            else if (desc.colorspace == AVIFGPU_COLORSPACE_YCBCR)
+            {
+                formatRecord->maxData = 32768;
+            }
+            else
+            {
+                formatRecord->maxValue = (1 << desc.bit_depth) - 1;
+            }
+        }
+
+        const int32 blockRows = BlockRows(imageSize.v);
+        PinnedRows staging(ctx, static_cast<size_t>(std::max<int64_t>(rowBytes, 1)) * blockRows);
+        RecordDataGuard guard(formatRecord);
+        formatRecord->data = staging.get();
+        formatRecord->rowBytes = static_cast<int32>(rowBytes);
+
+        for (int32 top = 0; top < imageSize.v; top += blockRows)
+        {
+            const int32 bottom = std::min(top + blockRows, imageSize.v);
+            ThrowIfFailed(ctx, avifgpu_decode_rows(ctx, &desc, &planes, top, bottom - top, staging.get(), rowBytes));
+            SetRectOf(formatRecord, top, 0, bottom, imageSize.h);
+            OSErrException::ThrowIfError(formatRecord->advanceState()); // the host consumes rows [top, bottom)
+        }
+    }
+}
+
+namespace avifgpu_host
+{
+
+avifgpu_context* SharedContext()
+{
+    if (g_context == nullptr)
+    {
+        avifgpu_context* created = nullptr;
+        const int status = avifgpu_create(0, &created);
+        if (status != AVIFGPU_OK)
+        {
+            throw OSErrException(errPlugInHostInsufficient);
+        }
+        g_context = created;
+    }
+    return g_context;
+}
+
+void ReleaseSharedContext()
+{
+    if (g_context != nullptr)
+    {
+        avifgpu_destroy(g_context);
+        g_context = nullptr;
+    }
+}
+
+void SetRowsPerBlock(int32 rows) { g_rowsPerBlock = std::max<int32>(rows, 2); }
+
+} // namespace avifgpu_host
+
+ScopedHeifImage CreateHeifImageGrayEightBit(FormatRecordPtr formatRecord, AlphaState alphaState, const VPoint& imageSize, const SaveUIOptions& saveOptions)
+{
+    return EncodeThroughGpu(formatRecord, alphaState, imageSize, saveOptions, 8, true);
+}
+
+ScopedHeifImage CreateHeifImageGraySixteenBit(FormatRecordPtr formatRecord, AlphaState alphaState, const VPoint& imageSize, const SaveUIOptions& saveOptions)
+{
+    return EncodeThroughGpu(formatRecord, alphaState, imageSize, saveOptions, 16, true);
+}
+
+ScopedHeifImage CreateHeifImageGrayThirtyTwoBit(FormatRecordPtr formatRecord, AlphaState alphaState, const VPoint& imageSize, const SaveUIOptions& saveOptions)
+{
+    return EncodeThroughGpu(formatRecord, alphaState, imageSize, saveOptions, 32, true);
+}
+
+ScopedHeifImage CreateHeifImageRGBEightBit(FormatRecordPtr formatRecord, AlphaState alphaState, const VPoint& imageSize, const SaveUIOptions& saveOptions)
+{
+    return EncodeThroughGpu(formatRecord, alphaState, imageSize, saveOptions, 8, false);
+}
+
+ScopedHeifImage CreateHeifImageRGBSixteenBit(FormatRecordPtr formatRecord, AlphaState alphaState, const VPoint& imageSize, const SaveUIOptions& saveOptions)
+{
+    return EncodeThroughGpu(formatRecord, alphaState, imageSize, saveOptions, 16, false);
+}
+
+ScopedHeifImage CreateHeifImageRGBThirtyTwoBit(FormatRecordPtr formatRecord, AlphaState alphaState, const VPoint& imageSize, const SaveUIOptions& saveOptions)
+{
+    return EncodeThroughGpu(formatRecord, alphaState, imageSize, saveOptions, 32, false);
+}
+
+void ReadHeifImageGrayEightBit(const heif_image* image, AlphaState alphaState, const heif_color_profile_nclx* nclxProfile, FormatRecordPtr formatRecord)
+{
+    DecodeThroughGpu(image, alphaState, nclxProfile, nullptr, formatRecord, 8, true);
+}
+
+void ReadHeifImageGraySixteenBit(const heif_image* image, AlphaState alphaState, const heif_color_profile_nclx* nclxProfile, FormatRecordPtr formatRecord)
+{
+    DecodeThroughGpu(image, alphaState, nclxProfile, nullptr, formatRecord, 16, true);
+}
+
+void ReadHeifImageGrayThirtyTwoBit(const heif_image* image, AlphaState alphaState, const heif_color_profile_nclx* nclxProfile, const LoadUIOptions& loadOptions, FormatRecordPtr formatRecord)
+{
+    if (nclxProfile == nullptr)
+    {
+        throw std::runtime_error("The nclxProfile is null."); // ReadHeifImage.cpp:870-873
+    }
+    DecodeThroughGpu(image, alphaState, nclxProfile, &loadOptions, formatRecord, 32, true);
+}
+
+void ReadHeifImageRGBEightBit(const heif_image* image, AlphaState alphaState, const heif_color_profile_nclx* nclxProfile, FormatRecordPtr formatRecord)
+{
+    DecodeThroughGpu(image, alphaState, nclxProfile, nullptr, formatRecord, 8, false);
+}
+
+void ReadHeifImageRGBSixteenBit(const heif_image* image, AlphaState alphaState, const heif_color_profile_nclx* nclxProfile, FormatRecordPtr formatRecord)
+{
+    DecodeThroughGpu(image, alphaState, nclxProfile, nullptr, formatRecord, 16, false);
+}
+
+void ReadHeifImageRGBThirtyTwoBit(const heif_image* image, AlphaState alphaState, const heif_color_profile_nclx* nclxProfile, const LoadUIOptions& loadOptions, FormatRecordPtr formatRecord)
+{
+    if (nclxProfile == nullptr)
+    {
+        throw std::runtime_error("The nclxProfile is null."); // ReadHeifImage.cpp:956-959
+    }
+    DecodeThroughGpu(image, alphaState, nclxProfile, &loadOptions, formatRecord, 32, false);
+}
