@@ -22,11 +22,18 @@ namespace avifgpu
 int LaunchEncodeGeneric(const EncodeParams& params, int hostDepth, void* stream);
 int LaunchDecodeGeneric(const DecodeParams& params, void* stream);
 int LaunchEncodeFast(const EncodeParams& params, int hostDepth, void* stream);   // 0 = not applicable
+int LaunchEncodeFastInteger(const EncodeParams& params, int hostDepth, void* stream); // 0 = not applicable
+cudaError_t BuildGray16Lut(uint16_t* deviceLut, int smpte428, uint32_t maxCode, void* stream);
 int LaunchDecodeFast(const DecodeParams& params, void* stream);                  // 0 = not applicable
 
 int LaunchEncode(const EncodeParams& params, int hostDepth, void* stream)
 {
-    const int fast = LaunchEncodeFast(params, hostDepth, stream);
+    int fast = LaunchEncodeFast(params, hostDepth, stream);
+    if (fast != 0)
+    {
+        return fast;
+    }
+    fast = LaunchEncodeFastInteger(params, hostDepth, stream);
     if (fast != 0)
     {
         return fast;
@@ -79,6 +86,48 @@ struct avifgpu_context
     Buffer pinnedPlanes[kPipelineStreams][AVIFGPU_MAX_PLANES];
     Buffer transferScratch[2];
     std::vector<CurveTable*> curveTables; // exact step tables, built on first use per (curve, param, depth)
+    struct Gray16Lut
+    {
+        int depth = 0;
+        int smpte428 = 0;
+        uint16_t* device = nullptr;
+    };
+    std::vector<Gray16Lut> gray16Luts;
+
+    // The 65536-entry code table of a Gray16 host configuration (built on the device on first use), or nullptr.
+    const uint16_t* Gray16LutFor(const avifgpu_encode_desc& d)
+    {
+        if (d.host_depth != 16 || d.host_channels != 1 || d.layout != AVIFGPU_LAYOUT_REFERENCE || d.image_bit_depth <= 8)
+        {
+            return nullptr;
+        }
+        const int smpte428 = d.gray16_curve == AVIFGPU_GRAY16_SMPTE428 ? 1 : 0;
+        for (const Gray16Lut& l : gray16Luts)
+        {
+            if (l.depth == d.image_bit_depth && l.smpte428 == smpte428)
+            {
+                return l.device;
+            }
+        }
+        Gray16Lut lut;
+        lut.depth = d.image_bit_depth;
+        lut.smpte428 = smpte428;
+        if (cudaMalloc(&lut.device, 65536 * sizeof(uint16_t)) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return nullptr;
+        }
+        if (BuildGray16Lut(lut.device, smpte428, (1u << d.image_bit_depth) - 1u, streams[0]) != cudaSuccess ||
+            cudaStreamSynchronize(streams[0]) != cudaSuccess)
+        {
+            cudaGetLastError();
+            cudaFree(lut.device);
+            return nullptr;
+        }
+        launches += 1;
+        gray16Luts.push_back(lut);
+        return lut.device;
+    }
 
     // The verified step table for a float-host encode description, or nullptr when the description does not use
     // one / the table could not be verified (then the generic exact kernel serves the configuration).
@@ -344,6 +393,10 @@ AVIFGPU_EXPORT void avifgpu_destroy(avifgpu_context* ctx)
         FreeCurveTable(t);
         delete t;
     }
+    for (auto& l : ctx->gray16Luts)
+    {
+        cudaFree(l.device);
+    }
     delete ctx;
 }
 
@@ -520,6 +573,7 @@ AVIFGPU_EXPORT int avifgpu_encode_rows_device(avifgpu_context* ctx, const avifgp
     {
         p.curveTable = table->valid ? &table->view : nullptr;
     }
+    p.gray16Lut = ctx->Gray16LutFor(*desc);
     const int launched = LaunchEncode(p, desc->host_depth, cuda_stream);
     if (launched < 0)
     {
@@ -645,6 +699,7 @@ AVIFGPU_EXPORT int avifgpu_encode_rows(avifgpu_context* ctx, const avifgpu_encod
     {
         base.curveTable = table->valid ? &table->view : nullptr;
     }
+    base.gray16Lut = ctx->Gray16LutFor(*desc);
     const int64_t rowPayload = static_cast<int64_t>(desc->width) * EncodeHostColBytes(*desc);
     const int64_t deviceRowStride = (rowPayload + 255) & ~255ll;
     const bool rowsPinned = IsPinned(host_rows);
@@ -903,6 +958,7 @@ AVIFGPU_EXPORT int avifgpu_prepare_encode(avifgpu_context* ctx, const avifgpu_en
     }
     DeviceGuard guard(ctx->device);
     CurveTable* table = ctx->CurveTableFor(*desc);
+    ctx->Gray16LutFor(*desc);
     if (out_stats != nullptr)
     {
         std::memset(out_stats, 0, sizeof(*out_stats));

@@ -39,6 +39,7 @@ struct EncodeParams
     float chromaOffset;
     // Host-side extras for the launcher (ignored by the kernels):
     const CurveTableView* curveTable; // verified exact step table for `transfer`, or nullptr
+    const uint16_t* gray16Lut;        // 65536-entry code table for Gray16 hosts (device memory), or nullptr
     int32_t smCount;
 };
 

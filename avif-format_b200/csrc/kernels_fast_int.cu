@@ -1,0 +1,447 @@
+// kernels_fast_int.cu -- tuned kernels for the 16-bit integer hosts (BASELINE configs 4 and 5).  Both are pure
+// streaming conversions (a few float operations per sample), so the design goal is simply to keep HBM busy:
+// 128-bit loads and stores, several of them in flight per thread, no integer<->float conversion instructions
+// (they issue on the quarter-rate pipe and would cap config 4 just below the HBM roofline).
+//
+//   Gray16 -> Y plane          one 65536-entry uint16 table in shared memory (128 KB), built once per
+//                              configuration by evaluating the exact per-sample formula for every input; a thread
+//                              converts 8 samples per 128-bit load.
+//   RGB(A)16 -> planar YCbCr   the 16-bit -> N-bit mapping is evaluated arithmetically (it is four float
+//                              operations), the forward matrix and the 4:2:2 / 4:2:0 down-filter are fused, a
+//                              thread converts 8 pixels (x 2 rows for 4:2:0).
+#include "kernel_params.h"
+#include "../../include/avifgpu.h"
+
+#include <cuda_runtime.h>
+
+namespace avifgpu
+{
+
+using namespace avifpix;
+using avifmath::LibmTables;
+
+namespace
+{
+
+// ---- Gray16 --------------------------------------------------------------------------------------------------------
+
+constexpr int kLutThreads = 1024;
+constexpr int kLutEntries = 65536;
+
+// Fills lut[v] for every 16-bit host sample with the exact code of the configuration:
+//   reference LUT path   clamp((int)((v / 32768f) * max + 0.5f), 0, max)                       WriteHeifImage.cpp:140-166
+//   SMPTE 428 curve      (u16)clamp(LinearToSMPTE428(v / 32768f) * max, 0, max)                 DESIGN.md "Config 5"
+__global__ void __launch_bounds__(256) BuildGray16LutKernel(uint16_t* __restrict__ lut, int smpte428, uint32_t maxCode)
+{
+    __shared__ uint64_t libmStorage[96];
+    const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const float maxCodeFloat = static_cast<float>(maxCode);
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < kLutEntries; v += gridDim.x * blockDim.x)
+    {
+        uint32_t code;
+        if (smpte428)
+        {
+            code = FloatToCode(LinearToSMPTE428(static_cast<float>(v) / 32768.0f, t), maxCodeFloat);
+        }
+        else
+        {
+            code = DepthLutEntry(v, 32768.0f, maxCode);
+        }
+        lut[v] = static_cast<uint16_t>(code);
+    }
+}
+
+struct Gray16Params
+{
+    const uint8_t* rows;
+    int64_t rowStride;
+    uint8_t* planeY;
+    int64_t strideY;
+    int32_t chunksPerRow; // 8 samples each
+    int32_t rowCount;
+    const uint16_t* lut;  // 65536 entries, global memory
+};
+
+__device__ __forceinline__ uint4 LookupEight(const uint16_t* __restrict__ lut, uint4 in)
+{
+    uint4 out;
+    out.x = lut[in.x & 0xffffu] | (static_cast<uint32_t>(lut[in.x >> 16]) << 16);
+    out.y = lut[in.y & 0xffffu] | (static_cast<uint32_t>(lut[in.y >> 16]) << 16);
+    out.z = lut[in.z & 0xffffu] | (static_cast<uint32_t>(lut[in.z >> 16]) << 16);
+    out.w = lut[in.w & 0xffffu] | (static_cast<uint32_t>(lut[in.w >> 16]) << 16);
+    return out;
+}
+
+__global__ void __launch_bounds__(kLutThreads, 1) EncodeGray16LutKernel(const Gray16Params p)
+{
+    extern __shared__ __align__(16) uint16_t sharedLut[];
+    {
+        const uint4* source = reinterpret_cast<const uint4*>(p.lut);
+        uint4* target = reinterpret_cast<uint4*>(sharedLut);
+        for (int i = threadIdx.x; i < kLutEntries * 2 / 16; i += blockDim.x)
+        {
+            target[i] = source[i];
+        }
+    }
+    __syncthreads();
+
+    constexpr int kUnroll = 4;
+    const long long chunks = static_cast<long long>(p.chunksPerRow) * p.rowCount;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; base < chunks; base += stride * kUnroll)
+    {
+        uint4 in[kUnroll];
+        long long outOffset[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+        {
+            const long long chunk = base + u * stride;
+            if (chunk < chunks)
+            {
+                const long long row = chunk / p.chunksPerRow;
+                const long long column = chunk - row * p.chunksPerRow;
+                in[u] = __ldcs(reinterpret_cast<const uint4*>(p.rows + row * p.rowStride + column * 16));
+                outOffset[u] = row * p.strideY + column * 16;
+            }
+            else
+            {
+                in[u] = make_uint4(0u, 0u, 0u, 0u);
+                outOffset[u] = -1;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+        {
+            if (outOffset[u] >= 0)
+            {
+                __stcs(reinterpret_cast<uint4*>(p.planeY + outOffset[u]), LookupEight(sharedLut, in[u]));
+            }
+        }
+    }
+}
+
+// ---- RGB(A)16 -> planar YCbCr ---------------------------------------------------------------------------------------
+
+constexpr int kRgbThreads = 256;
+constexpr float kTwo23 = 8388608.0f;
+
+// (float)v for v < 2^23 without the conversion instruction.
+__device__ __forceinline__ float UintToFloatExact(uint32_t v) { return __uint_as_float(0x4b000000u | v) - kTwo23; }
+
+// 2^23 + min(trunc(t), maxCode) as a float, for 0 <= t < 2^23: adding 2^23 with round-toward-zero leaves floor(t) in
+// the low mantissa bits.  Bit-identical to (int)t followed by the upper clamp of the reference's LUT builder.
+__device__ __forceinline__ float BiasedTrunc(float t, float biasedMax) { return fminf(__fadd_rz(t, kTwo23), biasedMax); }
+
+struct Rgb16Params
+{
+    const uint8_t* rows;
+    int64_t rowStride;
+    uint8_t* plane[4];
+    int64_t stride[4];
+    int32_t groupsPerRow; // 8 pixels each
+    int32_t rowCount;     // even when YS == 1
+    float maxCodeFloat;
+    float biasedMax;      // 2^23 + maxCode
+    ForwardMatrix matrix;
+    float chromaOffset;
+    int32_t topLeft;
+};
+
+// Host sample (0..32768, or beyond: the formula is defined to continue) -> 2^23 + code, as a float.
+__device__ __forceinline__ float SampleToBiasedCode(uint32_t v, const Rgb16Params& p)
+{
+    // WriteHeifImage.cpp:140-166: (int)((v / 32768f) * max + 0.5f), clamped
+    const float t = ((UintToFloatExact(v) * (1.0f / 32768.0f)) * p.maxCodeFloat) + 0.5f;
+    return BiasedTrunc(t, p.biasedMax);
+}
+
+__device__ __forceinline__ uint32_t BiasedToCode(float biased) { return __float_as_uint(biased) & 0x7fffffu; }
+
+template <int CHANNELS, int XS, int YS>
+__global__ void __launch_bounds__(kRgbThreads) EncodeRgb16PlanarKernel(const Rgb16Params p)
+{
+    constexpr int kRows = 1 + YS;
+    constexpr int kWordsPerRow = CHANNELS * 4; // 8 pixels x CHANNELS x 2 bytes / 4
+    const long long groups = static_cast<long long>(p.groupsPerRow) * ((p.rowCount + YS) >> YS);
+    for (long long group = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; group < groups;
+         group += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const long long rowPair = group / p.groupsPerRow;
+        const int column = static_cast<int>(group - rowPair * p.groupsPerRow); // in units of 8 pixels
+        const long long y0 = rowPair << YS;
+
+        uint32_t words[kRows][kWordsPerRow];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+        {
+            const uint4* source = reinterpret_cast<const uint4*>(p.rows + (y0 + r) * p.rowStride + static_cast<long long>(column) * (kWordsPerRow * 4));
+#pragma unroll
+            for (int q = 0; q < kWordsPerRow / 4; ++q)
+            {
+                const uint4 w = __ldcs(source + q);
+                words[r][4 * q + 0] = w.x;
+                words[r][4 * q + 1] = w.y;
+                words[r][4 * q + 2] = w.z;
+                words[r][4 * q + 3] = w.w;
+            }
+        }
+
+        float cb[kRows][8], cr[kRows][8];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+        {
+            uint32_t yCodes[8];
+            uint32_t aCodes[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+            {
+                // sample k of the row sits in half-word k: word k/2, low or high half
+                auto sample = [&](int k) -> uint32_t
+                {
+                    const uint32_t w = words[r][k >> 1];
+                    return (k & 1) ? (w >> 16) : (w & 0xffffu);
+                };
+                const float rb = SampleToBiasedCode(sample(i * CHANNELS + 0), p);
+                const float gb = SampleToBiasedCode(sample(i * CHANNELS + 1), p);
+                const float bb = SampleToBiasedCode(sample(i * CHANNELS + 2), p);
+                const float rf = rb - kTwo23, gf = gb - kTwo23, bf = bb - kTwo23;
+                float yf;
+                if (p.matrix.identity)
+                {
+                    yf = gf;
+                    cb[r][i] = bf;
+                    cr[r][i] = rf;
+                }
+                else
+                {
+                    yf = ((p.matrix.kr * rf) + (p.matrix.kg * gf)) + (p.matrix.kb * bf);
+                    cb[r][i] = (bf - yf) * p.matrix.cbScale;
+                    cr[r][i] = (rf - yf) * p.matrix.crScale;
+                }
+                yCodes[i] = BiasedToCode(BiasedTrunc(yf + 0.5f, p.biasedMax));
+                if (CHANNELS == 4)
+                {
+                    aCodes[i] = BiasedToCode(SampleToBiasedCode(sample(i * CHANNELS + 3), p));
+                }
+            }
+            const long long offset = (y0 + r) * p.stride[0] + static_cast<long long>(column) * 16;
+            __stcs(reinterpret_cast<uint4*>(p.plane[0] + offset),
+                   make_uint4(yCodes[0] | (yCodes[1] << 16), yCodes[2] | (yCodes[3] << 16), yCodes[4] | (yCodes[5] << 16), yCodes[6] | (yCodes[7] << 16)));
+            if (CHANNELS == 4)
+            {
+                __stcs(reinterpret_cast<uint4*>(p.plane[3] + (y0 + r) * p.stride[3] + static_cast<long long>(column) * 16),
+                       make_uint4(aCodes[0] | (aCodes[1] << 16), aCodes[2] | (aCodes[3] << 16), aCodes[4] | (aCodes[5] << 16), aCodes[6] | (aCodes[7] << 16)));
+            }
+        }
+
+        // chroma: down-filter in float, then quantise (the offset is 0 for the identity matrix)
+        auto quantise = [&](float c) -> uint32_t { return BiasedToCode(BiasedTrunc((c + p.chromaOffset) + 0.5f, p.biasedMax)); };
+        if (XS == 0)
+        {
+#pragma unroll
+            for (int r = 0; r < kRows; ++r)
+            {
+                uint32_t cbCode[8], crCode[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                {
+                    cbCode[i] = quantise(cb[r][i]);
+                    crCode[i] = quantise(cr[r][i]);
+                }
+                const long long offset = static_cast<long long>(column) * 16;
+                __stcs(reinterpret_cast<uint4*>(p.plane[1] + (y0 + r) * p.stride[1] + offset),
+                       make_uint4(cbCode[0] | (cbCode[1] << 16), cbCode[2] | (cbCode[3] << 16), cbCode[4] | (cbCode[5] << 16), cbCode[6] | (cbCode[7] << 16)));
+                __stcs(reinterpret_cast<uint4*>(p.plane[2] + (y0 + r) * p.stride[2] + offset),
+                       make_uint4(crCode[0] | (crCode[1] << 16), crCode[2] | (crCode[3] << 16), crCode[4] | (crCode[5] << 16), crCode[6] | (crCode[7] << 16)));
+            }
+        }
+        else
+        {
+            uint32_t cbCode[4], crCode[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+            {
+                float cbv, crv;
+                if (p.topLeft)
+                {
+                    cbv = cb[0][2 * s];
+                    crv = cr[0][2 * s];
+                }
+                else if (YS == 1)
+                {
+                    cbv = ((cb[0][2 * s] + cb[0][2 * s + 1]) + (cb[kRows - 1][2 * s] + cb[kRows - 1][2 * s + 1])) * 0.25f;
+                    crv = ((cr[0][2 * s] + cr[0][2 * s + 1]) + (cr[kRows - 1][2 * s] + cr[kRows - 1][2 * s + 1])) * 0.25f;
+                }
+                else
+                {
+                    cbv = (cb[0][2 * s] + cb[0][2 * s + 1]) * 0.5f;
+                    crv = (cr[0][2 * s] + cr[0][2 * s + 1]) * 0.5f;
+                }
+                cbCode[s] = quantise(cbv);
+                crCode[s] = quantise(crv);
+            }
+            const long long offset = static_cast<long long>(column) * 8;
+            const long long chromaRow = YS ? rowPair : y0;
+            __stcs(reinterpret_cast<uint2*>(p.plane[1] + chromaRow * p.stride[1] + offset), make_uint2(cbCode[0] | (cbCode[1] << 16), cbCode[2] | (cbCode[3] << 16)));
+            __stcs(reinterpret_cast<uint2*>(p.plane[2] + chromaRow * p.stride[2] + offset), make_uint2(crCode[0] | (crCode[1] << 16), crCode[2] | (crCode[3] << 16)));
+        }
+    }
+}
+
+bool Aligned(const void* p, int64_t stride, int alignment)
+{
+    return (reinterpret_cast<uintptr_t>(p) % alignment) == 0 && (stride % alignment) == 0;
+}
+
+template <int CHANNELS>
+cudaError_t LaunchRgb16(const Rgb16Params& rp, int xs, int ys, int smCount, cudaStream_t stream)
+{
+    const long long groups = static_cast<long long>(rp.groupsPerRow) * ((rp.rowCount + ys) >> ys);
+    long long blocks = (groups + kRgbThreads - 1) / kRgbThreads;
+    const long long cap = static_cast<long long>(smCount) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const unsigned grid = static_cast<unsigned>(blocks);
+    if (xs == 1 && ys == 1) EncodeRgb16PlanarKernel<CHANNELS, 1, 1><<<grid, kRgbThreads, 0, stream>>>(rp);
+    else if (xs == 1) EncodeRgb16PlanarKernel<CHANNELS, 1, 0><<<grid, kRgbThreads, 0, stream>>>(rp);
+    else EncodeRgb16PlanarKernel<CHANNELS, 0, 0><<<grid, kRgbThreads, 0, stream>>>(rp);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+int LaunchEncodeGeneric(const EncodeParams& params, int hostDepth, void* stream);
+
+cudaError_t BuildGray16Lut(uint16_t* deviceLut, int smpte428, uint32_t maxCode, void* streamHandle)
+{
+    BuildGray16LutKernel<<<64, 256, 0, static_cast<cudaStream_t>(streamHandle)>>>(deviceLut, smpte428, maxCode);
+    return cudaGetLastError();
+}
+
+// Returns the number of kernels launched, 0 if this configuration is not covered, or a negative status.
+int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHandle)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
+    if (hostDepth != 16 || p.imageDepth <= 8)
+    {
+        return 0;
+    }
+    const int smCount = p.smCount > 0 ? p.smCount : 148;
+
+    if (p.channels == 1 && !p.planar)
+    {
+        if (p.gray16Lut == nullptr || p.width < 8 || !Aligned(p.rows, p.rowStride, 16) || !Aligned(p.plane[0], p.planeStride[0], 16))
+        {
+            return 0;
+        }
+        static bool configured = false;
+        if (!configured)
+        {
+            if (cudaFuncSetAttribute(EncodeGray16LutKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutEntries * 2) != cudaSuccess)
+            {
+                return AVIFGPU_ERR_CUDA;
+            }
+            configured = true;
+        }
+        Gray16Params gp{};
+        gp.rows = static_cast<const uint8_t*>(p.rows);
+        gp.rowStride = p.rowStride;
+        gp.planeY = static_cast<uint8_t*>(p.plane[0]);
+        gp.strideY = p.planeStride[0];
+        gp.chunksPerRow = p.width / 8;
+        gp.rowCount = p.rowCount;
+        gp.lut = p.gray16Lut;
+        EncodeGray16LutKernel<<<smCount, kLutThreads, kLutEntries * 2, stream>>>(gp);
+        if (cudaGetLastError() != cudaSuccess)
+        {
+            return AVIFGPU_ERR_CUDA;
+        }
+        int launched = 1;
+        const int covered = gp.chunksPerRow * 8;
+        if (covered < p.width)
+        {
+            EncodeParams strip = p;
+            strip.rows = static_cast<const uint8_t*>(p.rows) + static_cast<int64_t>(covered) * 2;
+            strip.width = p.width - covered;
+            strip.plane[0] = static_cast<uint8_t*>(p.plane[0]) + static_cast<int64_t>(covered) * 2;
+            const int n = LaunchEncodeGeneric(strip, hostDepth, streamHandle);
+            if (n < 0) return n;
+            launched += n;
+        }
+        return launched;
+    }
+
+    // The biased-truncation trick needs non-negative intermediates: true for every matrix with kr, kg, kb >= 0
+    // (all of H.273's); anything else takes the generic kernel.
+    if (p.planar && (p.channels == 3 || p.channels == 4) && !p.premultiply &&
+        (p.matrix.identity || (p.matrix.kr >= 0.0f && p.matrix.kg >= 0.0f && p.matrix.kb >= 0.0f && p.matrix.kr < 1.0f && p.matrix.kb < 1.0f)))
+    {
+        const int chromaAlign = p.xs ? 8 : 16;
+        if (p.width < 8 || !Aligned(p.rows, p.rowStride, 16) || !Aligned(p.plane[0], p.planeStride[0], 16) ||
+            !Aligned(p.plane[1], p.planeStride[1], chromaAlign) || !Aligned(p.plane[2], p.planeStride[2], chromaAlign) ||
+            (p.channels == 4 && !Aligned(p.plane[3], p.planeStride[3], 16)))
+        {
+            return 0;
+        }
+        const int width8 = p.width & ~7;
+        const int evenRows = p.ys ? (p.rowCount & ~1) : p.rowCount;
+        if (evenRows < 1)
+        {
+            return 0;
+        }
+        Rgb16Params rp{};
+        rp.rows = static_cast<const uint8_t*>(p.rows);
+        rp.rowStride = p.rowStride;
+        for (int k = 0; k < 4; ++k)
+        {
+            rp.plane[k] = static_cast<uint8_t*>(p.plane[k]);
+            rp.stride[k] = p.planeStride[k];
+        }
+        rp.groupsPerRow = width8 / 8;
+        rp.rowCount = evenRows;
+        rp.maxCodeFloat = p.maxCodeFloat;
+        rp.biasedMax = 8388608.0f + p.maxCodeFloat;
+        rp.matrix = p.matrix;
+        rp.chromaOffset = p.chromaOffset;
+        rp.topLeft = p.topLeft;
+        const cudaError_t e = p.channels == 4 ? LaunchRgb16<4>(rp, p.xs, p.ys, smCount, stream) : LaunchRgb16<3>(rp, p.xs, p.ys, smCount, stream);
+        if (e != cudaSuccess)
+        {
+            return AVIFGPU_ERR_CUDA;
+        }
+        int launched = 1;
+        const int colBytes = p.channels * 2;
+        if (width8 < p.width)
+        {
+            EncodeParams strip = p;
+            strip.rows = static_cast<const uint8_t*>(p.rows) + static_cast<int64_t>(width8) * colBytes;
+            strip.width = p.width - width8;
+            strip.plane[0] = static_cast<uint8_t*>(p.plane[0]) + static_cast<int64_t>(width8) * 2;
+            strip.plane[1] = static_cast<uint8_t*>(p.plane[1]) + static_cast<int64_t>(width8 >> p.xs) * 2;
+            strip.plane[2] = static_cast<uint8_t*>(p.plane[2]) + static_cast<int64_t>(width8 >> p.xs) * 2;
+            if (p.channels == 4) strip.plane[3] = static_cast<uint8_t*>(p.plane[3]) + static_cast<int64_t>(width8) * 2;
+            const int n = LaunchEncodeGeneric(strip, hostDepth, streamHandle);
+            if (n < 0) return n;
+            launched += n;
+        }
+        if (evenRows < p.rowCount)
+        {
+            EncodeParams strip = p;
+            strip.rows = static_cast<const uint8_t*>(p.rows) + static_cast<int64_t>(evenRows) * p.rowStride;
+            strip.rowCount = p.rowCount - evenRows;
+            strip.width = width8;
+            strip.plane[0] = static_cast<uint8_t*>(p.plane[0]) + static_cast<int64_t>(evenRows) * p.planeStride[0];
+            strip.plane[1] = static_cast<uint8_t*>(p.plane[1]) + static_cast<int64_t>(evenRows >> p.ys) * p.planeStride[1];
+            strip.plane[2] = static_cast<uint8_t*>(p.plane[2]) + static_cast<int64_t>(evenRows >> p.ys) * p.planeStride[2];
+            if (p.channels == 4) strip.plane[3] = static_cast<uint8_t*>(p.plane[3]) + static_cast<int64_t>(evenRows) * p.planeStride[3];
+            const int n = LaunchEncodeGeneric(strip, hostDepth, streamHandle);
+            if (n < 0) return n;
+            launched += n;
+        }
+        return launched;
+    }
+    return 0;
+}
+
+} // namespace avifgpu

@@ -250,7 +250,7 @@ AVIF_HD uint32_t TruncateToCode(float v, int maxCode)
 
 AVIF_HD uint32_t QuantiseLuma(float y, int maxCode) { return TruncateToCode(y + 0.5f, maxCode); }
 
-// chromaOffset = (float)(1 << (depth-1)), or 0 for the identity matrix.
+// chromaOffset = max/2 as a float (the decoder's chroma zero), or 0 for the identity matrix.
 AVIF_HD uint32_t QuantiseChroma(float c, float chromaOffset, int maxCode) { return TruncateToCode((c + chromaOffset) + 0.5f, maxCode); }
 
 // ---- decode side: YuvLookupTables.cpp / YuvDecode.cpp -----------------------------------------------------

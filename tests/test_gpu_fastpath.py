@@ -118,3 +118,41 @@ def test_unaligned_device_buffers_fall_back_correctly(gpu, port):
     for e, v in zip(expected, views):
         if e is not None:
             assert np.array_equal(v.cpu().numpy().view(np.uint16), e)
+
+
+# ---- 16-bit integer hosts (kernels_fast_int.cu) ------------------------------------------------------------------------
+
+@pytest.mark.parametrize("w,h", [(8, 2), (9, 3), (16, 1), (67, 5), (256, 17), (1031, 6)])
+@pytest.mark.parametrize("channels", [3, 4])
+@pytest.mark.parametrize("chroma", [abi.CHROMA_420, abi.CHROMA_422, abi.CHROMA_444])
+def test_rgb16_planar_fast_kernel(gpu, port, w, h, channels, chroma):
+    rng = cases.rng_for(f"rgb16_{w}x{h}_{channels}_{chroma}")
+    rows = cases.int_host_rows(rng, h, w, channels, 16, beyond=True)
+    alpha = abi.ALPHA_NONE if channels == 3 else abi.ALPHA_STRAIGHT
+    for depth, down, nclx in ((10, abi.DOWN_FILTER_BOX, None), (12, abi.DOWN_FILTER_TOP_LEFT, cases.NCLX_709()),
+                              (10, abi.DOWN_FILTER_BOX, cases.NCLX_GBR() if chroma == abi.CHROMA_444 else cases.NCLX_2020_PQ())):
+        desc = abi.EncodeDesc(w, h, 16, channels, alpha, depth, abi.TRANSFER_CLIP, 80, abi.LAYOUT_PLANAR_YCBCR, chroma, down, abi.GRAY16_LUT, nclx)
+        got = gpu.encode(desc, rows, pad=8)
+        assert cases.same_planes(port.encode(desc, rows), got), (depth, down)
+        for g in got:
+            if g is not None:
+                assert (g.base[:, g.shape[1]:] == 0xCD).all(), "wrote into the row padding"
+
+
+@pytest.mark.parametrize("w,h", [(8, 1), (13, 3), (64, 9), (4096, 4)])
+@pytest.mark.parametrize("curve", [abi.GRAY16_LUT, abi.GRAY16_SMPTE428])
+@pytest.mark.parametrize("depth", [10, 12])
+def test_gray16_lut_fast_kernel(gpu, port, w, h, curve, depth):
+    rng = cases.rng_for(f"gray16_{w}x{h}_{curve}_{depth}")
+    rows = cases.int_host_rows(rng, h, w, 1, 16, beyond=True)
+    desc = abi.EncodeDesc(w, h, 16, 1, abi.ALPHA_NONE, depth, gray16_curve=curve)
+    assert cases.same_planes(port.encode(desc, rows), gpu.encode(desc, rows, pad=8))
+
+
+def test_gray16_lut_every_input(gpu, port):
+    """All 65536 host samples through both Gray16 curves, against the CPU checker."""
+    rows = np.arange(65536, dtype=np.uint32).astype(np.uint16).reshape(16, 4096)
+    for curve in (abi.GRAY16_LUT, abi.GRAY16_SMPTE428):
+        for depth in (10, 12):
+            desc = abi.EncodeDesc(4096, 16, 16, 1, abi.ALPHA_NONE, depth, gray16_curve=curve)
+            assert cases.same_planes(port.encode(desc, rows), gpu.encode(desc, rows))
