@@ -619,6 +619,7 @@ AVIFGPU_EXPORT int avifgpu_decode_rows_device(avifgpu_context* ctx, const avifgp
     p.rowStride = row_stride_bytes;
     p.rowCount = nrows;
     p.yPhase = y0 & p.ys;
+    p.smCount = ctx->smCount;
     for (int k = 0; k < AVIFGPU_MAX_PLANES; ++k)
     {
         const PlaneGeometry g = DecodePlaneGeometry(*desc, k);
@@ -873,6 +874,7 @@ AVIFGPU_EXPORT int avifgpu_decode_rows(avifgpu_context* ctx, const avifgpu_decod
         DecodeParams p = base;
         p.rowCount = rows;
         p.yPhase = yFirst & p.ys;
+        p.smCount = ctx->smCount;
         for (int k = 0; k < AVIFGPU_MAX_PLANES; ++k)
         {
             const PlaneGeometry& g = geometry[k];

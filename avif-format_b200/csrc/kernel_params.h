@@ -67,6 +67,7 @@ struct DecodeParams
     float lumaR, lumaG, lumaB;
     float gammaMinusOne;
     float hlgPeak;
+    int32_t smCount;       // host-side extra for the launcher
 };
 
 // Launchers implemented in kernels_*.cu.  They only enqueue work on `stream` and return the number of kernels

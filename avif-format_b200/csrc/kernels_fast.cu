@@ -516,6 +516,4 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
     return launched;
 }
 
-int LaunchDecodeFast(const DecodeParams&, void*) { return 0; }
-
 } // namespace avifgpu

@@ -156,3 +156,26 @@ def test_gray16_lut_every_input(gpu, port):
         for depth in (10, 12):
             desc = abi.EncodeDesc(4096, 16, 16, 1, abi.ALPHA_NONE, depth, gray16_curve=curve)
             assert cases.same_planes(port.encode(desc, rows), gpu.encode(desc, rows))
+
+
+# ---- float decode (kernels_fast_decode.cu) -------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("w,h", [(4, 2), (5, 3), (128, 2), (131, 7), (260, 9), (1024, 16)])
+@pytest.mark.parametrize("chroma", [abi.CHROMA_420, abi.CHROMA_422, abi.CHROMA_444])
+def test_ycc_to_rgb32_fast_kernel(gpu, port, w, h, chroma):
+    for bit_depth, nclx, kwargs in ((10, cases.NCLX_2020_HLG(1), dict(hlg_apply_ootf=1)),
+                                    (10, cases.NCLX_2020_HLG(0), dict(hlg_apply_ootf=0)),
+                                    (12, cases.NCLX_2020_PQ(1), dict(pq_peak_nits=1000)),
+                                    (12, cases.NCLX_2020_428(0), dict()),
+                                    (10, abi.Nclx(1, abi.PRIMARIES_BT709, abi.TRANSFER_CHAR_HLG, abi.MATRIX_BT709, 1), dict(hlg_display_gamma=1.4, hlg_peak_nits=400))):
+        desc = abi.DecodeDesc(w, h, abi.COLORSPACE_YCBCR, chroma, bit_depth, abi.ALPHA_NONE, 32, nclx, **kwargs)
+        planes = cases.code_planes(cases.rng_for(f"dec32_{w}x{h}_{chroma}_{bit_depth}"), desc, overshoot=True)
+        expected = port.decode(desc, planes, threads=4)
+        got = gpu.decode(desc, planes)
+        assert cases.same_bits(expected, got), (bit_depth, kwargs, int((expected.view(np.uint32) != got.view(np.uint32)).sum()))
+        # odd first rows (4:2:0 blocks may start anywhere on decode) must still agree
+        if h > 3:
+            out = np.zeros_like(expected)
+            gpu.decode(desc, planes, y0=0, nrows=1, out=out[0:1])
+            gpu.decode(desc, planes, y0=1, nrows=h - 1, out=out[1:])
+            assert cases.same_bits(expected, out)
