@@ -24,6 +24,7 @@ int LaunchDecodeGeneric(const DecodeParams& params, void* stream);
 int LaunchEncodeFast(const EncodeParams& params, int hostDepth, void* stream);   // 0 = not applicable
 int LaunchEncodeFastInteger(const EncodeParams& params, int hostDepth, void* stream); // 0 = not applicable
 cudaError_t BuildGray16Lut(uint16_t* deviceLut, int smpte428, uint32_t maxCode, void* stream);
+long long VerifyHlgDivisions(void* stream);
 int LaunchDecodeFast(const DecodeParams& params, void* stream);                  // 0 = not applicable
 
 int LaunchEncode(const EncodeParams& params, int hostDepth, void* stream)
@@ -93,6 +94,20 @@ struct avifgpu_context
         uint16_t* device = nullptr;
     };
     std::vector<Gray16Lut> gray16Luts;
+    int hlgDivisionState = -1; // -1 not checked yet, 0 keep IEEE divisions, 1 fast divisions verified exact
+
+    // HLG decode replaces two constant divisions by a 3-instruction form, but only after comparing it with the
+    // IEEE division over every numerator the call sites can produce, on this device.
+    int VerifiedHlgDivisions()
+    {
+        if (hlgDivisionState < 0)
+        {
+            const long long disagreements = VerifyHlgDivisions(streams[0]);
+            hlgDivisionState = disagreements == 0 ? 1 : 0;
+            launches += 1;
+        }
+        return hlgDivisionState;
+    }
 
     // The 65536-entry code table of a Gray16 host configuration (built on the device on first use), or nullptr.
     const uint16_t* Gray16LutFor(const avifgpu_encode_desc& d)
@@ -620,6 +635,8 @@ AVIFGPU_EXPORT int avifgpu_decode_rows_device(avifgpu_context* ctx, const avifgp
     p.rowCount = nrows;
     p.yPhase = y0 & p.ys;
     p.smCount = ctx->smCount;
+    DeviceGuard deviceGuardForTables(ctx->device);
+    p.verifiedHlgDivisions = (desc->host_depth == 32 && transfer == AVIFGPU_TRANSFER_HLG) ? ctx->VerifiedHlgDivisions() : 0;
     for (int k = 0; k < AVIFGPU_MAX_PLANES; ++k)
     {
         const PlaneGeometry g = DecodePlaneGeometry(*desc, k);
@@ -827,6 +844,7 @@ AVIFGPU_EXPORT int avifgpu_decode_rows(avifgpu_context* ctx, const avifgpu_decod
     }
 
     DeviceGuard guard(ctx->device);
+    base.verifiedHlgDivisions = (desc->host_depth == 32 && transfer == AVIFGPU_TRANSFER_HLG) ? ctx->VerifiedHlgDivisions() : 0;
     const int64_t rowPayload = static_cast<int64_t>(desc->width) * DecodeHostColBytes(*desc);
     const int64_t deviceRowStride = (rowPayload + 255) & ~255ll;
     const int sliceRows = SliceRows(nrows, rowPayload);

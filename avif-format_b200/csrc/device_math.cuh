@@ -368,6 +368,27 @@ AVIF_HD float Expf(float x, const LibmTables& t)
     return static_cast<float>(y);
 }
 
+// The body of Expf for arguments known to be finite with |x| < 88 (no overflow / underflow / NaN screening).
+AVIF_HD float ExpfNoScreen(float x, const LibmTables& t)
+{
+    const double C[3] = AVIF_LIBM_EXP2F_POLY_SCALED;
+    const double xd = static_cast<double>(x);
+    const double z = AVIF_LIBM_EXP2F_INVLN2_SCALED * xd;
+    double kd = z + AVIF_LIBM_EXP2F_SHIFT;
+    const uint64_t ki = AsUint64(kd);
+    kd -= AVIF_LIBM_EXP2F_SHIFT;
+    const double r = z - kd;
+    uint64_t bits = t.exp2f[ki % 32];
+    bits += ki << (52 - 5);
+    const double s = AsDouble(bits);
+    const double zz = fma(C[0], r, C[1]);
+    const double r2 = r * r;
+    double y = fma(C[2], r, 1.0);
+    y = fma(zz, r2, y);
+    y = y * s;
+    return static_cast<float>(y);
+}
+
 // logf(x) as glibc computes it (sysdeps/ieee754/flt-32/e_logf.c).
 AVIF_HD float Logf(float x, const LibmTables& t)
 {

@@ -67,7 +67,8 @@ struct DecodeParams
     float lumaR, lumaG, lumaB;
     float gammaMinusOne;
     float hlgPeak;
-    int32_t smCount;       // host-side extra for the launcher
+    int32_t smCount;              // host-side extra for the launcher
+    int32_t verifiedHlgDivisions; // 1 once the context has verified HLGToLinearUnit's fast divisions on this device
 };
 
 // Launchers implemented in kernels_*.cu.  They only enqueue work on `stream` and return the number of kernels

@@ -63,9 +63,12 @@ constexpr int kQueueCapacity = 256;                              // in-band samp
 constexpr int kSharedQueuePerWarp = kQueueCapacity * 2;
 __host__ __device__ constexpr int SharedFixedBytes(int warps) { return kSharedLibm + kSharedOctaves + warps * (kSharedStagePerWarp + kSharedQueuePerWarp); }
 
-// The flat table (128 KB for 12-bit PQ) leaves room for one CTA per SM: 16 warps (measured: 24 warps at 58
-// registers were slower -- the compiler serialises the 24 independent look-ups of a lane when registers are
-// short).  The two-level table is small enough for two CTAs of 8 warps.
+// The flat table (128 KB for 12-bit PQ) leaves room for one CTA per SM: 16 warps.  Measured alternatives on the
+// 8K PQ frame (Gpx/s): 16 warps, direct 48-byte-per-lane loads 170 | same with loads remapped to be perfectly
+// coalesced through the staging area 158 | 24 warps at 58 registers 140 | register prefetch of the next tile 150 |
+// 12 warps with cp.async double-buffered staging 120.  The kernel is bound by instruction issue; resident warps
+// with enough registers to interleave the 24 independent look-ups matter more than how the bytes arrive.
+// The two-level table is small enough for two CTAs of 8 warps.
 template <int TABLE>
 struct FastConfig
 {

@@ -124,6 +124,39 @@ AVIF_HD float HLGToLinear(float value, const LibmTables& t)
     return value;
 }
 
+#if defined(__CUDACC__)
+// x / d for a constant d through its rounded reciprocal and one residual correction (Markstein): three
+// full-rate instructions instead of the ~14 of an IEEE division.  The result equals the correctly rounded
+// quotient for almost every (x, d); this library only uses it where a verification kernel has compared it with
+// the IEEE division for EVERY numerator the call site can produce (kernels_fast_decode.cu, VerifyHlgDivisions),
+// so "almost" never enters: a site that failed verification keeps the true division.
+__device__ __forceinline__ float DivideByConstant(float x, float d, float reciprocal)
+{
+    const float q = __fmul_rn(x, reciprocal);
+    const float r = __fmaf_rn(-q, d, x);
+    return __fmaf_rn(r, reciprocal, q);
+}
+
+// HLGToLinear (ColorTransfer.cpp:166-190) for value in [0, 1] (the decoders clamp before calling it), with the two
+// constant divisions -- (value - c) / a over the 2^23 possible numerators and (e + b) / 12 over [1, 16) --
+// replaced by DivideByConstant when `verifiedDivisions` is set.  The exp argument is within (-0.34, 2.47), so the
+// overflow / underflow screening of expf cannot trigger and is skipped.
+__device__ __forceinline__ float HLGToLinearUnit(float value, bool verifiedDivisions, const LibmTables& t)
+{
+    constexpr float a = 0.17883277f;
+    constexpr float b = 0.28466892f;
+    constexpr float c = 0.55991073f;
+    if (value > 0.5f)
+    {
+        const float numerator = value - c;
+        const float argument = verifiedDivisions ? DivideByConstant(numerator, a, 1.0f / a) : numerator / a;
+        const float e = avifmath::ExpfNoScreen(argument, t) + b;
+        return verifiedDivisions ? DivideByConstant(e, 12.0f, 1.0f / 12.0f) : e / 12.0f;
+    }
+    return (value * value) * (1.0f / 3.0f);
+}
+#endif
+
 // ColorTransfer.cpp:192-205.  gammaMinusOne = displayGamma - 1.0f (float subtraction, hoisted).
 AVIF_HD void ApplyHLGOOTF(float& r, float& g, float& b, float lumaR, float lumaG, float lumaB, float gammaMinusOne,
                           float nominalPeakBrightness, const LibmTables& t)
