@@ -414,7 +414,7 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     table->view.flatCount = 0;
     if (!flat.empty())
     {
-        if (!Check(cudaMalloc(&table->deviceFlat, flat.size() * sizeof(uint2)), "cudaMalloc", &table->error) ||
+        if (!Check(cudaMalloc(&table->deviceFlat, (flat.size() + 1) * sizeof(uint2)), "cudaMalloc", &table->error) ||
             !Check(cudaMemcpyAsync(table->deviceFlat, flat.data(), flat.size() * sizeof(uint2), cudaMemcpyHostToDevice, stream), "H2D", &table->error))
         {
             FreeCurveTable(table);

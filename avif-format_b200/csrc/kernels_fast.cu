@@ -96,9 +96,14 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
     {
         if (TABLE == kTableFlat)
         {
-            for (int i = threadIdx.x; i < p.table.flatCount; i += blockDim.x)
+            // 128 KB from L2: 128-bit copies, eight in flight per thread (the table is 16-byte aligned, count is even-padded)
+            const uint4* source = reinterpret_cast<const uint4*>(p.table.flat);
+            uint4* target = reinterpret_cast<uint4*>(flatEntries);
+            const int pairs = (p.table.flatCount + 1) / 2;
+#pragma unroll 8
+            for (int i = threadIdx.x; i < pairs; i += blockDim.x)
             {
-                flatEntries[i] = p.table.flat[i];
+                target[i] = __ldg(source + i);
             }
         }
         else
@@ -136,6 +141,31 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
     const int stepX = warpCount - stepRows * tilesX;
     int tileRow = firstTile / tilesX;
     int tileX = firstTile - tileRow * tilesX;
+    // Software pipeline: the six 128-bit loads of tile i+1 are issued as soon as the look-ups of tile i have
+    // consumed the registers, so they are in flight during the exact path, the matrix and the stores of tile i.
+    uint4 raw[6];
+    auto loadTile = [&](int row, int column, bool valid)
+    {
+        const int x = column * kTilePixels + lane * 4;
+        const int y = row * 2;
+        const bool active = valid && x < p.width;
+        const bool second = active && (y + 1) < p.rowCount;
+        const uint8_t* r0 = p.rows + static_cast<int64_t>(y) * p.rowStride + static_cast<int64_t>(x) * 12;
+        const uint8_t* r1 = r0 + p.rowStride;
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+        {
+            raw[q] = active ? __ldg(reinterpret_cast<const uint4*>(r0 + 16 * q)) : zero;
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+        {
+            raw[3 + q] = second ? __ldg(reinterpret_cast<const uint4*>(r1 + 16 * q)) : zero;
+        }
+    };
+    loadTile(tileRow, tileX, firstTile < tileCount);
+
     for (int tile = firstTile; tile < tileCount; tile += warpCount, tileRow += stepRows, tileX += stepX)
     {
         if (tileX >= tilesX)
@@ -148,23 +178,6 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
         const bool laneActive = x0 < p.width;
         const bool secondRow = (y0 + 1) < p.rowCount;
 
-        // ---- load 2 rows x 4 pixels x RGB as six 128-bit words ---------------------------------------------
-        uint4 raw[6];
-        {
-            const uint8_t* r0 = p.rows + static_cast<int64_t>(y0) * p.rowStride + static_cast<int64_t>(x0) * 12;
-            const uint8_t* r1 = r0 + p.rowStride;
-            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-            {
-                raw[q] = laneActive ? __ldg(reinterpret_cast<const uint4*>(r0 + 16 * q)) : zero;
-            }
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-            {
-                raw[3 + q] = (laneActive && secondRow) ? __ldg(reinterpret_cast<const uint4*>(r1 + 16 * q)) : zero;
-            }
-        }
         uint32_t code[kValuesPerLane];
 
         if (CURVE == kCurveClip)
@@ -176,6 +189,16 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
                 code[4 * q + 1] = FloatToCode(__uint_as_float(raw[q].y), p.maxCodeFloat);
                 code[4 * q + 2] = FloatToCode(__uint_as_float(raw[q].z), p.maxCodeFloat);
                 code[4 * q + 3] = FloatToCode(__uint_as_float(raw[q].w), p.maxCodeFloat);
+            }
+            {
+                int nextRow = tileRow + stepRows;
+                int nextX = tileX + stepX;
+                if (nextX >= tilesX)
+                {
+                    nextX -= tilesX;
+                    ++nextRow;
+                }
+                loadTile(nextRow, nextX, tile + warpCount < tileCount);
             }
         }
         else
@@ -205,6 +228,16 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
                 asm("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p or.b32 %0, %0, %2; }" : "+r"(bandMask) : "r"(static_cast<uint32_t>(inBand)), "r"(1u << j));
             }
 
+            {
+                int nextRow = tileRow + stepRows;
+                int nextX = tileX + stepX;
+                if (nextX >= tilesX)
+                {
+                    nextX -= tilesX;
+                    ++nextRow;
+                }
+                loadTile(nextRow, nextX, tile + warpCount < tileCount);
+            }
             // Warp-level compaction: exclusive prefix sum of the per-lane counts gives every lane its queue range.
             const int mine = __popc(bandMask);
             int inclusive = mine;
@@ -359,7 +392,7 @@ template <int CURVE, int XS, int YS, int TABLE>
 size_t FastEncodeSharedBytes(const FastEncodeParams& fp)
 {
     const size_t tableBytes = CURVE == kCurveClip ? 0
-                              : (TABLE == kTableFlat ? static_cast<size_t>(fp.table.flatCount) * sizeof(uint2)
+                              : (TABLE == kTableFlat ? static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4)
                                                      : static_cast<size_t>(fp.table.bucketCount) * sizeof(uint32_t));
     return static_cast<size_t>(SharedFixedBytes(FastConfig<TABLE>::warps)) + tableBytes;
 }
@@ -411,7 +444,7 @@ template <int CURVE>
 cudaError_t DispatchTable(const FastEncodeParams& fp, int xs, int ys, int smCount, cudaStream_t stream)
 {
     if (fp.table.flat != nullptr &&
-        static_cast<size_t>(SharedFixedBytes(FastConfig<kTableFlat>::warps)) + static_cast<size_t>(fp.table.flatCount) * sizeof(uint2) <=
+        static_cast<size_t>(SharedFixedBytes(FastConfig<kTableFlat>::warps)) + static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4) <=
             static_cast<size_t>(FastConfig<kTableFlat>::sharedLimit))
     {
         return DispatchChroma<CURVE, kTableFlat>(fp, xs, ys, smCount, stream);
