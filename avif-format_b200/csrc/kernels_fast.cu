@@ -27,6 +27,9 @@ using avifmath::LibmTables;
 namespace
 {
 
+#ifndef AVIF_FLAT_THREADS
+#define AVIF_FLAT_THREADS 512
+#endif
 constexpr int kTilePixels = 128;     // per row
 constexpr int kValuesPerLane = 24;   // 2 rows x 4 pixels x 3 channels
 constexpr int kLaneStrideWords = 28; // staging stride per lane (16-byte aligned, conflict-free for STS.128)
@@ -72,7 +75,7 @@ __host__ __device__ constexpr int SharedFixedBytes(int warps) { return kSharedLi
 template <int TABLE>
 struct FastConfig
 {
-    static constexpr int threads = TABLE == kTableFlat ? 512 : 256;
+    static constexpr int threads = TABLE == kTableFlat ? AVIF_FLAT_THREADS : 256;
     static constexpr int warps = threads / 32;
     static constexpr int blocksPerSm = TABLE == kTableFlat ? 1 : 2;
     static constexpr int sharedLimit = TABLE == kTableFlat ? 227 * 1024 : 112 * 1024;
