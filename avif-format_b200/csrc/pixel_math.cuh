@@ -146,14 +146,15 @@ __device__ __forceinline__ float HLGToLinearUnit(float value, bool verifiedDivis
     constexpr float a = 0.17883277f;
     constexpr float b = 0.28466892f;
     constexpr float c = 0.55991073f;
-    if (value > 0.5f)
-    {
-        const float numerator = value - c;
-        const float argument = verifiedDivisions ? DivideByConstant(numerator, a, 1.0f / a) : numerator / a;
-        const float e = avifmath::ExpfNoScreen(argument, t) + b;
-        return verifiedDivisions ? DivideByConstant(e, 12.0f, 1.0f / 12.0f) : e / 12.0f;
-    }
-    return (value * value) * (1.0f / 3.0f);
+    // Both branches are evaluated and one is selected: on typical data half the lanes of a warp take each side, so
+    // a real branch would execute both anyway, plus the divergence bookkeeping.  (For value <= 0.5 the exponential's
+    // argument is in [-3.14, -0.33]: harmless, and its result is discarded.)
+    const float numerator = value - c;
+    const float argument = verifiedDivisions ? DivideByConstant(numerator, a, 1.0f / a) : numerator / a;
+    const float e = avifmath::ExpfNoScreen(argument, t) + b;
+    const float high = verifiedDivisions ? DivideByConstant(e, 12.0f, 1.0f / 12.0f) : e / 12.0f;
+    const float low = (value * value) * (1.0f / 3.0f);
+    return value > 0.5f ? high : low;
 }
 #endif
 

@@ -473,29 +473,37 @@ def run_b200(args, workload, rank, world, local_rank):
 
 
 def run_tile_mode(torch, dist, gpu, avifgpu, wl, device, rank, world, args, stream_handle):
-    """ONE frame, rank r converts row block r, then the planar buffer is assembled on every rank with one
-    all_gather per plane.  Returns timings (convert-only and convert+gather) for rank 0 to print."""
-    rows_per = ((wl.rows_total // world) + 1) & ~1
-    y0 = min(rank * rows_per, wl.rows_total)
-    n = max(min(rows_per, wl.rows_total - y0), 0)
-    desc = wl.encode_desc(n)
-    full = wl.make_device_input(torch, device, 4242)[0]
+    """ONE frame, rank r converts row block r (avifgpu.sharding.row_blocks: even boundaries, no halo), then the planar
+    buffer is assembled on every rank with one all_gather per plane.  Returns timings (convert-only and
+    convert+gather) for rank 0 to print, after checking the gathered planes against a single-GPU conversion."""
+    from avifgpu import sharding
+    blocks = sharding.row_blocks(wl.rows_total, world)
+    y0, n = blocks[rank]
+    desc = sharding.block_desc(wl.enc, n)
+    full = wl.make_device_input(torch, device, 4242)[0]  # same seed on every rank: the same frame
     block = full[y0:y0 + n]
-    shapes_block = abi.encode_plane_shapes(wl.encode_desc(rows_per))
+    shapes = sharding.max_block_plane_shapes(wl.enc, blocks)
     dt = torch.int16 if wl.enc.image_bit_depth > 8 else torch.uint8
-    local = [None if s is None else torch.zeros(s, dtype=dt, device=device) for s in shapes_block]
-    gathered = [None if s is None else torch.empty((world,) + tuple(s), dtype=dt, device=device) for s in shapes_block]
+    local = [None if s is None else torch.zeros(s, dtype=dt, device=device) for s in shapes]
 
     def convert():
-        gpu.encode_device(desc, block.data_ptr(), block.stride(0) * block.element_size(), avifgpu.planes_from_tensors(local),
-                          stream=stream_handle)
+        if n > 0:
+            gpu.encode_device(desc, block.data_ptr(), block.stride(0) * block.element_size(), avifgpu.planes_from_tensors(local),
+                              stream=stream_handle)
 
     def gather():
-        for l, g in zip(local, gathered):
-            if l is not None:
-                dist.all_gather_into_tensor(g, l)
+        return sharding.gather_encode_planes(dist, torch, wl.enc, blocks, local)
 
-    for _ in range(3):
+    convert()
+    planes = gather()
+    torch.cuda.synchronize(device)
+    # correctness of the tiling + gather: compare with the whole frame converted on this GPU alone
+    whole = wl.make_device_output(torch, device)
+    gpu.encode_device(wl.enc, full.data_ptr(), full.stride(0) * full.element_size(), avifgpu.planes_from_tensors(whole), stream=stream_handle)
+    torch.cuda.synchronize(device)
+    identical = all(torch.equal(a, b) for a, b in zip(planes, whole) if a is not None)
+    del planes, whole
+    for _ in range(2):
         convert()
         gather()
     dist.barrier()
@@ -513,7 +521,8 @@ def run_tile_mode(torch, dist, gpu, avifgpu, wl, device, rank, world, args, stre
     t = torch.tensor([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])], device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     convert_ms, both_ms = (float(v) / args.steps for v in t.tolist())
-    return {"mode": "one frame, row-block tiles + all_gather per plane", "convert_ms": convert_ms, "convert_plus_gather_ms": both_ms,
+    return {"mode": "one frame, even row-block tiles, one all_gather per plane to every rank", "identical_to_single_gpu": bool(identical),
+            "convert_ms": convert_ms, "convert_plus_gather_ms": both_ms,
             "convert_gpx_s": wl.pixels / (convert_ms * 1e-3) / 1e9, "convert_plus_gather_gpx_s": wl.pixels / (both_ms * 1e-3) / 1e9}
 
 
