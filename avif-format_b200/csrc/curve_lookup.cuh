@@ -51,22 +51,55 @@ __device__ __forceinline__ uint32_t LookupCurveCode(uint32_t bits, const uint2* 
 }
 
 // Flat-table look-up (see CurveTableView::flat): `flat` is indexed by (bucket number - low), `span` = high - low.
-// Branch-free, 12 integer instructions + one 64-bit shared-memory load.  The bucket number is taken with an
-// ARITHMETIC shift, so every float with the sign bit set (negative values, -0, negative NaNs) yields a negative
-// index that the single clamp-to-[0, span] instruction (DPX min + relu) sends to the lowest bucket; that bucket
-// holds no step (.x = 0, so `bits < .x` is false) and decodes to code 0 exactly as the reference's
-// `value < 0 -> 0` / NaN -> 0 does.  +inf and positive NaNs are reported in band (they do not follow the steps).
-__device__ __forceinline__ uint32_t LookupCurveCodeFlat(uint32_t bits, const uint2* __restrict__ flat, uint32_t shift, int32_t low,
-                                                        int32_t span, bool& inBand)
+// Branch-free: ten integer/float instructions + one 64-bit shared-memory load, result as a float.  The bucket number
+// is taken with an ARITHMETIC shift, so every float with the sign bit set (negative values, -0, negative NaNs)
+// yields a negative index that the single add-clamp-to-[0, span] instruction (DPX) sends to the lowest bucket; that
+// bucket holds no step (.x = 0, so `bits < .x` is false) and decodes to code 0 exactly as the reference's
+// `value < 0 -> 0` / NaN -> 0 does.  +inf and the positive NaNs (bits > 0x7f7fffff) do NOT follow the steps; they
+// land in the top bucket (max code, never in band) and the caller must route them to ExactCurveCode itself.
+__device__ __forceinline__ float LookupCurveFlat(uint32_t bits, const uint2* __restrict__ flat, uint32_t shift, int32_t negativeLow, int32_t span,
+                                                 bool& inBand, uint2& entryOut)
 {
-    const int32_t index = __vimin_s32_relu((static_cast<int32_t>(bits) >> shift) - low, span);
+    const int32_t index = __viaddmin_s32_relu(static_cast<int32_t>(bits) >> shift, negativeLow, span);
     const uint2 entry = flat[index];
+    entryOut = entry;
     const uint32_t distance = bits - entry.x;
-    inBand = (distance < (entry.y & 0xfffffu)) || (static_cast<int32_t>(bits) > 0x7f7fffff);
-    uint32_t code;
-    asm("{ .reg .pred below; setp.lt.u32 below, %1, %2; shr.u32 %0, %3, 20; @below sub.u32 %0, %0, 1; }"
-        : "=r"(code) : "r"(bits), "r"(entry.x), "r"(entry.y));
+    inBand = distance < (entry.y & kFlatWidthMask);
+    float code;
+    asm("{ .reg .pred below; .reg .b32 upper; setp.lt.u32 below, %1, %2; and.b32 upper, %3, 0xfffff000; mov.b32 %0, upper; @below add.rn.f32 %0, %0, 0fBF800000; }"
+        : "=f"(code) : "r"(bits), "r"(entry.x), "r"(entry.y));
     return code;
+}
+
+__device__ __forceinline__ float LookupCurveFlat(uint32_t bits, const uint2* __restrict__ flat, uint32_t shift, int32_t negativeLow, int32_t span,
+                                                 bool& inBand)
+{
+    uint2 entry;
+    return LookupCurveFlat(bits, flat, shift, negativeLow, span, inBand, entry);
+}
+
+// Position of an in-band sample's bit in CurveTableView::bandBits (entry = the sample's flat entry).
+__device__ __forceinline__ uint32_t BandBitIndex(uint32_t bits, const uint2 entry, uint32_t strideLog2)
+{
+    const uint32_t k = static_cast<uint32_t>(__float2int_rz(__uint_as_float(entry.y & ~kFlatWidthMask)));
+    return (k << strideLog2) + (bits - entry.x);
+}
+
+// Complete flat look-up for one finite sample, bitmap included (used by the verifier; the conversion kernel inlines
+// the same steps around its own batching).
+__device__ __forceinline__ uint32_t LookupCurveCodeFlatResolved(uint32_t bits, const CurveTableView& table, bool& inBand)
+{
+    uint2 entry;
+    const float code = LookupCurveFlat(bits, table.flat, table.flatShift, -static_cast<int32_t>(table.flatLow),
+                                       static_cast<int32_t>(table.flatHigh - table.flatLow), inBand, entry);
+    uint32_t result = static_cast<uint32_t>(code);
+    if (inBand)
+    {
+        const uint32_t bitIndex = BandBitIndex(bits, entry, table.bandStrideLog2);
+        const uint32_t word = table.bandBits[bitIndex >> 5];
+        result -= ((word >> (bitIndex & 31u)) & 1u) ^ 1u;
+    }
+    return result;
 }
 
 } // namespace avifgpu

@@ -75,16 +75,20 @@ __global__ void __launch_bounds__(kSweepThreads) VerifyKernel(float pqMultiplier
         uint32_t fast = LookupCurveCode(bits, table.octaves, table.buckets, inBand);
         if (table.flat != nullptr)
         {
-            // the flat variant must agree as well (its bands differ: count the union)
-            bool inBandFlat;
-            const uint32_t fastFlat = LookupCurveCodeFlat(bits, table.flat, table.flatShift, static_cast<int32_t>(table.flatLow), static_cast<int32_t>(table.flatHigh - table.flatLow), inBandFlat);
-            if (!inBandFlat && fastFlat != ExactCurveCode<CURVE>(__uint_as_float(bits), pqMultiplier, maxCodeFloat, t))
+            // The flat variant, band bitmap included, must reproduce the exact curve for every finite input;
+            // +inf / NaN are the caller's to route to the exact evaluation (curve_lookup.cuh).
+            if (bits <= 0x7f7fffffu)
             {
-                ++mismatches;
-            }
-            if (inBandFlat)
-            {
-                ++flatInBand;
+                bool inBandFlat;
+                const uint32_t fastFlat = LookupCurveCodeFlatResolved(bits, table, inBandFlat);
+                if (fastFlat != ExactCurveCode<CURVE>(__uint_as_float(bits), pqMultiplier, maxCodeFloat, t))
+                {
+                    ++mismatches;
+                }
+                if (inBandFlat)
+                {
+                    ++flatInBand;
+                }
             }
         }
         if (inBand)
@@ -110,12 +114,49 @@ __global__ void __launch_bounds__(kSweepThreads) VerifyKernel(float pqMultiplier
     }
 }
 
+// Band bitmap: one warp per 32-bit word, lane = bit.  bands[i] = {first_k, width, k}.
+template <int CURVE>
+__global__ void __launch_bounds__(kSweepThreads) FillBandBitsKernel(float pqMultiplier, float maxCodeFloat, const uint3* __restrict__ bands, int bandCount,
+                                                                   uint32_t strideLog2, uint32_t* __restrict__ bandBits)
+{
+    __shared__ uint64_t libmStorage[96];
+    const avifmath::LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
+    __syncthreads();
+
+    const uint32_t wordsPerBand = (1u << strideLog2) / 32u;
+    const uint64_t words = static_cast<uint64_t>(bandCount) * wordsPerBand;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warpsInGrid = static_cast<uint64_t>(gridDim.x) * (blockDim.x / 32);
+    for (uint64_t w = static_cast<uint64_t>(blockIdx.x) * (blockDim.x / 32) + (threadIdx.x >> 5); w < words; w += warpsInGrid)
+    {
+        const uint3 band = bands[w / wordsPerBand];
+        const uint32_t offset = static_cast<uint32_t>(w % wordsPerBand) * 32u + lane;
+        bool atOrAbove = false;
+        if (offset < band.y)
+        {
+            atOrAbove = ExactCurveCode<CURVE>(__uint_as_float(band.x + offset), pqMultiplier, maxCodeFloat, t) >= band.z;
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, atOrAbove);
+        if (lane == 0 && offset < band.y)
+        {
+            bandBits[((static_cast<uint64_t>(band.z) << strideLog2) >> 5) + (w % wordsPerBand)] = word;
+        }
+    }
+}
+
 struct Step
 {
     uint32_t first; // min{bits : code >= k}
     uint32_t end;   // max(first, max{bits : code < k})
     uint32_t k;
 };
+
+uint32_t FloatBits(float v)
+{
+    uint32_t bits;
+    std::memcpy(&bits, &v, sizeof bits);
+    return bits;
+}
 
 bool Check(cudaError_t e, const char* what, std::string* error)
 {
@@ -134,9 +175,11 @@ void FreeCurveTable(CurveTable* table)
     if (table->deviceOctaves) cudaFree(table->deviceOctaves);
     if (table->deviceBuckets) cudaFree(table->deviceBuckets);
     if (table->deviceFlat) cudaFree(table->deviceFlat);
+    if (table->deviceBandBits) cudaFree(table->deviceBandBits);
     table->deviceOctaves = nullptr;
     table->deviceBuckets = nullptr;
     table->deviceFlat = nullptr;
+    table->deviceBandBits = nullptr;
     table->valid = false;
 }
 
@@ -343,7 +386,8 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
 
     // ---- flat variant ----------------------------------------------------------------------------------------
     std::vector<uint2> flat;
-    uint32_t flatShift = 0, flatLow = 0, flatHigh = 0;
+    std::vector<uint3> flatBands; // {first, width, k} of every step with a fuzzy band
+    uint32_t flatShift = 0, flatLow = 0, flatHigh = 0, bandStrideLog2 = 5;
     if (!steps.empty())
     {
         int shift = static_cast<int>(kFlatMaxShift);
@@ -384,14 +428,27 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
                         // the bucket meets step `next`: its start, its band, or the tail of its band.  Samples in
                         // [first, end] are in band when the step has a fuzzy band (end > first).
                         const uint32_t bandWidth = steps[next].end > steps[next].first ? (steps[next].end - steps[next].first + 1u) : 0u;
-                        usable = usable && bandWidth < (1u << 20);
-                        flat[b] = make_uint2(steps[next].first, (steps[next].k << 20) | bandWidth);
+                        usable = usable && bandWidth <= kFlatWidthMask;
+                        flat[b] = make_uint2(steps[next].first, FloatBits(static_cast<float>(steps[next].k)) | bandWidth);
                     }
                     else
                     {
-                        flat[b] = make_uint2(0u, static_cast<uint32_t>(next) << 20); // no step: code = steps below
+                        flat[b] = make_uint2(0u, FloatBits(static_cast<float>(next))); // no step: code = steps below
                     }
                 }
+                for (const Step& s : steps)
+                {
+                    if (s.end > s.first)
+                    {
+                        const uint32_t width = s.end - s.first + 1u;
+                        flatBands.push_back(make_uint3(s.first, width, s.k));
+                        while ((1u << bandStrideLog2) < width)
+                        {
+                            ++bandStrideLog2;
+                        }
+                    }
+                }
+                usable = usable && ((static_cast<uint64_t>(codeCount) << bandStrideLog2) / 8u) <= kBandBitmapMaxBytes;
             }
         }
         if (!usable)
@@ -412,6 +469,8 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     table->view.bucketCount = static_cast<int32_t>(buckets.size());
     table->view.flat = nullptr;
     table->view.flatCount = 0;
+    table->view.bandBits = nullptr;
+    table->view.bandStrideLog2 = 0;
     if (!flat.empty())
     {
         if (!Check(cudaMalloc(&table->deviceFlat, (flat.size() + 1) * sizeof(uint2)), "cudaMalloc", &table->error) ||
@@ -425,6 +484,40 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
         table->view.flatShift = flatShift;
         table->view.flatLow = flatLow;
         table->view.flatHigh = flatHigh;
+
+        // Band bitmap: the exact answer for every in-band float, one bit each, at (k << stride) + (bits - first_k).
+        const size_t bitmapBytes = (codeCount << bandStrideLog2) / 8u;
+        uint3* dBands = nullptr;
+        bool filled = Check(cudaMalloc(&table->deviceBandBits, bitmapBytes), "cudaMalloc", &table->error) &&
+                      Check(cudaMemsetAsync(table->deviceBandBits, 0, bitmapBytes, stream), "memset", &table->error);
+        if (filled && !flatBands.empty())
+        {
+            filled = Check(cudaMalloc(&dBands, flatBands.size() * sizeof(uint3)), "cudaMalloc", &table->error) &&
+                     Check(cudaMemcpyAsync(dBands, flatBands.data(), flatBands.size() * sizeof(uint3), cudaMemcpyHostToDevice, stream), "H2D", &table->error);
+            if (filled)
+            {
+                uint32_t* bitsOut = static_cast<uint32_t*>(table->deviceBandBits);
+                const int bandCount = static_cast<int>(flatBands.size());
+                if (curve == kCurveLinearToPQ)
+                {
+                    FillBandBitsKernel<kCurveLinearToPQ><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, dBands, bandCount, bandStrideLog2, bitsOut);
+                }
+                else
+                {
+                    FillBandBitsKernel<kCurveLinearToSMPTE428><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, dBands, bandCount, bandStrideLog2, bitsOut);
+                }
+                filled = Check(cudaStreamSynchronize(stream), "band bitmap", &table->error);
+            }
+            cudaFree(dBands);
+        }
+        if (!filled)
+        {
+            FreeCurveTable(table);
+            return false;
+        }
+        table->view.bandBits = static_cast<const uint32_t*>(table->deviceBandBits);
+        table->view.bandStrideLog2 = bandStrideLog2;
+        table->stats.bandBitmapBytes = bitmapBytes;
     }
     unsigned long long* dCounters = nullptr;
     ok = Check(cudaMemcpyAsync(table->deviceOctaves, octaves.data(), octaves.size() * sizeof(uint2), cudaMemcpyHostToDevice, stream), "H2D", &table->error) &&

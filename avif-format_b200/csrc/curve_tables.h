@@ -16,11 +16,16 @@
 //   * the conversion kernel does two shared-memory look-ups and a handful of integer instructions per sample;
 //     samples that fall inside a (conservatively widened) band -- about 2 % of typical data -- are handed to the
 //     exact evaluation, compacted across the warp so the exact code runs at full lane occupancy;
-//   * a verification kernel then re-sweeps every float and checks table == exact outside the bands; a table that
+//   * the flat variant goes one step further: inside the band of step k the exact code is k-1 or k (neighbouring
+//     bands never overlap, the builder checks), so ONE BIT per in-band float records the exact answer.  A fill
+//     kernel evaluates the exact curve for every in-band float (a few million) into a bitmap that lives in L2
+//     (1 MB for 12 bits); the conversion kernel resolves an in-band sample with one 32-bit load instead of ~150
+//     instructions of glibc-exact powf;
+//   * a verification kernel then re-sweeps every float and checks table (+ bitmap) == exact; a table that
 //     fails (it never has) is discarded and the generic kernel keeps serving that configuration.
 //
-// Nothing here approximates: every output is either decided by a threshold derived from the exact curve, or is
-// the exact curve itself.
+// Nothing here approximates: every output is either decided by a threshold derived from the exact curve, read from
+// a bit the exact curve wrote, or is the exact curve itself.
 #ifndef AVIF_CURVE_TABLES_H
 #define AVIF_CURVE_TABLES_H
 
@@ -48,10 +53,16 @@ constexpr uint32_t kOffsetResolutionBits = 19;      // offsets inside a bucket a
 // [flatLow << flatShift, (flatHigh + 1) << flatShift); inputs outside are clamped to the end buckets, which
 // hold no step.  One 64-bit entry per bucket:
 //     .x = bit pattern of the step's band start (first_k), 0 when the bucket meets no step
-//     .y = kUpper << 20 | bandWidth   (bandWidth = number of in-band floats from first_k on, < 2^20)
-// code = kUpper - (bits < .x); the sample is in band iff 0 <= bits - .x < bandWidth.
+//     .y = bit pattern of (float)kUpper | bandWidth   (kUpper < 2^12 leaves the low 12 mantissa bits free;
+//          bandWidth = number of in-band floats from first_k on, < 2^12)
+// code = kUpper - (bits < .x), delivered as a float (the forward matrix wants floats); the sample is in band iff
+// 0 <= bits - .x < bandWidth, and then bit ((kUpper << bandStrideLog2) + bits - .x) of bandBits says whether the
+// exact code is kUpper (1) or kUpper - 1 (0).
 constexpr uint32_t kFlatMaxShift = 14;
 constexpr uint32_t kFlatMaxBytes = 132 * 1024;
+constexpr uint32_t kFlatWidthBits = 12;
+constexpr uint32_t kFlatWidthMask = (1u << kFlatWidthBits) - 1u;
+constexpr uint64_t kBandBitmapMaxBytes = 8ull << 20;
 
 // Device-resident table (global memory; kernels stage it into shared memory).
 struct CurveTableView
@@ -64,6 +75,8 @@ struct CurveTableView
     uint32_t flatShift;
     uint32_t flatLow;         // bucket number (bits >> flatShift) of flat[0]
     uint32_t flatHigh;        // bucket number of flat[flatCount - 1]
+    const uint32_t* bandBits; // (maxCode + 1) << bandStrideLog2 bits: the exact answer for every in-band float
+    uint32_t bandStrideLog2;  // bits reserved per step (power of two >= the widest band)
 };
 
 struct CurveTableStats
@@ -71,7 +84,8 @@ struct CurveTableStats
     double buildMilliseconds = 0.0;
     uint64_t sweptInputs = 0;
     uint64_t inBandInputs = 0;     // inputs the kernel sends to the exact path (two-level table)
-    uint64_t flatInBandInputs = 0; // same for the flat variant (exact per-bucket band widths)
+    uint64_t flatInBandInputs = 0; // flat variant: inputs resolved through the band bitmap (exact per-step widths)
+    uint64_t bandBitmapBytes = 0;  // size of the flat variant's band bitmap
     int32_t flatBuckets = 0;       // 0 when the flat variant does not apply
     uint64_t verifyMismatches = 0; // must be 0
     int32_t steps = 0;             // thresholds found
@@ -91,6 +105,7 @@ struct CurveTable
     void* deviceOctaves = nullptr;
     void* deviceBuckets = nullptr;
     void* deviceFlat = nullptr;
+    void* deviceBandBits = nullptr;
 };
 
 // Builds (sweeps, assembles, uploads, verifies) the table on the current device.  Synchronous; uses `stream`.

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
     uint32_t* stage = stageAll + warpInBlock * (32 * kLaneStrideWords);
     uint32_t* myStage = stage + lane * kLaneStrideWords;
     uint16_t* queue = queueAll + warpInBlock * kQueueCapacity;
-    const uint2* flatBiased = flatEntries; // indexed by bucket - flatLow (the look-up applies the bias)
+    const uint32_t bandStrideLog2 = p.table.bandStrideLog2;
     const uint32_t flatShift = p.table.flatShift;
     const int32_t flatLow = static_cast<int32_t>(p.table.flatLow);
     const int32_t flatHigh = static_cast<int32_t>(p.table.flatHigh);
@@ -168,6 +168,17 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
         }
     };
     loadTile(tileRow, tileX, firstTile < tileCount);
+    auto prefetchNext = [&](int tile)
+    {
+        int nextRow = tileRow + stepRows;
+        int nextX = tileX + stepX;
+        if (nextX >= tilesX)
+        {
+            nextX -= tilesX;
+            ++nextRow;
+        }
+        loadTile(nextRow, nextX, tile + warpCount < tileCount);
+    };
 
     for (int tile = firstTile; tile < tileCount; tile += warpCount, tileRow += stepRows, tileX += stepX)
     {
@@ -181,33 +192,111 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
         const bool laneActive = x0 < p.width;
         const bool secondRow = (y0 + 1) < p.rowCount;
 
-        uint32_t code[kValuesPerLane];
+        float codeF[kValuesPerLane]; // the codes, as the floats the forward matrix consumes
 
         if (CURVE == kCurveClip)
         {
 #pragma unroll
             for (int q = 0; q < 6; ++q)
             {
-                code[4 * q + 0] = FloatToCode(__uint_as_float(raw[q].x), p.maxCodeFloat);
-                code[4 * q + 1] = FloatToCode(__uint_as_float(raw[q].y), p.maxCodeFloat);
-                code[4 * q + 2] = FloatToCode(__uint_as_float(raw[q].z), p.maxCodeFloat);
-                code[4 * q + 3] = FloatToCode(__uint_as_float(raw[q].w), p.maxCodeFloat);
+                codeF[4 * q + 0] = CodeToFloat(FloatToCode(__uint_as_float(raw[q].x), p.maxCodeFloat));
+                codeF[4 * q + 1] = CodeToFloat(FloatToCode(__uint_as_float(raw[q].y), p.maxCodeFloat));
+                codeF[4 * q + 2] = CodeToFloat(FloatToCode(__uint_as_float(raw[q].z), p.maxCodeFloat));
+                codeF[4 * q + 3] = CodeToFloat(FloatToCode(__uint_as_float(raw[q].w), p.maxCodeFloat));
             }
+            prefetchNext(tile);
+        }
+        else if (TABLE == kTableFlat)
+        {
+            // ---- float -> code through the exact step table; in-band samples are resolved by the band bitmap ----
+            // The raw bits stay reachable by a run-time index (the rare paths below) through the lane's staging row.
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
             {
-                int nextRow = tileRow + stepRows;
-                int nextX = tileX + stepX;
-                if (nextX >= tilesX)
+                *reinterpret_cast<uint4*>(myStage + 4 * q) = raw[q];
+            }
+            uint32_t bandMask = 0;
+            int32_t largest = 0; // max over the samples as signed integers: > 0x7f7fffff <=> a +inf / NaN is among them
+#pragma unroll
+            for (int j = 0; j < kValuesPerLane; ++j)
+            {
+                const uint4 w = raw[j >> 2];
+                const uint32_t bits = (j & 3) == 0 ? w.x : (j & 3) == 1 ? w.y : (j & 3) == 2 ? w.z : w.w;
+                bool inBand;
+                codeF[j] = LookupCurveFlat(bits, flatEntries, flatShift, -flatLow, flatHigh - flatLow, inBand);
+                asm("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p or.b32 %0, %0, %2; }" : "+r"(bandMask) : "r"(static_cast<uint32_t>(inBand)), "r"(1u << j));
+                if (j % 3 == 2)
                 {
-                    nextX -= tilesX;
-                    ++nextRow;
+                    const uint4 w1 = raw[(j - 1) >> 2];
+                    const uint4 w2 = raw[(j - 2) >> 2];
+                    const uint32_t bits1 = ((j - 1) & 3) == 0 ? w1.x : ((j - 1) & 3) == 1 ? w1.y : ((j - 1) & 3) == 2 ? w1.z : w1.w;
+                    const uint32_t bits2 = ((j - 2) & 3) == 0 ? w2.x : ((j - 2) & 3) == 1 ? w2.y : ((j - 2) & 3) == 2 ? w2.z : w2.w;
+                    largest = max(largest, __vimax3_s32(static_cast<int32_t>(bits), static_cast<int32_t>(bits1), static_cast<int32_t>(bits2)));
                 }
-                loadTile(nextRow, nextX, tile + warpCount < tileCount);
+            }
+            prefetchNext(tile);
+
+            // +inf / NaN (never in real frames): flag them for the exact evaluation.
+            uint32_t exactMask = 0;
+            if (__any_sync(0xffffffffu, largest > 0x7f7fffff))
+            {
+#pragma unroll
+                for (int j = 0; j < kValuesPerLane; ++j)
+                {
+                    if (static_cast<int32_t>(myStage[j]) > 0x7f7fffff)
+                    {
+                        exactMask |= 1u << j;
+                    }
+                }
+            }
+
+            // In-band samples (~1.5 % of typical data, so a lane rarely has more than one): one bit of the L2-resident
+            // band bitmap says whether the exact code is the table's kUpper or one less.
+            uint32_t lowerMask = 0;
+            {
+                uint32_t pending = bandMask;
+                while (pending != 0)
+                {
+                    const int j = __ffs(static_cast<int>(pending)) - 1;
+                    pending &= pending - 1;
+                    const uint32_t bits = myStage[j];
+                    bool inBand;
+                    uint2 entry;
+                    LookupCurveFlat(bits, flatEntries, flatShift, -flatLow, flatHigh - flatLow, inBand, entry);
+                    const uint32_t bitIndex = BandBitIndex(bits, entry, bandStrideLog2);
+                    const uint32_t word = __ldg(p.table.bandBits + (bitIndex >> 5));
+                    lowerMask |= (((word >> (bitIndex & 31u)) & 1u) ^ 1u) << j;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kValuesPerLane; ++j)
+            {
+                asm("{ .reg .pred p; .reg .b32 t; and.b32 t, %1, %2; setp.ne.u32 p, t, 0; @p add.rn.f32 %0, %0, 0fBF800000; }"
+                    : "+f"(codeF[j]) : "r"(lowerMask), "r"(1u << j));
+            }
+            if (__any_sync(0xffffffffu, exactMask != 0))
+            {
+                uint32_t pending = exactMask;
+                while (pending != 0)
+                {
+                    const int j = __ffs(static_cast<int>(pending)) - 1;
+                    pending &= pending - 1;
+                    myStage[j] = ExactCurveCode<CURVE == kCurveClip ? kCurveLinearToPQ : CURVE>(__uint_as_float(myStage[j]), p.pqMultiplier, p.maxCodeFloat, t);
+                }
+#pragma unroll
+                for (int j = 0; j < kValuesPerLane; ++j)
+                {
+                    if (exactMask & (1u << j))
+                    {
+                        codeF[j] = CodeToFloat(myStage[j]);
+                    }
+                }
             }
         }
         else
         {
-            // ---- float -> code through the exact step table; in-band samples go to the exact path ------------
-            // Stage the raw sample bits where any lane can fetch them (the exact path runs compacted).
+            // ---- two-level table; in-band samples go to the exact evaluation, compacted across the warp ---------
+            uint32_t code[kValuesPerLane];
 #pragma unroll
             for (int q = 0; q < 6; ++q)
             {
@@ -220,27 +309,10 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
                 const uint4 w = raw[j >> 2];
                 const uint32_t bits = (j & 3) == 0 ? w.x : (j & 3) == 1 ? w.y : (j & 3) == 2 ? w.z : w.w;
                 bool inBand;
-                if (TABLE == kTableFlat)
-                {
-                    code[j] = LookupCurveCodeFlat(bits, flatBiased, flatShift, flatLow, flatHigh - flatLow, inBand);
-                }
-                else
-                {
-                    code[j] = LookupCurveCode(bits, octaves, tableWords, inBand);
-                }
+                code[j] = LookupCurveCode(bits, octaves, tableWords, inBand);
                 asm("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p or.b32 %0, %0, %2; }" : "+r"(bandMask) : "r"(static_cast<uint32_t>(inBand)), "r"(1u << j));
             }
-
-            {
-                int nextRow = tileRow + stepRows;
-                int nextX = tileX + stepX;
-                if (nextX >= tilesX)
-                {
-                    nextX -= tilesX;
-                    ++nextRow;
-                }
-                loadTile(nextRow, nextX, tile + warpCount < tileCount);
-            }
+            prefetchNext(tile);
             // Warp-level compaction: exclusive prefix sum of the per-lane counts gives every lane its queue range.
             const int mine = __popc(bandMask);
             int inclusive = mine;
@@ -292,6 +364,11 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
                 }
                 __syncwarp(); // the staging area is rewritten by the next tile
             }
+#pragma unroll
+            for (int j = 0; j < kValuesPerLane; ++j)
+            {
+                codeF[j] = CodeToFloat(code[j]);
+            }
         }
 
         if (!laneActive)
@@ -310,7 +387,7 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
             {
                 const int j = r * 12 + i * 3;
                 float yf;
-                ForwardPixel(p.matrix, code[j], code[j + 1], code[j + 2], yf, cb[r][i], cr[r][i]);
+                ForwardPixelFloat(p.matrix, codeF[j], codeF[j + 1], codeF[j + 2], yf, cb[r][i], cr[r][i]);
                 yCode[r][i] = QuantiseLuma(yf, p.maxCode);
             }
         }

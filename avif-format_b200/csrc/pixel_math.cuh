@@ -252,11 +252,8 @@ struct ForwardMatrix
 // the integer pipe is the busy one, so the conversion is cheaper here than the usual 2^23 bit trick.
 AVIF_HD float CodeToFloat(uint32_t code) { return static_cast<float>(code); }
 
-AVIF_HD void ForwardPixel(const ForwardMatrix& m, uint32_t rc, uint32_t gc, uint32_t bc, float& y, float& cb, float& cr)
+AVIF_HD void ForwardPixelFloat(const ForwardMatrix& m, float r, float g, float b, float& y, float& cb, float& cr)
 {
-    const float r = CodeToFloat(rc);
-    const float g = CodeToFloat(gc);
-    const float b = CodeToFloat(bc);
     if (m.identity)
     {
         y = g;
@@ -267,6 +264,11 @@ AVIF_HD void ForwardPixel(const ForwardMatrix& m, uint32_t rc, uint32_t gc, uint
     y = ((m.kr * r) + (m.kg * g)) + (m.kb * b);
     cb = (b - y) * m.cbScale;
     cr = (r - y) * m.crScale;
+}
+
+AVIF_HD void ForwardPixel(const ForwardMatrix& m, uint32_t rc, uint32_t gc, uint32_t bc, float& y, float& cb, float& cr)
+{
+    ForwardPixelFloat(m, CodeToFloat(rc), CodeToFloat(gc), CodeToFloat(bc), y, cb, cr);
 }
 
 // clamp((int)(v), 0, maxCode).  On the device the float -> unsigned conversion saturates negatives (and NaN) to
