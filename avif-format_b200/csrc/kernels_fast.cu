@@ -2,89 +2,53 @@
 // to kernels_generic.cu (LaunchEncodeFast / LaunchDecodeFast return 0 = "not applicable").  The arithmetic is the
 // same pixel_math.cuh; what changes is the work decomposition and where the transcendental work goes.
 //
-// Encode, float RGB -> planar YCbCr (BASELINE config 2: 7680x4320 RGB32f -> 12-bit PQ 4:2:0)
-// -----------------------------------------------------------------------------------------------
+// Encode, float RGB -> planar YCbCr: dispatch, plus the kernel for the cases kernels_fast_flat.cu does not take
+// (no transfer curve, or a curve whose step table only has the two-level form, e.g. SMPTE 428):
 //   * one warp converts a tile of 2 rows x 128 pixels; a lane owns 4 adjacent pixels in both rows = two 2x2
 //     chroma sites, so the 4:2:0 box filter needs no cross-lane traffic at all;
-//   * loads: 3 x LDG.128 per row per lane (48 contiguous bytes), a warp reads 1536 contiguous bytes per row;
-//     stores: Y 8 bytes per row per lane (256 contiguous bytes per warp), Cb / Cr 4 bytes per lane;
-//   * float -> code goes through the exact step tables of curve_tables.h (two shared-memory look-ups per
+//   * loads: 3 x LDG.128 per row per lane (48 contiguous bytes), issued one tile ahead; stores: Y 8 bytes per row
+//     per lane, Cb / Cr 4 bytes per lane;
+//   * float -> code goes through the two-level step table of curve_tables.h (two shared-memory look-ups per
 //     sample); samples inside a fuzzy band are queued per warp and evaluated with the exact glibc-identical powf
 //     at full lane occupancy (warp-level compaction), then patched back;
 //   * persistent grid: 2 CTAs of 8 warps per SM, warps stride over the tiles.
-#include "kernel_params.h"
-#include "curve_lookup.cuh"
+#include "kernels_fast_common.cuh"
 #include "../../include/avifgpu.h"
 
 #include <cuda_runtime.h>
+
 
 namespace avifgpu
 {
 
 using namespace avifpix;
+using namespace fastenc;
 using avifmath::LibmTables;
 
 namespace
 {
 
-#ifndef AVIF_FLAT_THREADS
-#define AVIF_FLAT_THREADS 512
-#endif
-constexpr int kTilePixels = 128;     // per row
-constexpr int kValuesPerLane = 24;   // 2 rows x 4 pixels x 3 channels
 constexpr int kLaneStrideWords = 28; // staging stride per lane (16-byte aligned, conflict-free for STS.128)
-constexpr int kCurveClip = 2;        // no transfer curve: code = trunc(clamp(v * max))
-constexpr int kTableTwoLevel = 0;
-constexpr int kTableFlat = 1;
-
-struct FastEncodeParams
-{
-    const uint8_t* rows;
-    int64_t rowStride;
-    uint8_t* planeY;
-    int64_t strideY;
-    uint8_t* planeCb;
-    int64_t strideCb;
-    uint8_t* planeCr;
-    int64_t strideCr;
-    int32_t width;    // multiple of 4
-    int32_t rowCount; // even when the chroma is vertically sub-sampled
-    float pqMultiplier;
-    float maxCodeFloat;
-    int32_t maxCode;
-    ForwardMatrix matrix;
-    float chromaOffset;
-    int32_t topLeft;
-    CurveTableView table;
-};
 
 // Shared-memory carve-up (bytes).
-constexpr int kSharedLibm = 768;
 constexpr int kSharedOctaves = 2048;
 constexpr int kSharedStagePerWarp = 32 * kLaneStrideWords * 4;   // sample bits, later the exact codes
 constexpr int kQueueCapacity = 256;                              // in-band samples per exact-path round (uint16 slots)
 constexpr int kSharedQueuePerWarp = kQueueCapacity * 2;
 __host__ __device__ constexpr int SharedFixedBytes(int warps) { return kSharedLibm + kSharedOctaves + warps * (kSharedStagePerWarp + kSharedQueuePerWarp); }
 
-// The flat table (128 KB for 12-bit PQ) leaves room for one CTA per SM: 16 warps.  Measured alternatives on the
-// 8K PQ frame (Gpx/s): 16 warps, direct 48-byte-per-lane loads 170 | same with loads remapped to be perfectly
-// coalesced through the staging area 158 | 24 warps at 58 registers 140 | register prefetch of the next tile 150 |
-// 12 warps with cp.async double-buffered staging 120.  The kernel is bound by instruction issue; resident warps
-// with enough registers to interleave the 24 independent look-ups matter more than how the bytes arrive.
-// The two-level table is small enough for two CTAs of 8 warps.
-template <int TABLE>
 struct FastConfig
 {
-    static constexpr int threads = TABLE == kTableFlat ? AVIF_FLAT_THREADS : 256;
+    static constexpr int threads = 256;
     static constexpr int warps = threads / 32;
-    static constexpr int blocksPerSm = TABLE == kTableFlat ? 1 : 2;
-    static constexpr int sharedLimit = TABLE == kTableFlat ? 227 * 1024 : 112 * 1024;
+    static constexpr int blocksPerSm = 2;
+    static constexpr int sharedLimit = 112 * 1024;
 };
 
-template <int CURVE, int XS, int YS, int TABLE>
-__global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>::blocksPerSm) EncodeRgbF32PlanarKernel(const FastEncodeParams p)
+template <int CURVE, int XS, int YS>
+__global__ void __launch_bounds__(FastConfig::threads, FastConfig::blocksPerSm) EncodeRgbF32PlanarKernel(const FastEncodeParams p)
 {
-    constexpr int kFastWarps = FastConfig<TABLE>::warps;
+    constexpr int kFastWarps = FastConfig::warps;
     constexpr int kSharedFixed = SharedFixedBytes(kFastWarps);
     extern __shared__ __align__(16) uint8_t sharedBytes[];
     uint64_t* libmStorage = reinterpret_cast<uint64_t*>(sharedBytes);
@@ -92,33 +56,17 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
     uint32_t* stageAll = reinterpret_cast<uint32_t*>(sharedBytes + kSharedLibm + kSharedOctaves);
     uint16_t* queueAll = reinterpret_cast<uint16_t*>(sharedBytes + kSharedLibm + kSharedOctaves + kFastWarps * kSharedStagePerWarp);
     uint32_t* tableWords = reinterpret_cast<uint32_t*>(sharedBytes + kSharedFixed);
-    uint2* flatEntries = reinterpret_cast<uint2*>(sharedBytes + kSharedFixed);
 
     const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
     if (CURVE != kCurveClip)
     {
-        if (TABLE == kTableFlat)
+        for (int i = threadIdx.x; i < 256; i += blockDim.x)
         {
-            // 128 KB from L2: 128-bit copies, eight in flight per thread (the table is 16-byte aligned, count is even-padded)
-            const uint4* source = reinterpret_cast<const uint4*>(p.table.flat);
-            uint4* target = reinterpret_cast<uint4*>(flatEntries);
-            const int pairs = (p.table.flatCount + 1) / 2;
-#pragma unroll 8
-            for (int i = threadIdx.x; i < pairs; i += blockDim.x)
-            {
-                target[i] = __ldg(source + i);
-            }
+            octaves[i] = p.table.octaves[i];
         }
-        else
+        for (int i = threadIdx.x; i < p.table.bucketCount; i += blockDim.x)
         {
-            for (int i = threadIdx.x; i < 256; i += blockDim.x)
-            {
-                octaves[i] = p.table.octaves[i];
-            }
-            for (int i = threadIdx.x; i < p.table.bucketCount; i += blockDim.x)
-            {
-                tableWords[i] = p.table.buckets[i];
-            }
+            tableWords[i] = p.table.buckets[i];
         }
     }
     __syncthreads();
@@ -128,10 +76,6 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
     uint32_t* stage = stageAll + warpInBlock * (32 * kLaneStrideWords);
     uint32_t* myStage = stage + lane * kLaneStrideWords;
     uint16_t* queue = queueAll + warpInBlock * kQueueCapacity;
-    const uint32_t bandStrideLog2 = p.table.bandStrideLog2;
-    const uint32_t flatShift = p.table.flatShift;
-    const int32_t flatLow = static_cast<int32_t>(p.table.flatLow);
-    const int32_t flatHigh = static_cast<int32_t>(p.table.flatHigh);
 
     const int tilesX = (p.width + kTilePixels - 1) / kTilePixels;
     const int tileRows = (p.rowCount + 1) / 2;
@@ -205,93 +149,6 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
                 codeF[4 * q + 3] = CodeToFloat(FloatToCode(__uint_as_float(raw[q].w), p.maxCodeFloat));
             }
             prefetchNext(tile);
-        }
-        else if (TABLE == kTableFlat)
-        {
-            // ---- float -> code through the exact step table; in-band samples are resolved by the band bitmap ----
-            // The raw bits stay reachable by a run-time index (the rare paths below) through the lane's staging row.
-#pragma unroll
-            for (int q = 0; q < 6; ++q)
-            {
-                *reinterpret_cast<uint4*>(myStage + 4 * q) = raw[q];
-            }
-            uint32_t bandMask = 0;
-            int32_t largest = 0; // max over the samples as signed integers: > 0x7f7fffff <=> a +inf / NaN is among them
-#pragma unroll
-            for (int j = 0; j < kValuesPerLane; ++j)
-            {
-                const uint4 w = raw[j >> 2];
-                const uint32_t bits = (j & 3) == 0 ? w.x : (j & 3) == 1 ? w.y : (j & 3) == 2 ? w.z : w.w;
-                bool inBand;
-                codeF[j] = LookupCurveFlat(bits, flatEntries, flatShift, -flatLow, flatHigh - flatLow, inBand);
-                asm("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p or.b32 %0, %0, %2; }" : "+r"(bandMask) : "r"(static_cast<uint32_t>(inBand)), "r"(1u << j));
-                if (j % 3 == 2)
-                {
-                    const uint4 w1 = raw[(j - 1) >> 2];
-                    const uint4 w2 = raw[(j - 2) >> 2];
-                    const uint32_t bits1 = ((j - 1) & 3) == 0 ? w1.x : ((j - 1) & 3) == 1 ? w1.y : ((j - 1) & 3) == 2 ? w1.z : w1.w;
-                    const uint32_t bits2 = ((j - 2) & 3) == 0 ? w2.x : ((j - 2) & 3) == 1 ? w2.y : ((j - 2) & 3) == 2 ? w2.z : w2.w;
-                    largest = max(largest, __vimax3_s32(static_cast<int32_t>(bits), static_cast<int32_t>(bits1), static_cast<int32_t>(bits2)));
-                }
-            }
-            prefetchNext(tile);
-
-            // +inf / NaN (never in real frames): flag them for the exact evaluation.
-            uint32_t exactMask = 0;
-            if (__any_sync(0xffffffffu, largest > 0x7f7fffff))
-            {
-#pragma unroll
-                for (int j = 0; j < kValuesPerLane; ++j)
-                {
-                    if (static_cast<int32_t>(myStage[j]) > 0x7f7fffff)
-                    {
-                        exactMask |= 1u << j;
-                    }
-                }
-            }
-
-            // In-band samples (~1.5 % of typical data, so a lane rarely has more than one): one bit of the L2-resident
-            // band bitmap says whether the exact code is the table's kUpper or one less.
-            uint32_t lowerMask = 0;
-            {
-                uint32_t pending = bandMask;
-                while (pending != 0)
-                {
-                    const int j = __ffs(static_cast<int>(pending)) - 1;
-                    pending &= pending - 1;
-                    const uint32_t bits = myStage[j];
-                    bool inBand;
-                    uint2 entry;
-                    LookupCurveFlat(bits, flatEntries, flatShift, -flatLow, flatHigh - flatLow, inBand, entry);
-                    const uint32_t bitIndex = BandBitIndex(bits, entry, bandStrideLog2);
-                    const uint32_t word = __ldg(p.table.bandBits + (bitIndex >> 5));
-                    lowerMask |= (((word >> (bitIndex & 31u)) & 1u) ^ 1u) << j;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kValuesPerLane; ++j)
-            {
-                asm("{ .reg .pred p; .reg .b32 t; and.b32 t, %1, %2; setp.ne.u32 p, t, 0; @p add.rn.f32 %0, %0, 0fBF800000; }"
-                    : "+f"(codeF[j]) : "r"(lowerMask), "r"(1u << j));
-            }
-            if (__any_sync(0xffffffffu, exactMask != 0))
-            {
-                uint32_t pending = exactMask;
-                while (pending != 0)
-                {
-                    const int j = __ffs(static_cast<int>(pending)) - 1;
-                    pending &= pending - 1;
-                    myStage[j] = ExactCurveCode<CURVE == kCurveClip ? kCurveLinearToPQ : CURVE>(__uint_as_float(myStage[j]), p.pqMultiplier, p.maxCodeFloat, t);
-                }
-#pragma unroll
-                for (int j = 0; j < kValuesPerLane; ++j)
-                {
-                    if (exactMask & (1u << j))
-                    {
-                        codeF[j] = CodeToFloat(myStage[j]);
-                    }
-                }
-            }
         }
         else
         {
@@ -376,116 +233,31 @@ __global__ void __launch_bounds__(FastConfig<TABLE>::threads, FastConfig<TABLE>:
             continue;
         }
 
-        // ---- forward matrix, luma quantisation, chroma down-filter ------------------------------------------
-        float cb[2][4], cr[2][4];
-        uint32_t yCode[2][4];
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
         {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-            {
-                const int j = r * 12 + i * 3;
-                float yf;
-                ForwardPixelFloat(p.matrix, codeF[j], codeF[j + 1], codeF[j + 2], yf, cb[r][i], cr[r][i]);
-                yCode[r][i] = QuantiseLuma(yf, p.maxCode);
-            }
-        }
-        {
-            uint8_t* yRow = p.planeY + static_cast<int64_t>(y0) * p.strideY + static_cast<int64_t>(x0) * 2;
-            const uint2 packed0 = make_uint2(yCode[0][0] | (yCode[0][1] << 16), yCode[0][2] | (yCode[0][3] << 16));
-            __stcs(reinterpret_cast<uint2*>(yRow), packed0);
-            if (secondRow)
-            {
-                const uint2 packed1 = make_uint2(yCode[1][0] | (yCode[1][1] << 16), yCode[1][2] | (yCode[1][3] << 16));
-                __stcs(reinterpret_cast<uint2*>(yRow + p.strideY), packed1);
-            }
-        }
-        if (XS == 1 && YS == 1)
-        {
-            uint32_t cbCode[2], crCode[2];
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-            {
-                float cbv, crv;
-                if (p.topLeft)
-                {
-                    cbv = cb[0][2 * s];
-                    crv = cr[0][2 * s];
-                }
-                else
-                {
-                    cbv = ((cb[0][2 * s] + cb[0][2 * s + 1]) + (cb[1][2 * s] + cb[1][2 * s + 1])) * 0.25f;
-                    crv = ((cr[0][2 * s] + cr[0][2 * s + 1]) + (cr[1][2 * s] + cr[1][2 * s + 1])) * 0.25f;
-                }
-                cbCode[s] = QuantiseChroma(cbv, p.chromaOffset, p.maxCode);
-                crCode[s] = QuantiseChroma(crv, p.chromaOffset, p.maxCode);
-            }
-            const int64_t column = static_cast<int64_t>(x0 >> 1) * 2;
-            __stcs(reinterpret_cast<uint32_t*>(p.planeCb + static_cast<int64_t>(tileRow) * p.strideCb + column), cbCode[0] | (cbCode[1] << 16));
-            __stcs(reinterpret_cast<uint32_t*>(p.planeCr + static_cast<int64_t>(tileRow) * p.strideCr + column), crCode[0] | (crCode[1] << 16));
-        }
-        else if (XS == 1)
-        {
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-            {
-                if (r == 1 && !secondRow) break;
-                uint32_t cbCode[2], crCode[2];
-#pragma unroll
-                for (int s = 0; s < 2; ++s)
-                {
-                    const float cbv = p.topLeft ? cb[r][2 * s] : (cb[r][2 * s] + cb[r][2 * s + 1]) * 0.5f;
-                    const float crv = p.topLeft ? cr[r][2 * s] : (cr[r][2 * s] + cr[r][2 * s + 1]) * 0.5f;
-                    cbCode[s] = QuantiseChroma(cbv, p.chromaOffset, p.maxCode);
-                    crCode[s] = QuantiseChroma(crv, p.chromaOffset, p.maxCode);
-                }
-                const int64_t column = static_cast<int64_t>(x0 >> 1) * 2;
-                __stcs(reinterpret_cast<uint32_t*>(p.planeCb + static_cast<int64_t>(y0 + r) * p.strideCb + column), cbCode[0] | (cbCode[1] << 16));
-                __stcs(reinterpret_cast<uint32_t*>(p.planeCr + static_cast<int64_t>(y0 + r) * p.strideCr + column), crCode[0] | (crCode[1] << 16));
-            }
-        }
-        else
-        {
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-            {
-                if (r == 1 && !secondRow) break;
-                uint32_t cbCode[4], crCode[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                {
-                    cbCode[i] = QuantiseChroma(cb[r][i], p.chromaOffset, p.maxCode);
-                    crCode[i] = QuantiseChroma(cr[r][i], p.chromaOffset, p.maxCode);
-                }
-                const int64_t column = static_cast<int64_t>(x0) * 2;
-                __stcs(reinterpret_cast<uint2*>(p.planeCb + static_cast<int64_t>(y0 + r) * p.strideCb + column),
-                       make_uint2(cbCode[0] | (cbCode[1] << 16), cbCode[2] | (cbCode[3] << 16)));
-                __stcs(reinterpret_cast<uint2*>(p.planeCr + static_cast<int64_t>(y0 + r) * p.strideCr + column),
-                       make_uint2(crCode[0] | (crCode[1] << 16), crCode[2] | (crCode[3] << 16)));
-            }
+            const int64_t chromaRow = YS ? tileRow : y0;
+            const int64_t chromaColumn = static_cast<int64_t>(XS ? (x0 >> 1) : x0) * 2;
+            StoreTile<XS, YS>(p, codeF, p.planeY + static_cast<int64_t>(y0) * p.strideY + static_cast<int64_t>(x0) * 2,
+                              p.planeCb + chromaRow * p.strideCb + chromaColumn, p.planeCr + chromaRow * p.strideCr + chromaColumn, secondRow);
         }
     }
 }
 
-template <int CURVE, int XS, int YS, int TABLE>
+template <int CURVE, int XS, int YS>
 size_t FastEncodeSharedBytes(const FastEncodeParams& fp)
 {
-    const size_t tableBytes = CURVE == kCurveClip ? 0
-                              : (TABLE == kTableFlat ? static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4)
-                                                     : static_cast<size_t>(fp.table.bucketCount) * sizeof(uint32_t));
-    return static_cast<size_t>(SharedFixedBytes(FastConfig<TABLE>::warps)) + tableBytes;
+    const size_t tableBytes = CURVE == kCurveClip ? 0 : static_cast<size_t>(fp.table.bucketCount) * sizeof(uint32_t);
+    return static_cast<size_t>(SharedFixedBytes(FastConfig::warps)) + tableBytes;
 }
 
-template <int CURVE, int XS, int YS, int TABLE>
+template <int CURVE, int XS, int YS>
 cudaError_t LaunchFastEncodeKernel(const FastEncodeParams& fp, int smCount, cudaStream_t stream)
 {
-    using Config = FastConfig<TABLE>;
-    const size_t shared = FastEncodeSharedBytes<CURVE, XS, YS, TABLE>(fp);
+    using Config = FastConfig;
+    const size_t shared = FastEncodeSharedBytes<CURVE, XS, YS>(fp);
     static bool configured = false; // per instantiation
     if (!configured)
     {
-        const cudaError_t e = cudaFuncSetAttribute(EncodeRgbF32PlanarKernel<CURVE, XS, YS, TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        const cudaError_t e = cudaFuncSetAttribute(EncodeRgbF32PlanarKernel<CURVE, XS, YS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    Config::sharedLimit);
         if (e != cudaSuccess)
         {
@@ -508,28 +280,26 @@ cudaError_t LaunchFastEncodeKernel(const FastEncodeParams& fp, int smCount, cuda
     {
         blocks = resident;
     }
-    EncodeRgbF32PlanarKernel<CURVE, XS, YS, TABLE><<<static_cast<unsigned>(blocks), Config::threads, shared, stream>>>(fp);
+    EncodeRgbF32PlanarKernel<CURVE, XS, YS><<<static_cast<unsigned>(blocks), Config::threads, shared, stream>>>(fp);
     return cudaGetLastError();
 }
 
-template <int CURVE, int TABLE>
+template <int CURVE>
 cudaError_t DispatchChroma(const FastEncodeParams& fp, int xs, int ys, int smCount, cudaStream_t stream)
 {
-    if (xs == 1 && ys == 1) return LaunchFastEncodeKernel<CURVE, 1, 1, TABLE>(fp, smCount, stream);
-    if (xs == 1) return LaunchFastEncodeKernel<CURVE, 1, 0, TABLE>(fp, smCount, stream);
-    return LaunchFastEncodeKernel<CURVE, 0, 0, TABLE>(fp, smCount, stream);
+    if (xs == 1 && ys == 1) return LaunchFastEncodeKernel<CURVE, 1, 1>(fp, smCount, stream);
+    if (xs == 1) return LaunchFastEncodeKernel<CURVE, 1, 0>(fp, smCount, stream);
+    return LaunchFastEncodeKernel<CURVE, 0, 0>(fp, smCount, stream);
 }
 
 template <int CURVE>
 cudaError_t DispatchTable(const FastEncodeParams& fp, int xs, int ys, int smCount, cudaStream_t stream)
 {
-    if (fp.table.flat != nullptr &&
-        static_cast<size_t>(SharedFixedBytes(FastConfig<kTableFlat>::warps)) + static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4) <=
-            static_cast<size_t>(FastConfig<kTableFlat>::sharedLimit))
+    if (FlatEncodeApplies(fp))
     {
-        return DispatchChroma<CURVE, kTableFlat>(fp, xs, ys, smCount, stream);
+        return LaunchFastEncodeFlat(fp, CURVE, xs, ys, smCount, stream);
     }
-    return DispatchChroma<CURVE, kTableTwoLevel>(fp, xs, ys, smCount, stream);
+    return DispatchChroma<CURVE>(fp, xs, ys, smCount, stream);
 }
 
 bool Aligned(const void* p, int64_t stride, int alignment)
@@ -556,6 +326,10 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
     if (curve != kCurveClip && (p.curveTable == nullptr || p.curveTable->buckets == nullptr))
     {
         return 0; // no verified table for this curve: the generic exact kernel serves it
+    }
+    if (!ForwardMatrixStaysInRange(p.matrix, p.chromaOffset, static_cast<int>(p.maxCode)))
+    {
+        return 0; // an exotic matrix: the generic kernel clamps
     }
     if (!Aligned(p.rows, p.rowStride, 16) || !Aligned(p.plane[0], p.planeStride[0], 8) ||
         !Aligned(p.plane[1], p.planeStride[1], p.xs ? 4 : 8) || !Aligned(p.plane[2], p.planeStride[2], p.xs ? 4 : 8))
@@ -595,7 +369,7 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
     cudaError_t e;
     if (curve == kCurveLinearToPQ) e = DispatchTable<kCurveLinearToPQ>(fp, p.xs, p.ys, smCount, stream);
     else if (curve == kCurveLinearToSMPTE428) e = DispatchTable<kCurveLinearToSMPTE428>(fp, p.xs, p.ys, smCount, stream);
-    else e = DispatchChroma<kCurveClip, kTableTwoLevel>(fp, p.xs, p.ys, smCount, stream);
+    else e = DispatchChroma<kCurveClip>(fp, p.xs, p.ys, smCount, stream);
     if (e != cudaSuccess)
     {
         return AVIFGPU_ERR_CUDA;

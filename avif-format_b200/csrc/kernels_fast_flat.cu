@@ -1,0 +1,368 @@
+// kernels_fast_flat.cu -- the float RGB -> planar YCbCr encode kernel for curves whose step table has the flat
+// form (curve_tables.h): BASELINE config 2, 7680x4320 RGB32f -> 12-bit PQ 4:2:0.
+//
+//   * one CTA per SM, kFlatWarps warps; the 128 KB flat table sits in shared memory next to one 3 KB staging
+//     buffer per warp.  Measured on the 8K PQ frame (Gpx/s): 16 warps 238 | 20: 251 | 24: 273 | 28: 278 | 30: 267
+//     (30 leaves 64 registers); the kernel is bound by instruction issue and shared-memory wavefronts, so resident
+//     warps matter, and the copy engine keeps the per-warp register cost of a fetch at zero;
+//   * a warp converts tiles of 2 rows x 128 pixels.  The two 1536-byte row segments of a tile are fetched by the
+//     copy engine (cp.async.bulk, completion on the warp's own mbarrier) straight into the staging buffer, so the
+//     fetch of tile i+1 costs the warp two instructions and no registers and overlaps the matrix and the stores of
+//     tile i; the lanes then read their 48 bytes per row with three conflict-free LDS.128;
+//   * float -> code: one 64-bit table look-up per sample (LookupCurveFlat); samples inside a fuzzy band (~1.5 %)
+//     are resolved by one bit of the L2-resident band bitmap, fetched for up to two samples of a lane at a time;
+//     +inf / NaN take the exact glibc-identical evaluation;
+//   * forward matrix, quantisation, chroma down-filter and stores: StoreTile (kernels_fast_common.cuh).
+#include "kernels_fast_common.cuh"
+#include "../../include/avifgpu.h"
+
+namespace avifgpu
+{
+
+using namespace avifpix;
+using namespace fastenc;
+using avifmath::LibmTables;
+
+namespace
+{
+
+#ifndef AVIF_FLAT_WARPS
+#define AVIF_FLAT_WARPS 28
+#endif
+constexpr int kFlatWarps = AVIF_FLAT_WARPS;
+constexpr int kFlatThreads = kFlatWarps * 32;
+constexpr int kRowSegmentBytes = kTilePixels * 12;      // one tile row of RGB32f
+constexpr int kStageBytesPerWarp = 2 * kRowSegmentBytes; // both rows, linear
+constexpr int kRowSegmentWords = kRowSegmentBytes / 4;
+constexpr int kSharedBarriers = 256;                     // kFlatWarps x 8 bytes, padded
+constexpr int kSharedLimit = 227 * 1024;
+__host__ __device__ constexpr int FlatFixedBytes() { return kSharedLibm + kSharedBarriers + kFlatWarps * kStageBytesPerWarp; }
+
+// How the persistent warps walk the tiles, worked out once on the host (the grid is known at launch) so that the
+// kernel's per-tile bookkeeping is additions of launch constants.
+struct FlatSchedule
+{
+    int32_t tilesX, tileCount, warpCount;
+    int32_t stepRows, stepX;          // warpCount tiles further = stepRows tile rows down and stepX columns right ...
+    int32_t lastColumnBytes;          // row-segment bytes of the last tile column (width need not be a multiple of 128)
+    int32_t unpairedTileRow;          // tile row whose second image row does not exist (odd row count), or -1
+    int64_t advanceSource[2], advanceY[2], advanceCb[2], advanceCr[2]; // byte advance per step: [0] plain, [1] with a column wrap
+};
+
+__device__ __forceinline__ uint32_t SharedAddress(const void* pointer) { return static_cast<uint32_t>(__cvta_generic_to_shared(pointer)); }
+
+// One lane of the (converged) warp.
+__device__ __forceinline__ bool ElectOne()
+{
+    uint32_t elected;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(elected));
+    return elected != 0;
+}
+
+__device__ __forceinline__ void BarrierInit(uint32_t barrier, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barrier), "r"(arrivals) : "memory");
+}
+
+__device__ __forceinline__ void BarrierExpect(uint32_t barrier, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barrier), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void BulkCopyToShared(uint32_t target, const void* source, uint32_t bytes, uint32_t barrier)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(target), "l"(source), "r"(bytes),
+                 "r"(barrier)
+                 : "memory");
+}
+
+__device__ __forceinline__ void BarrierWait(uint32_t barrier, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred done;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n"
+        "@done bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(barrier),
+        "r"(parity)
+        : "memory");
+}
+
+template <int CURVE, int XS, int YS>
+__global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const FastEncodeParams p, const FlatSchedule schedule)
+{
+    extern __shared__ __align__(128) uint8_t sharedBytes[];
+    uint64_t* libmStorage = reinterpret_cast<uint64_t*>(sharedBytes);
+    uint64_t* barriers = reinterpret_cast<uint64_t*>(sharedBytes + kSharedLibm);
+    uint8_t* stageAll = sharedBytes + kSharedLibm + kSharedBarriers;
+    uint2* flatEntries = reinterpret_cast<uint2*>(sharedBytes + FlatFixedBytes());
+
+    const int lane = threadIdx.x & 31;
+    // Read through a shuffle so the compiler knows the warp index (and everything derived from it: tile coordinates,
+    // copy addresses) is warp-uniform and keeps it in the uniform datapath, which the bulk-copy instruction needs.
+    const int warpInBlock = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const uint32_t barrier = SharedAddress(barriers + warpInBlock);
+    uint32_t* stage = reinterpret_cast<uint32_t*>(stageAll + warpInBlock * kStageBytesPerWarp);
+    const uint32_t stageAddress = SharedAddress(stage);
+    const uint32_t* myStage = stage + lane * 12; // row 0; row 1 is kRowSegmentWords further
+
+    const int tilesX = schedule.tilesX;
+    const int tileCount = schedule.tileCount;
+    const int warpCount = schedule.warpCount;
+    const int firstTile = static_cast<int>(blockIdx.x) * kFlatWarps + warpInBlock;
+    int tileRow = firstTile / tilesX;
+    int tileX = firstTile - tileRow * tilesX;
+
+    // The tile's origin in the source rows (warp-uniform byte offset) and the lane's first sample in the three planes;
+    // all advanced by launch constants.
+    constexpr int kChromaRowsPerTile = YS ? 1 : 2;
+    constexpr int kChromaTileBytes = XS ? kTilePixels : 2 * kTilePixels;
+    int64_t sourceOffset = static_cast<int64_t>(tileRow) * 2 * p.rowStride + static_cast<int64_t>(tileX) * kRowSegmentBytes;
+    uint8_t* yPointer = p.planeY + static_cast<int64_t>(tileRow) * 2 * p.strideY + static_cast<int64_t>(tileX) * (2 * kTilePixels) + lane * 8;
+    uint8_t* cbPointer = p.planeCb + static_cast<int64_t>(tileRow) * kChromaRowsPerTile * p.strideCb + static_cast<int64_t>(tileX) * kChromaTileBytes + lane * (XS ? 4 : 8);
+    uint8_t* crPointer = p.planeCr + static_cast<int64_t>(tileRow) * kChromaRowsPerTile * p.strideCr + static_cast<int64_t>(tileX) * kChromaTileBytes + lane * (XS ? 4 : 8);
+
+    // One elected lane asks the copy engine for a tile's row segments.
+    auto fetchTile = [&](int row, int column, int64_t offset)
+    {
+        const uint32_t bytes = column == tilesX - 1 ? static_cast<uint32_t>(schedule.lastColumnBytes) : static_cast<uint32_t>(kRowSegmentBytes);
+        const bool second = row != schedule.unpairedTileRow;
+        const uint8_t* source = p.rows + offset;
+        BarrierExpect(barrier, second ? 2u * bytes : bytes);
+        BulkCopyToShared(stageAddress, source, bytes, barrier);
+        if (second)
+        {
+            BulkCopyToShared(stageAddress + kRowSegmentBytes, source + p.rowStride, bytes, barrier);
+        }
+    };
+
+    if (ElectOne())
+    {
+        BarrierInit(barrier, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (firstTile < tileCount)
+        {
+            fetchTile(tileRow, tileX, sourceOffset); // in flight while the table is staged
+        }
+    }
+
+    const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
+    {
+        // 128 KB from L2: 128-bit copies, eight in flight per thread (the table is 16-byte aligned, count is even-padded)
+        const uint4* source = reinterpret_cast<const uint4*>(p.table.flat);
+        uint4* target = reinterpret_cast<uint4*>(flatEntries);
+        const int pairs = (p.table.flatCount + 1) / 2;
+#pragma unroll 8
+        for (int i = threadIdx.x; i < pairs; i += blockDim.x)
+        {
+            target[i] = __ldg(source + i);
+        }
+    }
+    __syncthreads();
+
+    const uint32_t flatShift = p.table.flatShift;
+    const int32_t negativeLow = -static_cast<int32_t>(p.table.flatLow);
+    const int32_t span = static_cast<int32_t>(p.table.flatHigh - p.table.flatLow);
+    const uint32_t bandStrideLog2 = p.table.bandStrideLog2;
+    const uint32_t* __restrict__ bandBits = p.table.bandBits;
+    uint32_t parity = 0;
+
+#pragma unroll 1
+    for (int tile = firstTile; tile < tileCount; tile += warpCount)
+    {
+        const bool laneActive = tileX * kTilePixels + lane * 4 < p.width;
+        const bool secondRow = tileRow != schedule.unpairedTileRow;
+        // where this warp goes next
+        int nextRow = tileRow + schedule.stepRows;
+        int nextX = tileX + schedule.stepX;
+        const bool wraps = nextX >= tilesX;
+        if (wraps)
+        {
+            nextX -= tilesX;
+            ++nextRow;
+        }
+        const int64_t nextSourceOffset = sourceOffset + (wraps ? schedule.advanceSource[1] : schedule.advanceSource[0]);
+
+        BarrierWait(barrier, parity);
+        parity ^= 1u;
+
+        // ---- float -> code through the exact step table ------------------------------------------------------------
+        float codeF[kValuesPerLane]; // the codes, as the floats the forward matrix consumes
+        uint32_t bandMask = 0;
+        int32_t largest = 0; // max over the samples as signed integers: > 0x7f7fffff <=> a +inf / NaN is among them
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+        {
+            const uint4 w = *reinterpret_cast<const uint4*>(myStage + (q / 3) * kRowSegmentWords + (q % 3) * 4);
+            const uint32_t bits[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+            {
+                const int j = 4 * q + e;
+                bool inBand;
+                codeF[j] = LookupCurveFlat(bits[e], flatEntries, flatShift, negativeLow, span, inBand);
+                asm("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p or.b32 %0, %0, %2; }" : "+r"(bandMask) : "r"(static_cast<uint32_t>(inBand)), "r"(1u << j));
+            }
+            largest = max(largest, __vimax3_s32(static_cast<int32_t>(w.x), static_cast<int32_t>(w.y), static_cast<int32_t>(w.z)));
+            largest = max(largest, static_cast<int32_t>(w.w));
+        }
+
+        // ---- in-band samples: one bit of the band bitmap each, two loads in flight per lane ---------------------------
+        auto stagedBits = [&](int j) { return myStage[j + (j >= 12 ? kRowSegmentWords - 12 : 0)]; };
+        uint32_t lowerMask = 0; // samples whose exact code is one below the table's
+        {
+            uint32_t pending = bandMask;
+            while (pending != 0)
+            {
+                const int j0 = __ffs(static_cast<int>(pending)) - 1;
+                pending &= pending - 1;
+                const uint32_t bits0 = stagedBits(j0);
+                bool inBand;
+                uint2 entry0;
+                LookupCurveFlat(bits0, flatEntries, flatShift, negativeLow, span, inBand, entry0);
+                const uint32_t index0 = BandBitIndex(bits0, entry0, bandStrideLog2);
+                const uint32_t word0 = __ldg(bandBits + (index0 >> 5));
+                uint32_t word1 = 0xffffffffu, index1 = 0, sample1 = 0;
+                if (pending != 0)
+                {
+                    const int j1 = __ffs(static_cast<int>(pending)) - 1;
+                    pending &= pending - 1;
+                    const uint32_t bits1 = stagedBits(j1);
+                    uint2 entry1;
+                    LookupCurveFlat(bits1, flatEntries, flatShift, negativeLow, span, inBand, entry1);
+                    index1 = BandBitIndex(bits1, entry1, bandStrideLog2);
+                    word1 = __ldg(bandBits + (index1 >> 5));
+                    sample1 = 1u << j1;
+                }
+                lowerMask |= (((word0 >> (index0 & 31u)) & 1u) ^ 1u) << j0;
+                if (((word1 >> (index1 & 31u)) & 1u) == 0)
+                {
+                    lowerMask |= sample1;
+                }
+            }
+        }
+
+        // ---- +inf / NaN (never in real frames): the exact evaluation, lane by lane ------------------------------------
+        if (__any_sync(0xffffffffu, largest > 0x7f7fffff))
+        {
+            for (int j = 0; j < kValuesPerLane; ++j)
+            {
+                const uint32_t bits = stagedBits(j);
+                if (static_cast<int32_t>(bits) > 0x7f7fffff)
+                {
+                    const float exact = CodeToFloat(ExactCurveCode<CURVE>(__uint_as_float(bits), p.pqMultiplier, p.maxCodeFloat, t));
+#pragma unroll
+                    for (int slot = 0; slot < kValuesPerLane; ++slot)
+                    {
+                        if (slot == j)
+                        {
+                            codeF[slot] = exact;
+                        }
+                    }
+                }
+            }
+        }
+
+        // The staging buffer is free: fetch the next tile while this one goes through the matrix and the stores.
+        __syncwarp();
+        if (tile + warpCount < tileCount && ElectOne())
+        {
+            fetchTile(nextRow, nextX, nextSourceOffset);
+        }
+
+#pragma unroll
+        for (int j = 0; j < kValuesPerLane; ++j)
+        {
+            if (lowerMask & (1u << j))
+            {
+                codeF[j] -= 1.0f;
+            }
+        }
+
+        if (laneActive)
+        {
+            StoreTile<XS, YS>(p, codeF, yPointer, cbPointer, crPointer, secondRow);
+        }
+        tileRow = nextRow;
+        tileX = nextX;
+        sourceOffset = nextSourceOffset;
+        yPointer += wraps ? schedule.advanceY[1] : schedule.advanceY[0];
+        cbPointer += wraps ? schedule.advanceCb[1] : schedule.advanceCb[0];
+        crPointer += wraps ? schedule.advanceCr[1] : schedule.advanceCr[0];
+    }
+}
+
+template <int CURVE, int XS, int YS>
+cudaError_t LaunchFlatKernel(const FastEncodeParams& fp, int smCount, cudaStream_t stream)
+{
+    const size_t shared = static_cast<size_t>(FlatFixedBytes()) + static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
+    static bool configured = false; // per instantiation
+    if (!configured)
+    {
+        const cudaError_t e = cudaFuncSetAttribute(EncodeRgbF32FlatKernel<CURVE, XS, YS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSharedLimit);
+        if (e != cudaSuccess)
+        {
+            return e;
+        }
+        configured = true;
+    }
+    const long long tiles = static_cast<long long>((fp.width + kTilePixels - 1) / kTilePixels) * ((fp.rowCount + 1) / 2);
+    if (tiles > 0x7fffffffll || shared > static_cast<size_t>(kSharedLimit))
+    {
+        return cudaErrorInvalidValue;
+    }
+    long long blocks = (tiles + kFlatWarps - 1) / kFlatWarps;
+    if (blocks > smCount)
+    {
+        blocks = smCount;
+    }
+    constexpr int64_t chromaRowsPerTile = YS ? 1 : 2;
+    constexpr int64_t chromaTileBytes = XS ? kTilePixels : 2 * kTilePixels;
+    FlatSchedule schedule{};
+    schedule.tilesX = (fp.width + kTilePixels - 1) / kTilePixels;
+    schedule.tileCount = static_cast<int32_t>(tiles);
+    schedule.warpCount = static_cast<int32_t>(blocks) * kFlatWarps;
+    schedule.stepRows = schedule.warpCount / schedule.tilesX;
+    schedule.stepX = schedule.warpCount % schedule.tilesX;
+    schedule.lastColumnBytes = (fp.width - (schedule.tilesX - 1) * kTilePixels) * 12;
+    schedule.unpairedTileRow = (fp.rowCount & 1) ? fp.rowCount / 2 : -1;
+    const auto advance = [&](int64_t rowBytes, int64_t tileBytes, int64_t out[2])
+    {
+        out[0] = schedule.stepRows * rowBytes + schedule.stepX * tileBytes;
+        out[1] = out[0] + rowBytes - schedule.tilesX * tileBytes;
+    };
+    advance(2 * fp.rowStride, kRowSegmentBytes, schedule.advanceSource);
+    advance(2 * fp.strideY, 2 * kTilePixels, schedule.advanceY);
+    advance(chromaRowsPerTile * fp.strideCb, chromaTileBytes, schedule.advanceCb);
+    advance(chromaRowsPerTile * fp.strideCr, chromaTileBytes, schedule.advanceCr);
+    EncodeRgbF32FlatKernel<CURVE, XS, YS><<<static_cast<unsigned>(blocks), kFlatThreads, shared, stream>>>(fp, schedule);
+    return cudaGetLastError();
+}
+
+template <int CURVE>
+cudaError_t DispatchFlatChroma(const FastEncodeParams& fp, int xs, int ys, int smCount, cudaStream_t stream)
+{
+    if (xs == 1 && ys == 1) return LaunchFlatKernel<CURVE, 1, 1>(fp, smCount, stream);
+    if (xs == 1) return LaunchFlatKernel<CURVE, 1, 0>(fp, smCount, stream);
+    return LaunchFlatKernel<CURVE, 0, 0>(fp, smCount, stream);
+}
+
+} // namespace
+
+// True when the flat kernel can serve this table (flat variant present, bitmap built, everything fits in shared memory).
+bool FlatEncodeApplies(const FastEncodeParams& fp)
+{
+    return fp.table.flat != nullptr && fp.table.bandBits != nullptr &&
+           static_cast<size_t>(FlatFixedBytes()) + static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4) <= static_cast<size_t>(kSharedLimit);
+}
+
+cudaError_t LaunchFastEncodeFlat(const FastEncodeParams& fp, int curve, int xs, int ys, int smCount, cudaStream_t stream)
+{
+    if (curve == kCurveLinearToPQ) return DispatchFlatChroma<kCurveLinearToPQ>(fp, xs, ys, smCount, stream);
+    return DispatchFlatChroma<kCurveLinearToSMPTE428>(fp, xs, ys, smCount, stream);
+}
+
+} // namespace avifgpu

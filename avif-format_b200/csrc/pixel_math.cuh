@@ -286,6 +286,29 @@ AVIF_HD uint32_t TruncateToCode(float v, int maxCode)
 
 AVIF_HD uint32_t QuantiseLuma(float y, int maxCode) { return TruncateToCode(y + 0.5f, maxCode); }
 
+// The same quantisers without the upper clamp, for callers that have checked ForwardMatrixStaysInRange(): the
+// float -> unsigned conversion already sends negatives (and NaN) to 0, and the matrix cannot reach maxCode + 1.
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t QuantiseLumaInRange(float y) { return __float2uint_rz(y + 0.5f); }
+__device__ __forceinline__ uint32_t QuantiseChromaInRange(float c, float chromaOffset) { return __float2uint_rz((c + chromaOffset) + 0.5f); }
+#endif
+
+// True when, for R'G'B' codes in [0, maxCode], Y + 0.5 and C + chromaOffset + 0.5 stay below maxCode + 1 with a
+// margin (0.25) far above the float rounding of the five-operation matrix and the box filter (< 0.01 at 16 bits).
+inline bool ForwardMatrixStaysInRange(const ForwardMatrix& m, float chromaOffset, int maxCode)
+{
+    if (m.identity)
+    {
+        return true; // Y = G, Cb = B, Cr = R: codes pass through
+    }
+    const double max = static_cast<double>(maxCode);
+    const double lumaTop = (static_cast<double>(m.kr) + m.kg + m.kb) * max + 0.5;
+    const double cbTop = max * (1.0 - m.kb) * m.cbScale + chromaOffset + 0.5;
+    const double crTop = max * (1.0 - m.kr) * m.crScale + chromaOffset + 0.5;
+    const double limit = max + 0.75;
+    return m.kr >= 0 && m.kg >= 0 && m.kb >= 0 && m.kb < 1 && m.kr < 1 && lumaTop < limit && cbTop < limit && crTop < limit;
+}
+
 // chromaOffset = max/2 as a float (the decoder's chroma zero), or 0 for the identity matrix.
 AVIF_HD uint32_t QuantiseChroma(float c, float chromaOffset, int maxCode) { return TruncateToCode((c + chromaOffset) + 0.5f, maxCode); }
 

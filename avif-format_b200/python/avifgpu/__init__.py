@@ -13,7 +13,7 @@ from . import abi
 from .abi import *  # noqa: F401,F403  (enums and structs)
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-LIBRARY_PATH = os.path.join(_PKG_ROOT, "lib", "libavifgpu.so")
+LIBRARY_PATH = os.environ.get("AVIFGPU_LIBRARY") or os.path.join(_PKG_ROOT, "lib", "libavifgpu.so")
 
 _lib = None
 
