@@ -42,6 +42,25 @@ __device__ __constant__ const double kPowfLog2TableConst[32] = { AVIF_LIBM_POWF_
 __device__ __constant__ const double kLogfTableConst[32] = { AVIF_LIBM_LOGF_TABLE };
 #endif
 
+#if defined(__CUDACC__)
+// The polynomial coefficients, as NON-const __constant__ data: an FP64 instruction takes a constant-bank operand
+// directly, whereas a binary64 literal costs two register moves at every use (measured: ~16 % of the instructions
+// of the float decode kernel).  Not const on purpose -- a const initialiser would be folded back into literals.
+static __device__ __constant__ double kLibmExp2fPolyConst[3] = AVIF_LIBM_EXP2F_POLY;
+static __device__ __constant__ double kLibmExp2fPolyScaledConst[3] = AVIF_LIBM_EXP2F_POLY_SCALED;
+static __device__ __constant__ double kLibmExp2fInvLn2ScaledConst[1] = { AVIF_LIBM_EXP2F_INVLN2_SCALED };
+static __device__ __constant__ double kLibmPowfLog2PolyConst[5] = AVIF_LIBM_POWF_LOG2_POLY;
+static __device__ __constant__ double kLibmLogfPolyConst[3] = AVIF_LIBM_LOGF_POLY;
+static __device__ __constant__ double kLibmLogfLn2Const[1] = { AVIF_LIBM_LOGF_LN2 };
+#endif
+#if defined(__CUDA_ARCH__)
+#define AVIF_LIBM_COEFFICIENTS(name, count, deviceArray, literal) const double* const name = deviceArray
+#define AVIF_LIBM_SCALAR(deviceArray, literal) (deviceArray[0])
+#else
+#define AVIF_LIBM_COEFFICIENTS(name, count, deviceArray, literal) const double name[count] = literal
+#define AVIF_LIBM_SCALAR(deviceArray, literal) (literal)
+#endif
+
 static const uint64_t kExp2fTableHost[32] = { AVIF_LIBM_EXP2F_TABLE };
 static const double kPowfLog2TableHost[32] = { AVIF_LIBM_POWF_LOG2_TABLE };
 static const double kLogfTableHost[32] = { AVIF_LIBM_LOGF_TABLE };
@@ -168,7 +187,7 @@ AVIF_HD double SmallIntToDouble(int32_t k)
 // takes (no negative bases), so it is omitted.
 AVIF_HD float Exp2Inline(double xd, const LibmTables& t)
 {
-    const double C[3] = AVIF_LIBM_EXP2F_POLY;
+    AVIF_LIBM_COEFFICIENTS(C, 3, kLibmExp2fPolyConst, AVIF_LIBM_EXP2F_POLY);
     // x = k/N + r with r in [-1/(2N), 1/(2N)], N = 32
     double kd = xd + AVIF_LIBM_EXP2F_SHIFT_SCALED;
     const uint64_t ki = AsUint64(kd);
@@ -189,7 +208,7 @@ AVIF_HD float Exp2Inline(double xd, const LibmTables& t)
 // log2 of the positive normal float whose bits are ix (glibc e_powf.c log2_inline), in binary64.
 AVIF_HD double Log2Inline(uint32_t ix, const LibmTables& t)
 {
-    const double A[5] = AVIF_LIBM_POWF_LOG2_POLY;
+    AVIF_LIBM_COEFFICIENTS(A, 5, kLibmPowfLog2PolyConst, AVIF_LIBM_POWF_LOG2_POLY);
     // x = 2^k z; z in [OFF, 2*OFF) with OFF = 0x3f330000; 16 sub-intervals
     const uint32_t tmp = ix - 0x3f330000u;
     const int i = static_cast<int>((tmp >> (23 - 4)) % 16);
@@ -328,7 +347,7 @@ AVIF_HD float Powf(float x, float y, const LibmTables& t)
 // expf(x) as glibc computes it (sysdeps/ieee754/flt-32/e_expf.c).
 AVIF_HD float Expf(float x, const LibmTables& t)
 {
-    const double C[3] = AVIF_LIBM_EXP2F_POLY_SCALED;
+    AVIF_LIBM_COEFFICIENTS(C, 3, kLibmExp2fPolyScaledConst, AVIF_LIBM_EXP2F_POLY_SCALED);
     const uint32_t abstop = (AsUint(x) >> 20) & 0x7ff;
     if (abstop >= (0x42b00000u >> 20)) // |x| >= 88 or x is nan
     {
@@ -351,7 +370,7 @@ AVIF_HD float Expf(float x, const LibmTables& t)
     }
     const double xd = static_cast<double>(x);
     // x*N/Ln2 = k + r with r in [-1/2, 1/2] and int k.
-    const double z = AVIF_LIBM_EXP2F_INVLN2_SCALED * xd;
+    const double z = AVIF_LIBM_SCALAR(kLibmExp2fInvLn2ScaledConst, AVIF_LIBM_EXP2F_INVLN2_SCALED) * xd;
     double kd = z + AVIF_LIBM_EXP2F_SHIFT;
     const uint64_t ki = AsUint64(kd);
     kd -= AVIF_LIBM_EXP2F_SHIFT;
@@ -371,9 +390,9 @@ AVIF_HD float Expf(float x, const LibmTables& t)
 // The body of Expf for arguments known to be finite with |x| < 88 (no overflow / underflow / NaN screening).
 AVIF_HD float ExpfNoScreen(float x, const LibmTables& t)
 {
-    const double C[3] = AVIF_LIBM_EXP2F_POLY_SCALED;
+    AVIF_LIBM_COEFFICIENTS(C, 3, kLibmExp2fPolyScaledConst, AVIF_LIBM_EXP2F_POLY_SCALED);
     const double xd = static_cast<double>(x);
-    const double z = AVIF_LIBM_EXP2F_INVLN2_SCALED * xd;
+    const double z = AVIF_LIBM_SCALAR(kLibmExp2fInvLn2ScaledConst, AVIF_LIBM_EXP2F_INVLN2_SCALED) * xd;
     double kd = z + AVIF_LIBM_EXP2F_SHIFT;
     const uint64_t ki = AsUint64(kd);
     kd -= AVIF_LIBM_EXP2F_SHIFT;
@@ -392,7 +411,7 @@ AVIF_HD float ExpfNoScreen(float x, const LibmTables& t)
 // logf(x) as glibc computes it (sysdeps/ieee754/flt-32/e_logf.c).
 AVIF_HD float Logf(float x, const LibmTables& t)
 {
-    const double A[3] = AVIF_LIBM_LOGF_POLY;
+    AVIF_LIBM_COEFFICIENTS(A, 3, kLibmLogfPolyConst, AVIF_LIBM_LOGF_POLY);
     uint32_t ix = AsUint(x);
     if (ix == 0x3f800000u)
     {
@@ -427,7 +446,7 @@ AVIF_HD float Logf(float x, const LibmTables& t)
 
     // log(x) = log1p(z/c-1) + log(c) + k*Ln2
     const double r = fma(z, invc, -1.0);
-    const double y0 = fma(SmallIntToDouble(k), AVIF_LIBM_LOGF_LN2, logc);
+    const double y0 = fma(SmallIntToDouble(k), AVIF_LIBM_SCALAR(kLibmLogfLn2Const, AVIF_LIBM_LOGF_LN2), logc);
 
     const double r2 = r * r;
     double y = fma(A[1], r, A[2]);

@@ -139,9 +139,10 @@ __device__ __forceinline__ float DivideByConstant(float x, float d, float recipr
 
 // HLGToLinear (ColorTransfer.cpp:166-190) for value in [0, 1] (the decoders clamp before calling it), with the two
 // constant divisions -- (value - c) / a over the 2^23 possible numerators and (e + b) / 12 over [1, 16) --
-// replaced by DivideByConstant when `verifiedDivisions` is set.  The exp argument is within (-0.34, 2.47), so the
+// replaced by DivideByConstant when `verifiedDivisions` (a compile-time choice) is set.  The exp argument is within (-0.34, 2.47), so the
 // overflow / underflow screening of expf cannot trigger and is skipped.
-__device__ __forceinline__ float HLGToLinearUnit(float value, bool verifiedDivisions, const LibmTables& t)
+template <bool verifiedDivisions>
+__device__ __forceinline__ float HLGToLinearUnit(float value, const LibmTables& t)
 {
     constexpr float a = 0.17883277f;
     constexpr float b = 0.28466892f;
