@@ -261,7 +261,10 @@ AVIF_HD bool ZeroInfNan(uint32_t ix) { return 2 * ix - 1 >= 2u * 0x7f800000u - 1
 AVIF_HD bool IsSignaling(uint32_t ix) { return 2 * (ix ^ 0x00400000u) > 2u * 0x7fc00000u; }
 
 // powf(x, y) as glibc computes it (sysdeps/ieee754/flt-32/e_powf.c), errno / exception flags aside.
-AVIF_HD float Powf(float x, float y, const LibmTables& t)
+// kBaseNotNegative = true is a promise by the caller that x's sign bit is clear (x is +0, positive, +inf or a
+// positive-signed NaN); the negative-base handling and the sign of the result then drop out at compile time.
+template <bool kBaseNotNegative>
+AVIF_HD float PowfImpl(float x, float y, const LibmTables& t)
 {
     uint32_t signBias = 0;
     uint32_t ix = AsUint(x);
@@ -296,14 +299,14 @@ AVIF_HD float Powf(float x, float y, const LibmTables& t)
         if (ZeroInfNan(ix))
         {
             float x2 = x * x;
-            if ((ix & 0x80000000u) && CheckInt(iy) == 1)
+            if (!kBaseNotNegative && (ix & 0x80000000u) && CheckInt(iy) == 1)
             {
                 x2 = -x2;
             }
             return (iy & 0x80000000u) ? 1 / x2 : x2;
         }
         // x and y are non-zero finite.
-        if (ix & 0x80000000u)
+        if (!kBaseNotNegative && (ix & 0x80000000u))
         {
             // Finite x < 0.
             const int yint = CheckInt(iy);
@@ -343,6 +346,11 @@ AVIF_HD float Powf(float x, float y, const LibmTables& t)
     const float result = Exp2Inline(ylogx, t);
     return signBias ? -result : result;
 }
+
+AVIF_HD float Powf(float x, float y, const LibmTables& t) { return PowfImpl<false>(x, y, t); }
+
+// Powf for a base whose sign bit is known to be clear.
+AVIF_HD float PowfOfNonNegative(float x, float y, const LibmTables& t) { return PowfImpl<true>(x, y, t); }
 
 // expf(x) as glibc computes it (sysdeps/ieee754/flt-32/e_expf.c).
 AVIF_HD float Expf(float x, const LibmTables& t)

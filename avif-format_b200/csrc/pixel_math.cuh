@@ -160,11 +160,14 @@ __device__ __forceinline__ float HLGToLinearUnit(float value, const LibmTables& 
 #endif
 
 // ColorTransfer.cpp:192-205.  gammaMinusOne = displayGamma - 1.0f (float subtraction, hoisted).
+// kLumaNotNegative: the caller knows r, g, b >= +0 (the decoders clamp to [0, 1] before the inverse OETF) and the
+// luma coefficients are positive, so the luma's sign bit is clear and powf needs no negative-base handling.
+template <bool kLumaNotNegative = false>
 AVIF_HD void ApplyHLGOOTF(float& r, float& g, float& b, float lumaR, float lumaG, float lumaB, float gammaMinusOne,
                           float nominalPeakBrightness, const LibmTables& t)
 {
     const float luma = (r * lumaR) + (g * lumaG) + (b * lumaB);
-    const float factor = nominalPeakBrightness * avifmath::Powf(luma, gammaMinusOne, t);
+    const float factor = nominalPeakBrightness * avifmath::PowfImpl<kLumaNotNegative>(luma, gammaMinusOne, t);
     r *= factor;
     g *= factor;
     b *= factor;

@@ -86,9 +86,14 @@ int main(int argc, char** argv)
         const Tally neg = Sweep(0x80000000u, 0xff800001u, stride * 16u + 1u, threads,
                                 [y](float x, const LibmTables& t) { return Powf(x, y, t); },
                                 [y](float x) { return powf(x, y); });
-        std::printf("powf y=%-14a compared=%llu mismatched=%llu first=%08x | negative-x compared=%llu mismatched=%llu first=%08x\n",
-                    y, pos.compared, pos.mismatched, pos.first, neg.compared, neg.mismatched, neg.first);
-        failed |= pos.mismatched != 0 || neg.mismatched != 0;
+        // the variant for bases whose sign bit is known to be clear (HLG OOTF luma) over its whole domain
+        const Tally unsignedBase = Sweep(0x00000000u, 0x7fc00001u, stride, threads,
+                                         [y](float x, const LibmTables& t) { return PowfOfNonNegative(x, y, t); },
+                                         [y](float x) { return powf(x, y); });
+        std::printf("powf y=%-14a compared=%llu mismatched=%llu first=%08x | negative-x compared=%llu mismatched=%llu first=%08x | "
+                    "non-negative variant mismatched=%llu\n",
+                    y, pos.compared, pos.mismatched, pos.first, neg.compared, neg.mismatched, neg.first, unsignedBase.mismatched);
+        failed |= pos.mismatched != 0 || neg.mismatched != 0 || unsignedBase.mismatched != 0;
     }
     {
         const Tally a = Sweep(0x00000000u, 0x7fc00001u, stride, threads,
