@@ -55,3 +55,87 @@ def gather_encode_planes(dist, torch, desc, blocks, local_planes, group=None):
         assert cursor == rows_total, (cursor, rows_total)
         out.append(full)
     return out
+
+
+class PeerPlanes:
+    """Whole-image planes that live on the OWNER rank's GPU and are mapped into every other rank's address space
+    through CUDA IPC (one process per GPU).  A rank hands `planes()` to avifgpu_encode_rows_device together with
+    its own (y0, nrows): the conversion kernel's stores then land in the owner's HBM over NVLink / NVSwitch, tile
+    by tile, while the kernel is still converting -- the "gather" is fused into the conversion and costs no extra
+    pass (the planes are 3 of the 15 bytes per pixel the kernel moves).  After the ranks' streams have drained and a
+    barrier, the owner holds the assembled image.
+
+    Needs a GPU per rank and peer access between them (any NVSwitch box); there is no CPU equivalent, so the gloo
+    tests cover the all_gather path (gather_encode_planes) and this class is exercised by `bench.py --mode tile`."""
+
+    def __init__(self, dist, desc, rank, owner=0, group=None):
+        from cuda.bindings import runtime as rt
+        self._rt = rt
+        self.rank, self.owner = rank, owner
+        self.shapes = abi.encode_plane_shapes(desc)
+        self.itemsize = 2 if desc.image_bit_depth > 8 else 1
+        self.pointers, self.strides, self._opened = [0] * 4, [0] * 4, []
+        meta = [None]
+        if rank == owner:
+            entries = []
+            for shape in self.shapes:
+                if shape is None:
+                    entries.append(None)
+                    continue
+                pitch = (shape[1] * self.itemsize + 255) // 256 * 256
+                ptr = self._ok(rt.cudaMalloc(pitch * max(shape[0], 1)))
+                handle = self._ok(rt.cudaIpcGetMemHandle(ptr))
+                entries.append((bytes(handle.reserved), pitch, int(ptr)))
+            meta = [entries]
+        dist.broadcast_object_list(meta, src=owner, group=group)
+        for k, entry in enumerate(meta[0]):
+            if entry is None:
+                continue
+            reserved, pitch, owner_ptr = entry
+            if rank == owner:
+                ptr = owner_ptr
+            else:
+                handle = rt.cudaIpcMemHandle_t()
+                handle.reserved = reserved
+                ptr = int(self._ok(rt.cudaIpcOpenMemHandle(handle, rt.cudaIpcMemLazyEnablePeerAccess)))
+                self._opened.append(ptr)
+            self.pointers[k], self.strides[k] = ptr, pitch
+
+    def _ok(self, result):
+        err = result[0]
+        if int(err) != 0:
+            raise RuntimeError(f"CUDA runtime error {err} in PeerPlanes")
+        return result[1] if len(result) > 1 else None
+
+    def planes(self):
+        """abi.Planes over the whole image (origin pointers), valid on this rank's device."""
+        planes = abi.Planes()
+        for k in range(4):
+            planes.data[k] = self.pointers[k] or None
+            planes.stride[k] = self.strides[k]
+        return planes
+
+    def owner_tensors(self, torch, device):
+        """The owner's view of the assembled planes as torch tensors (copies)."""
+        assert self.rank == self.owner
+        out = []
+        for k, shape in enumerate(self.shapes):
+            if shape is None:
+                out.append(None)
+                continue
+            dtype = torch.int16 if self.itemsize == 2 else torch.uint8
+            pitched = torch.empty((shape[0], self.strides[k] // self.itemsize), dtype=dtype, device=device)
+            self._ok(self._rt.cudaMemcpy(pitched.data_ptr(), self.pointers[k], self.strides[k] * shape[0],
+                                         self._rt.cudaMemcpyKind.cudaMemcpyDeviceToDevice))
+            out.append(pitched[:, :shape[1]].contiguous())
+        return out
+
+    def close(self):
+        for ptr in self._opened:
+            self._rt.cudaIpcCloseMemHandle(ptr)
+        self._opened = []
+        if self.rank == self.owner:
+            for ptr in self.pointers:
+                if ptr:
+                    self._rt.cudaFree(ptr)
+        self.pointers = [0] * 4
