@@ -181,6 +181,18 @@ AVIF_HD double SmallIntToDouble(int32_t k)
 #endif
 }
 
+// AsDouble(tableBits + (ki << 47)): the table entry with k / 32 added to its exponent (glibc: `t += ki << (52 - 5)`).
+// ki << 47 has no bits below bit 47, so on the device the addition is a single 32-bit add on the high word.
+AVIF_HD double ScaleTableEntry(uint64_t tableBits, uint64_t ki)
+{
+#if defined(__CUDA_ARCH__)
+    const uint32_t high = static_cast<uint32_t>(tableBits >> 32) + (static_cast<uint32_t>(ki) << 15);
+    return __hiloint2double(static_cast<int>(high), static_cast<int>(static_cast<uint32_t>(tableBits)));
+#else
+    return AsDouble(tableBits + (ki << (52 - 5)));
+#endif
+}
+
 // ---- exp2 core shared by powf (glibc e_powf.c exp2_inline) ------------------------------------------------
 
 // 2^xd rounded once to binary32, for |xd| < 126 (callers check).  sign_bias is 0 on every path this library
@@ -195,8 +207,7 @@ AVIF_HD float Exp2Inline(double xd, const LibmTables& t)
     const double r = xd - kd;
     // exp2(x) = 2^(k/N) * 2^r ~= s * (C0*r^3 + C1*r^2 + C2*r + 1)
     uint64_t bits = t.exp2f[ki % 32];
-    bits += ki << (52 - 5);
-    const double s = AsDouble(bits);
+    const double s = ScaleTableEntry(bits, ki);
     const double z = fma(C[0], r, C[1]);
     const double r2 = r * r;
     double y = fma(C[2], r, 1.0);
@@ -385,8 +396,7 @@ AVIF_HD float Expf(float x, const LibmTables& t)
     const double r = z - kd;
     // exp(x) = 2^(k/N) * 2^(r/N) ~= s * (C0*r^3 + C1*r^2 + C2*r + 1)
     uint64_t bits = t.exp2f[ki % 32];
-    bits += ki << (52 - 5);
-    const double s = AsDouble(bits);
+    const double s = ScaleTableEntry(bits, ki);
     const double zz = fma(C[0], r, C[1]);
     const double r2 = r * r;
     double y = fma(C[2], r, 1.0);
@@ -406,8 +416,7 @@ AVIF_HD float ExpfNoScreen(float x, const LibmTables& t)
     kd -= AVIF_LIBM_EXP2F_SHIFT;
     const double r = z - kd;
     uint64_t bits = t.exp2f[ki % 32];
-    bits += ki << (52 - 5);
-    const double s = AsDouble(bits);
+    const double s = ScaleTableEntry(bits, ki);
     const double zz = fma(C[0], r, C[1]);
     const double r2 = r * r;
     double y = fma(C[2], r, 1.0);

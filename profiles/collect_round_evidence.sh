@@ -1,3 +1,6 @@
+#!/bin/bash
+# The commands behind the *_final* files of this directory (run from the repo root on a B200 box; outputs land in
+# gpurun_out/ and are then summarised / copied here, see README.md).
 set -x
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 for w in c2 c3 c4 c5; do python bench.py --workload $w --steps 50 --warmup 5 2>&1 | tail -1 > gpurun_out/bench_${w}_final.json; cut -c1-120 gpurun_out/bench_${w}_final.json; done
