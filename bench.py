@@ -97,6 +97,14 @@ class Workload:
     def make_device_input(self, torch, device, seed):
         g = torch.Generator(device=device)
         g.manual_seed(seed)
+        if self.key == "c2" and getattr(self, "smooth", False):
+            # A smooth frame (supplementary, --data smooth): horizontal ramps per channel with 0.1 % noise, so that
+            # neighbouring pixels fall into the same step-table buckets the way natural images do.
+            x = torch.linspace(0.0, 1.0, self.w, device=device).repeat_interleave(3)
+            phase = torch.tensor([0.05, 0.35, 0.65], device=device).repeat(self.w)
+            base = 0.02 + 0.9 * torch.remainder(x + phase, 1.0)
+            noise = 1.0 + 1.0e-3 * (torch.rand((self.h, self.w * 3), generator=g, device=device) - 0.5)
+            return [(base[None, :] * noise).contiguous()]
         if self.key == "c2":
             n = (self.h, self.w * 3)
             kind = torch.rand(n, generator=g, device=device)
@@ -451,7 +459,7 @@ def run_b200(args, workload, rank, world, local_rank):
         line = {
             "metric": "Gpixels/s", "value": value, "unit": "Gpx/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": wl.dtype, "data": "synthetic",
+            "dtype": wl.dtype, "data": "synthetic" if not getattr(wl, "smooth", False) else "synthetic (smooth ramps + 0.1 % noise; supplementary)",
             "config": {"workload": wl.name, "pixels_per_step_per_gpu": wl.pixels, "parallelism": f"{world} independent frame(s), one per GPU",
                        "l2": f"{copies} rotating input/output sets of {wl.algorithmic_bytes / 1e6:.0f} MB each (> 126 MB L2)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -580,11 +588,14 @@ def main():
     ap.add_argument("--workload", choices=("c2", "c3", "c4", "c5"), default="c2")
     ap.add_argument("--mode", choices=("frames", "tile"), default="frames")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--data", choices=("random", "smooth"), default="random",
+                    help="c2 only: 'random' (default, SURVEY 8(d): the worst case for the table look-ups) or 'smooth' (supplementary)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = Workload(args.workload)
+    workload.smooth = args.data == "smooth"
     if args.impl == "reference":
         run_reference_impl(args, workload, rank, world)
         return
