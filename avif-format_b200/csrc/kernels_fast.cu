@@ -315,7 +315,7 @@ int LaunchEncodeGeneric(const EncodeParams& params, int hostDepth, void* stream)
 int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
-    if (hostDepth != 32 || !p.planar || p.channels != 3 || p.hasAlpha || p.imageDepth <= 8 || p.matrix.identity)
+    if (hostDepth != 32 || !p.planar || p.channels != 3 || p.hasAlpha || p.imageDepth <= 8)
     {
         return 0;
     }

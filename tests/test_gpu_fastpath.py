@@ -179,3 +179,46 @@ def test_ycc_to_rgb32_fast_kernel(gpu, port, w, h, chroma):
             gpu.decode(desc, planes, y0=0, nrows=1, out=out[0:1])
             gpu.decode(desc, planes, y0=1, nrows=h - 1, out=out[1:])
             assert cases.same_bits(expected, out)
+
+
+# ---- every float through the production kernel ---------------------------------------------------------------------------
+
+def test_every_float_through_the_production_encode_kernel(gpu):
+    """The step tables are verified against the exact curve by the builder's own sweep; this runs the PRODUCTION kernel
+    (copy-engine staging, table look-up, band bitmap, +inf / NaN route) over an image that contains every bit pattern
+    from +0 through the positive NaNs and on into the first negative values -- 2^31 + samples -- with the identity
+    (GBR) matrix in 4:4:4, so the three planes ARE the per-sample codes.  The expected planes come from the generic
+    exact kernel (glibc-identical powf per sample; reached by giving it a 2-byte-aligned plane origin), which
+    test_gpu_parity.py pins to the CPU checker."""
+    import torch
+    import avifgpu
+    dev = torch.device("cuda", gpu.device)
+    if torch.cuda.get_device_properties(dev).total_memory < 40 * 2**30:
+        pytest.skip("needs ~20 GB of device memory")
+    w = 4096
+    samples_per_row = w * 3
+    h = ((1 << 31) // samples_per_row + 2) & ~1
+    desc = abi.EncodeDesc(w, h, 32, 3, abi.ALPHA_NONE, 12, abi.TRANSFER_PQ, 80, abi.LAYOUT_PLANAR_YCBCR, abi.CHROMA_444,
+                          abi.DOWN_FILTER_BOX, abi.GRAY16_LUT, abi.Nclx(1, abi.PRIMARIES_BT2020, abi.TRANSFER_CHAR_PQ, 0, 1))
+    rows = torch.empty((h, samples_per_row), dtype=torch.float32, device=dev)
+    flat_bits = rows.view(torch.int32).view(-1)
+    chunk = 1 << 27
+    for start in range(0, flat_bits.numel(), chunk):
+        n = min(chunk, flat_bits.numel() - start)
+        flat_bits[start:start + n] = torch.arange(start, start + n, dtype=torch.int64, device=dev).to(torch.int32)  # wraps past 2^31
+    shapes = abi.encode_plane_shapes(desc)
+    fast = [None if s is None else torch.full(s, -1, dtype=torch.int16, device=dev) for s in shapes]
+    gpu.encode_device(desc, rows.data_ptr(), rows.stride(0) * 4, avifgpu.planes_from_tensors(fast))
+    backing = [None if s is None else torch.full((s[0], s[1] + 1), -1, dtype=torch.int16, device=dev) for s in shapes]
+    exact = [None if t is None else t[:, 1:] for t in backing]  # 2-byte aligned origins: the launcher takes the generic kernel
+    before = gpu.launch_count()
+    gpu.encode_device(desc, rows.data_ptr(), rows.stride(0) * 4, avifgpu.planes_from_tensors(exact))
+    torch.cuda.synchronize(dev)
+    assert gpu.launch_count() - before == 1
+    for k in range(3):
+        differing = int((fast[k] != exact[k]).sum().item())
+        assert differing == 0, f"plane {k}: {differing} of {fast[k].numel()} codes differ"
+    # and the planes are what the identity matrix promises: Y = G, Cb = B, Cr = R of monotone inputs
+    codes = exact[2].reshape(-1)[: (0x7f800000 // 3)].to(torch.int32) & 0xffff  # Cr = R samples, bits 0, 3, 6, ... below +inf
+    assert int(codes.max().item()) == 4095 and int(codes.min().item()) == 0
+    assert bool((codes[1:] >= codes[:-1] - 1).all().item())  # non-decreasing up to the one-code flips inside fuzzy bands
