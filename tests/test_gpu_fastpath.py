@@ -222,3 +222,35 @@ def test_every_float_through_the_production_encode_kernel(gpu):
     codes = exact[2].reshape(-1)[: (0x7f800000 // 3)].to(torch.int32) & 0xffff  # Cr = R samples, bits 0, 3, 6, ... below +inf
     assert int(codes.max().item()) == 4095 and int(codes.min().item()) == 0
     assert bool((codes[1:] >= codes[:-1] - 1).all().item())  # non-decreasing up to the one-code flips inside fuzzy bands
+
+
+def test_every_10bit_triple_through_the_production_decode_kernel(gpu):
+    """Config 3's whole input domain: all 2^30 (Y, Cb, Cr) triples of 10-bit codes as one 32768 x 32768 4:4:4 image
+    (what 4:2:0 feeds the per-pixel arithmetic is a subset of these), HLG + OOTF, through the tuned decode kernel and
+    through the generic exact kernel (reached with a row pointer that is only 4-byte aligned); the float outputs must
+    be bit-identical.  test_gpu_parity.py / test_gpu_fullsize.py pin the generic kernel to the reference's CPU loop."""
+    import torch
+    import avifgpu
+    dev = torch.device("cuda", gpu.device)
+    if torch.cuda.get_device_properties(dev).total_memory < 80 * 2**30:
+        pytest.skip("needs ~45 GB of device memory")
+    w = h = 1 << 15
+    desc = abi.DecodeDesc(w, h, abi.COLORSPACE_YCBCR, abi.CHROMA_444, 10, abi.ALPHA_NONE, 32, cases.NCLX_2020_HLG(1), 1, 1.2, 1000, 80)
+    index = torch.arange(w * h, dtype=torch.int32, device=dev).view(h, w)
+    planes = [(index & 1023).to(torch.int16), ((index >> 10) & 1023).to(torch.int16), (index >> 20).to(torch.int16)]
+    del index
+    struct = avifgpu.planes_from_tensors(planes + [None])
+    fast = torch.empty((h, w * 3), dtype=torch.float32, device=dev)
+    before = gpu.launch_count()
+    gpu.decode_device(desc, struct, fast.data_ptr(), fast.stride(0) * 4)
+    fast_launches = gpu.launch_count() - before
+    backing = torch.empty((h, w * 3 + 4), dtype=torch.float32, device=dev)
+    exact = backing[:, 1:w * 3 + 1]  # 4-byte aligned rows: the launcher takes the generic kernel
+    gpu.decode_device(desc, struct, exact.data_ptr(), exact.stride(0) * 4)
+    torch.cuda.synchronize(dev)
+    assert fast_launches >= 1
+    differing = 0
+    for y in range(0, h, 4096):  # compare in slabs to bound the temporaries
+        differing += int((fast[y:y + 4096].view(torch.int32) != exact[y:y + 4096].view(torch.int32)).sum().item())
+    assert differing == 0, f"{differing} of {fast.numel()} output samples differ"
+    assert bool(torch.isfinite(fast[:4096]).all().item())
