@@ -26,6 +26,7 @@ int LaunchEncodeFastInteger(const EncodeParams& params, int hostDepth, void* str
 cudaError_t BuildGray16Lut(uint16_t* deviceLut, int smpte428, uint32_t maxCode, void* stream);
 long long VerifyHlgDivisions(void* stream);
 int LaunchDecodeFast(const DecodeParams& params, void* stream);                  // 0 = not applicable
+int LaunchDecodeFastInteger(const DecodeParams& params, void* stream);           // 0 = not applicable
 
 int LaunchEncode(const EncodeParams& params, int hostDepth, void* stream)
 {
@@ -44,7 +45,12 @@ int LaunchEncode(const EncodeParams& params, int hostDepth, void* stream)
 
 int LaunchDecode(const DecodeParams& params, void* stream)
 {
-    const int fast = LaunchDecodeFast(params, stream);
+    int fast = LaunchDecodeFast(params, stream);
+    if (fast != 0)
+    {
+        return fast;
+    }
+    fast = LaunchDecodeFastInteger(params, stream);
     if (fast != 0)
     {
         return fast;

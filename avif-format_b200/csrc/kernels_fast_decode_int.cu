@@ -1,0 +1,410 @@
+// kernels_fast_decode_int.cu -- tuned decode kernels for the integer hosts: planar YCbCr (+ alpha) -> interleaved
+// RGB(A) 8-bit (YuvDecode.cpp:281-399 driven by ReadHeifImage.cpp:83-184) and 16-bit (YuvDecode.cpp:401-519 driven by
+// ReadHeifImage.cpp:186-288).  No transfer curve on these paths: table look-up, matrix, clamp, round -- HBM-bound work
+// (4.5 B/px for 8-bit 4:2:0) if the instruction count per pixel stays near 25.
+//
+//   * a warp converts units of (2 rows for 4:2:0, else 1) x 256 pixels; a lane owns 8 adjacent pixels per row: one
+//     64/128-bit load of Y per row, one 32/64-bit (sub-sampled) load of Cb and of Cr, 3-4 vector stores per row;
+//   * the unorm -> float tables (YuvLookupTables.cpp:115-192) sit in shared memory; for 16-bit hosts the alpha output
+//     (u16)(0.5f + a * 32768f) is tabulated whole;
+//   * the chroma-dependent terms of YuvDecode.cpp:306-312 are evaluated once per chroma site and reused for every luma
+//     sample the site covers (both rows of a 4:2:0 site); same float expressions, same association;
+//   * premultiplied alpha, odd starting rows of a 4:2:0 block, depths above 12 bits and unaligned buffers stay with the
+//     generic kernel.
+#include "kernel_params.h"
+#include "pixel_math.cuh"
+#include "../../include/avifgpu.h"
+
+#include <cuda_runtime.h>
+
+namespace avifgpu
+{
+
+using namespace avifpix;
+
+namespace
+{
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kBlocksPerSm = 3;
+constexpr int kUnitPixels = 256; // per row: 32 lanes x 8 pixels
+
+struct IntDecodeParams
+{
+    const uint8_t* plane[4];
+    int64_t planeStride[4];
+    uint8_t* rows;
+    int64_t rowStride;
+    int32_t width;    // multiple of 8
+    int32_t rowCount; // even when the chroma is vertically sub-sampled
+    int32_t bitDepth;
+    uint32_t maxCode;
+    RangeParams range;
+    InverseMatrix matrix;
+};
+
+// 8 consecutive samples of a plane as 32-bit codes.
+template <typename SampleT>
+__device__ __forceinline__ void LoadEight(const uint8_t* address, uint32_t (&codes)[8])
+{
+    if (sizeof(SampleT) == 1)
+    {
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(address));
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            codes[i] = (w.x >> (8 * i)) & 0xffu;
+            codes[4 + i] = (w.y >> (8 * i)) & 0xffu;
+        }
+    }
+    else
+    {
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(address));
+        const uint32_t words[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            codes[2 * i] = words[i] & 0xffffu;
+            codes[2 * i + 1] = words[i] >> 16;
+        }
+    }
+}
+
+// 4 consecutive samples (horizontally sub-sampled chroma under 8 luma samples).
+template <typename SampleT>
+__device__ __forceinline__ void LoadFour(const uint8_t* address, uint32_t (&codes)[8])
+{
+    if (sizeof(SampleT) == 1)
+    {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(address));
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            codes[i] = (w >> (8 * i)) & 0xffu;
+        }
+    }
+    else
+    {
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(address));
+        codes[0] = w.x & 0xffffu;
+        codes[1] = w.x >> 16;
+        codes[2] = w.y & 0xffffu;
+        codes[3] = w.y >> 16;
+    }
+}
+
+template <typename SampleT, int XS, int YS, int ALPHA>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSm) DecodeYccToRgbIntKernel(const IntDecodeParams p)
+{
+    constexpr bool kHost8 = sizeof(SampleT) == 1;
+    constexpr int kRows = YS ? 2 : 1;
+    constexpr int kSites = XS ? 4 : 8;          // chroma sites under a lane's 8 luma samples
+    constexpr int kChannels = ALPHA ? 4 : 3;
+    extern __shared__ __align__(16) uint8_t sharedBytes[];
+    float* tableY = reinterpret_cast<float*>(sharedBytes);
+    float* tableUV = tableY + (1u << p.bitDepth);
+    uint16_t* tableAlpha = reinterpret_cast<uint16_t*>(tableUV + (1u << p.bitDepth)); // 16-bit hosts with alpha only
+
+    for (uint32_t i = threadIdx.x; i <= p.maxCode; i += blockDim.x)
+    {
+        tableY[i] = UnormToFloatY(i, p.range);   // YuvLookupTables.cpp:157-171
+        tableUV[i] = UnormToFloatUV(i, p.range); // YuvLookupTables.cpp:173-184
+        if (ALPHA && !kHost8)
+        {
+            // YuvLookupTables.cpp:186-190 then YuvDecode.cpp:515
+            tableAlpha[i] = static_cast<uint16_t>(0.5f + (UnormToFloatPlain(i, p.range.maxChannelFloat) * 32768.0f));
+        }
+    }
+    __syncthreads();
+
+    // YuvDecode.cpp:306-312, the pixel-independent factors (same float expressions, evaluated once)
+    const float kr = p.matrix.kr, kg = p.matrix.kg, kb = p.matrix.kb;
+    const float rGain = (2 * (1 - kr));
+    const float bGain = (2 * (1 - kb));
+    const float gCr = kr * (1 - kr);
+    const float gCb = kb * (1 - kb);
+    const float outScale = kHost8 ? 255.0f : 32768.0f;
+
+    const int lane = threadIdx.x & 31;
+    const int warpInBlock = threadIdx.x >> 5;
+    const int unitsX = (p.width + kUnitPixels - 1) / kUnitPixels;
+    const int unitRows = (p.rowCount + kRows - 1) / kRows;
+    const long long unitCount = static_cast<long long>(unitsX) * unitRows;
+    const int warpCount = static_cast<int>(gridDim.x) * kWarps;
+
+#pragma unroll 1
+    for (long long unit = static_cast<long long>(blockIdx.x) * kWarps + warpInBlock; unit < unitCount; unit += warpCount)
+    {
+        const int unitRow = static_cast<int>(unit / unitsX);
+        const int x0 = static_cast<int>(unit - static_cast<long long>(unitRow) * unitsX) * kUnitPixels + lane * 8;
+        const int y0 = unitRow * kRows;
+        if (x0 >= p.width)
+        {
+            continue;
+        }
+        const bool secondRow = kRows == 2 && (y0 + 1) < p.rowCount;
+
+        // ---- chroma sites ---------------------------------------------------------------------------------------------
+        uint32_t cbCode[8], crCode[8];
+        {
+            const int64_t chromaRow = YS ? unitRow : y0;
+            const int64_t chromaColumn = static_cast<int64_t>(XS ? (x0 >> 1) : x0) * sizeof(SampleT);
+            if (XS)
+            {
+                LoadFour<SampleT>(p.plane[1] + chromaRow * p.planeStride[1] + chromaColumn, cbCode);
+                LoadFour<SampleT>(p.plane[2] + chromaRow * p.planeStride[2] + chromaColumn, crCode);
+            }
+            else
+            {
+                LoadEight<SampleT>(p.plane[1] + chromaRow * p.planeStride[1] + chromaColumn, cbCode);
+                LoadEight<SampleT>(p.plane[2] + chromaRow * p.planeStride[2] + chromaColumn, crCode);
+            }
+        }
+        uint32_t yCode[kRows][8];
+        uint32_t aCode[kRows][8];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+        {
+            if (r == 1 && !secondRow)
+            {
+                break;
+            }
+            LoadEight<SampleT>(p.plane[0] + static_cast<int64_t>(y0 + r) * p.planeStride[0] + static_cast<int64_t>(x0) * sizeof(SampleT), yCode[r]);
+            if (ALPHA)
+            {
+                LoadEight<SampleT>(p.plane[3] + static_cast<int64_t>(y0 + r) * p.planeStride[3] + static_cast<int64_t>(x0) * sizeof(SampleT), aCode[r]);
+            }
+        }
+        float rOffset[kSites], bOffset[kSites], gOffset[kSites];
+#pragma unroll
+        for (int s = 0; s < kSites; ++s)
+        {
+            const float Cb = tableUV[kHost8 ? cbCode[s] : min(cbCode[s], p.maxCode)];
+            const float Cr = tableUV[kHost8 ? crCode[s] : min(crCode[s], p.maxCode)];
+            rOffset[s] = rGain * Cr;
+            bOffset[s] = bGain * Cb;
+            gOffset[s] = ((2 * ((gCr * Cr) + (gCb * Cb))) / kg);
+        }
+
+        // ---- pixels ---------------------------------------------------------------------------------------------------
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+        {
+            if (r == 1 && !secondRow)
+            {
+                break;
+            }
+            uint32_t out[8][kChannels];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+            {
+                const int s = XS ? (i >> 1) : i;
+                const float Y = tableY[kHost8 ? yCode[r][i] : min(yCode[r][i], p.maxCode)];
+                // std::clamp(v, 0, 1) as the add's saturation modifier: the table entries are finite and Y >= +0, so the
+                // sums are never NaN or -0.0 and the two agree for every input.
+                const float R = __saturatef(Y + rOffset[s]);
+                const float B = __saturatef(Y + bOffset[s]);
+                const float G = __saturatef(Y - gOffset[s]);
+                out[i][0] = __float2uint_rz(0.5f + (R * outScale)); // YuvDecode.cpp:314-316 / 437-439
+                out[i][1] = __float2uint_rz(0.5f + (G * outScale));
+                out[i][2] = __float2uint_rz(0.5f + (B * outScale));
+                if (ALPHA)
+                {
+                    out[i][3] = kHost8 ? aCode[r][i] : tableAlpha[min(aCode[r][i], p.maxCode)];
+                }
+            }
+            uint8_t* target = p.rows + static_cast<int64_t>(y0 + r) * p.rowStride + static_cast<int64_t>(x0) * (kChannels * sizeof(SampleT));
+            if (kHost8)
+            {
+                // 8 pixels x kChannels bytes
+                uint32_t words[2 * kChannels];
+#pragma unroll
+                for (int w = 0; w < 2 * kChannels; ++w)
+                {
+                    uint32_t word = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                    {
+                        const int byteIndex = 4 * w + b;
+                        word |= out[byteIndex / kChannels][byteIndex % kChannels] << (8 * b);
+                    }
+                    words[w] = word;
+                }
+                if (ALPHA)
+                {
+                    __stcs(reinterpret_cast<uint4*>(target), make_uint4(words[0], words[1], words[2], words[3]));
+                    __stcs(reinterpret_cast<uint4*>(target) + 1, make_uint4(words[4], words[5], words[6], words[7]));
+                }
+                else
+                {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                    {
+                        __stcs(reinterpret_cast<uint2*>(target) + q, make_uint2(words[2 * q], words[2 * q + 1]));
+                    }
+                }
+            }
+            else
+            {
+                // 8 pixels x kChannels 16-bit samples
+                uint32_t words[4 * kChannels];
+#pragma unroll
+                for (int w = 0; w < 4 * kChannels; ++w)
+                {
+                    const int first = 2 * w;
+                    words[w] = out[first / kChannels][first % kChannels] | (out[(first + 1) / kChannels][(first + 1) % kChannels] << 16);
+                }
+#pragma unroll
+                for (int q = 0; q < kChannels; ++q)
+                {
+                    __stcs(reinterpret_cast<uint4*>(target) + q, make_uint4(words[4 * q], words[4 * q + 1], words[4 * q + 2], words[4 * q + 3]));
+                }
+            }
+        }
+    }
+}
+
+template <typename SampleT, int XS, int YS, int ALPHA>
+cudaError_t LaunchOne(const IntDecodeParams& fp, int smCount, cudaStream_t stream)
+{
+    const size_t entries = static_cast<size_t>(1) << fp.bitDepth;
+    const size_t shared = 2 * sizeof(float) * entries + ((ALPHA && sizeof(SampleT) == 2) ? sizeof(uint16_t) * entries : 0);
+    static bool configured = false;
+    if (!configured)
+    {
+        const cudaError_t e = cudaFuncSetAttribute(DecodeYccToRgbIntKernel<SampleT, XS, YS, ALPHA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess)
+        {
+            return e;
+        }
+        configured = true;
+    }
+    constexpr int rowsPerUnit = YS ? 2 : 1;
+    const long long units = static_cast<long long>((fp.width + kUnitPixels - 1) / kUnitPixels) * ((fp.rowCount + rowsPerUnit - 1) / rowsPerUnit);
+    long long blocks = (units + kWarps - 1) / kWarps;
+    const long long resident = static_cast<long long>(smCount) * kBlocksPerSm;
+    if (blocks > resident)
+    {
+        blocks = resident;
+    }
+    DecodeYccToRgbIntKernel<SampleT, XS, YS, ALPHA><<<static_cast<unsigned>(blocks), kThreads, shared, stream>>>(fp);
+    return cudaGetLastError();
+}
+
+template <typename SampleT, int ALPHA>
+cudaError_t DispatchChroma(const IntDecodeParams& fp, int xs, int ys, int smCount, cudaStream_t stream)
+{
+    if (xs == 1 && ys == 1) return LaunchOne<SampleT, 1, 1, ALPHA>(fp, smCount, stream);
+    if (xs == 1) return LaunchOne<SampleT, 1, 0, ALPHA>(fp, smCount, stream);
+    return LaunchOne<SampleT, 0, 0, ALPHA>(fp, smCount, stream);
+}
+
+bool Aligned(const void* p, int64_t stride, int alignment)
+{
+    return (reinterpret_cast<uintptr_t>(p) % alignment) == 0 && (stride % alignment) == 0;
+}
+
+} // namespace
+
+int LaunchDecodeGeneric(const DecodeParams& params, void* stream);
+
+// Returns the number of kernels launched, 0 if this configuration is not covered, or a negative status.
+int LaunchDecodeFastInteger(const DecodeParams& p, void* streamHandle)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
+    if (p.colorspace != AVIFGPU_COLORSPACE_YCBCR || (p.hostDepth != 8 && p.hostDepth != 16) || p.bitDepth > 12 || p.yPhase != 0 ||
+        (p.hasAlpha && p.premultiplied))
+    {
+        return 0;
+    }
+    const int sampleBytes = p.hostDepth == 8 ? 1 : 2;
+    if ((sampleBytes == 1) != (p.bitDepth <= 8))
+    {
+        return 0; // 8-bit hosts read 8-bit planes, 16-bit hosts read 16-bit planes (ReadHeifImage.cpp:83, 186)
+    }
+    const int channels = p.hasAlpha ? 4 : 3;
+    const int lumaAlign = 8 * sampleBytes;
+    const int chromaAlign = (p.xs ? 4 : 8) * sampleBytes;
+    const int rowAlign = channels == 4 ? 16 : 8 * sampleBytes; // RGB8: 64-bit stores, everything else 128-bit
+    if (!Aligned(p.plane[0], p.planeStride[0], lumaAlign) || !Aligned(p.plane[1], p.planeStride[1], chromaAlign) ||
+        !Aligned(p.plane[2], p.planeStride[2], chromaAlign) || (p.hasAlpha && !Aligned(p.plane[3], p.planeStride[3], lumaAlign)) ||
+        !Aligned(p.rows, p.rowStride, rowAlign))
+    {
+        return 0;
+    }
+    const int width8 = p.width & ~7;
+    const int evenRows = p.ys ? (p.rowCount & ~1) : p.rowCount;
+    if (width8 < 8 || evenRows < 1)
+    {
+        return 0;
+    }
+    IntDecodeParams fp{};
+    for (int k = 0; k < 4; ++k)
+    {
+        fp.plane[k] = static_cast<const uint8_t*>(p.plane[k]);
+        fp.planeStride[k] = p.planeStride[k];
+    }
+    fp.rows = static_cast<uint8_t*>(p.rows);
+    fp.rowStride = p.rowStride;
+    fp.width = width8;
+    fp.rowCount = evenRows;
+    fp.bitDepth = p.bitDepth;
+    fp.maxCode = p.maxCode;
+    fp.range = p.range;
+    fp.matrix = p.matrix;
+
+    const int smCount = p.smCount > 0 ? p.smCount : 148;
+    cudaError_t e;
+    if (sampleBytes == 1)
+    {
+        e = p.hasAlpha ? DispatchChroma<uint8_t, 1>(fp, p.xs, p.ys, smCount, stream) : DispatchChroma<uint8_t, 0>(fp, p.xs, p.ys, smCount, stream);
+    }
+    else
+    {
+        e = p.hasAlpha ? DispatchChroma<uint16_t, 1>(fp, p.xs, p.ys, smCount, stream) : DispatchChroma<uint16_t, 0>(fp, p.xs, p.ys, smCount, stream);
+    }
+    if (e != cudaSuccess)
+    {
+        return AVIFGPU_ERR_CUDA;
+    }
+    int launched = 1;
+    // Edges go through the generic kernel as sub-rectangles: the right strip (width % 8 columns) and, for vertically
+    // sub-sampled chroma, an odd last row.
+    if (width8 < p.width)
+    {
+        DecodeParams strip = p;
+        strip.width = p.width - width8;
+        strip.plane[0] = static_cast<const uint8_t*>(p.plane[0]) + static_cast<int64_t>(width8) * sampleBytes;
+        strip.plane[1] = static_cast<const uint8_t*>(p.plane[1]) + static_cast<int64_t>(width8 >> p.xs) * sampleBytes;
+        strip.plane[2] = static_cast<const uint8_t*>(p.plane[2]) + static_cast<int64_t>(width8 >> p.xs) * sampleBytes;
+        if (p.hasAlpha)
+        {
+            strip.plane[3] = static_cast<const uint8_t*>(p.plane[3]) + static_cast<int64_t>(width8) * sampleBytes;
+        }
+        strip.rows = static_cast<uint8_t*>(p.rows) + static_cast<int64_t>(width8) * channels * sampleBytes;
+        const int n = LaunchDecodeGeneric(strip, streamHandle);
+        if (n < 0) return n;
+        launched += n;
+    }
+    if (evenRows < p.rowCount)
+    {
+        DecodeParams strip = p;
+        strip.width = width8;
+        strip.rowCount = p.rowCount - evenRows;
+        strip.plane[0] = static_cast<const uint8_t*>(p.plane[0]) + static_cast<int64_t>(evenRows) * p.planeStride[0];
+        strip.plane[1] = static_cast<const uint8_t*>(p.plane[1]) + static_cast<int64_t>(evenRows >> p.ys) * p.planeStride[1];
+        strip.plane[2] = static_cast<const uint8_t*>(p.plane[2]) + static_cast<int64_t>(evenRows >> p.ys) * p.planeStride[2];
+        if (p.hasAlpha)
+        {
+            strip.plane[3] = static_cast<const uint8_t*>(p.plane[3]) + static_cast<int64_t>(evenRows) * p.planeStride[3];
+        }
+        strip.rows = static_cast<uint8_t*>(p.rows) + static_cast<int64_t>(evenRows) * p.rowStride;
+        const int n = LaunchDecodeGeneric(strip, streamHandle);
+        if (n < 0) return n;
+        launched += n;
+    }
+    return launched;
+}
+
+} // namespace avifgpu

@@ -1,0 +1,89 @@
+#!/usr/bin/env python3
+"""Device-resident throughput of configurations outside BASELINE.json's bench lines (they run wherever the dispatcher
+sends them): 8-bit and 16-bit decodes, 8-bit encode, at 8K.  Prints one JSON line per case.
+
+    python profiles/measure_generic_paths.py
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "avif-format_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+import avifgpu  # noqa: E402
+from avifgpu import abi  # noqa: E402
+
+W, H = 7680, 4320
+dev = torch.device("cuda", 0)
+gpu = avifgpu.Context(0)
+g = torch.Generator(device=dev)
+g.manual_seed(1)
+
+
+def timed(fn, steps=30):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def decode_case(name, bit_depth, host_depth, chroma, nclx, bytes_per_px, alpha=False):
+    desc = abi.DecodeDesc(W, H, abi.COLORSPACE_YCBCR, chroma, bit_depth, abi.ALPHA_STRAIGHT if alpha else abi.ALPHA_NONE, host_depth, nclx)
+    shapes = abi.decode_plane_shapes(desc)
+    dt = torch.uint8 if bit_depth == 8 else torch.int16
+    sets = []
+    for _ in range(3):
+        planes = [None if s is None else torch.randint(0, 1 << bit_depth, s, generator=g, device=dev, dtype=torch.int32).to(dt) for s in shapes]
+        ch = abi.decode_host_channels(desc)
+        out = torch.empty((H, W * ch), dtype={8: torch.uint8, 16: torch.int16, 32: torch.float32}[host_depth], device=dev)
+        sets.append((avifgpu.planes_from_tensors(planes), planes, out))
+    i = [0]
+
+    def run():
+        s = sets[i[0] % 3]
+        i[0] += 1
+        gpu.decode_device(desc, s[0], s[2].data_ptr(), s[2].stride(0) * s[2].element_size())
+    ms = timed(run)
+    print(json.dumps({"case": name, "ms": ms, "gpx_s": W * H / ms / 1e6, "gb_s": W * H * bytes_per_px / ms / 1e6}))
+
+
+def encode_case(name, host_depth, channels, image_depth, chroma, nclx, bytes_per_px, alpha=abi.ALPHA_NONE):
+    desc = abi.EncodeDesc(W, H, host_depth, channels, alpha, image_depth, abi.TRANSFER_CLIP, 80, abi.LAYOUT_PLANAR_YCBCR, chroma,
+                          abi.DOWN_FILTER_BOX, abi.GRAY16_LUT, nclx)
+    shapes = abi.encode_plane_shapes(desc)
+    sets = []
+    for _ in range(3):
+        if host_depth == 8:
+            rows = torch.randint(0, 256, (H, W * channels), generator=g, device=dev, dtype=torch.int32).to(torch.uint8)
+        else:
+            rows = torch.randint(0, 32769, (H, W * channels), generator=g, device=dev, dtype=torch.int32).to(torch.int16)
+        dt = torch.uint8 if image_depth == 8 else torch.int16
+        planes = [None if s is None else torch.empty(s, dtype=dt, device=dev) for s in shapes]
+        sets.append((rows, avifgpu.planes_from_tensors(planes), planes))
+    i = [0]
+
+    def run():
+        s = sets[i[0] % 3]
+        i[0] += 1
+        gpu.encode_device(desc, s[0].data_ptr(), s[0].stride(0) * s[0].element_size(), s[1])
+    ms = timed(run)
+    print(json.dumps({"case": name, "ms": ms, "gpx_s": W * H / ms / 1e6, "gb_s": W * H * bytes_per_px / ms / 1e6}))
+
+
+n601 = abi.Nclx(1, 1, 13, abi.MATRIX_BT601, 1)
+decode_case("decode 8-bit 4:2:0 -> RGB8 (a15)", 8, 8, abi.CHROMA_420, n601, 1.5 + 3)
+decode_case("decode 8-bit 4:4:4 + alpha -> RGBA8 (a15)", 8, 8, abi.CHROMA_444, n601, 4 + 4, alpha=True)
+decode_case("decode 10-bit 4:2:0 -> RGB16 (a14)", 10, 16, abi.CHROMA_420, n601, 3 + 6)
+decode_case("decode 12-bit 4:4:4 -> RGB16 (a14)", 12, 16, abi.CHROMA_444, n601, 6 + 6)
+encode_case("encode RGB8 -> 8-bit 4:2:0 (a3)", 8, 3, 8, abi.CHROMA_420, n601, 3 + 1.5)
+encode_case("encode RGBA8 -> 8-bit 4:4:4 + A (config 1 at 8K) (a3)", 8, 4, 8, abi.CHROMA_444, n601, 4 + 4, alpha=abi.ALPHA_STRAIGHT)
+encode_case("encode RGB8 -> 10-bit 4:2:0 (a3)", 8, 3, 10, abi.CHROMA_420, n601, 3 + 3)

@@ -254,3 +254,44 @@ def test_every_10bit_triple_through_the_production_decode_kernel(gpu):
         differing += int((fast[y:y + 4096].view(torch.int32) != exact[y:y + 4096].view(torch.int32)).sum().item())
     assert differing == 0, f"{differing} of {fast.numel()} output samples differ"
     assert bool(torch.isfinite(fast[:4096]).all().item())
+
+
+# ---- integer hosts, decode (kernels_fast_decode_int.cu) -----------------------------------------------------------------
+
+@pytest.mark.parametrize("w,h", [(8, 2), (9, 3), (24, 1), (67, 5), (256, 16), (263, 9), (1031, 6)])
+@pytest.mark.parametrize("chroma", [abi.CHROMA_420, abi.CHROMA_422, abi.CHROMA_444])
+@pytest.mark.parametrize("alpha", [abi.ALPHA_NONE, abi.ALPHA_STRAIGHT, abi.ALPHA_PREMULTIPLIED])
+def test_ycc_to_rgb_integer_fast_kernel(gpu, checker, w, h, chroma, alpha):
+    for bit_depth, host_depth, nclx in ((8, 8, cases.NCLX_601(1)), (8, 8, cases.NCLX_709(0)), (10, 16, cases.NCLX_601(1)),
+                                        (12, 16, cases.NCLX_2020_PQ(0))):
+        desc = abi.DecodeDesc(w, h, abi.COLORSPACE_YCBCR, chroma, bit_depth, alpha, host_depth, nclx)
+        planes = cases.code_planes(cases.rng_for(f"decint_{w}x{h}_{chroma}_{alpha}_{bit_depth}"), desc, overshoot=True)
+        expected = checker.decode(desc, planes, threads=4)
+        got = gpu.decode(desc, planes)
+        assert np.array_equal(expected, got), (bit_depth, host_depth, int((expected != got).sum()))
+        if h > 3:  # a block that starts on an odd row (generic kernel) next to blocks that do not
+            out = np.zeros_like(expected)
+            gpu.decode(desc, planes, y0=0, nrows=1, out=out[0:1])
+            gpu.decode(desc, planes, y0=1, nrows=h - 1, out=out[1:])
+            assert np.array_equal(expected, out)
+
+
+def test_every_8bit_triple_through_the_integer_decode_kernel(gpu):
+    """All 2^24 (Y, Cb, Cr) triples of 8-bit codes (4096 x 4096, 4:4:4, BT.601 full and limited range) through the tuned
+    kernel and through the generic kernel (reached with an unaligned row pointer): identical bytes."""
+    import torch
+    import avifgpu
+    dev = torch.device("cuda", gpu.device)
+    w = h = 4096
+    index = torch.arange(w * h, dtype=torch.int32, device=dev).view(h, w)
+    planes = [(index & 255).to(torch.uint8), ((index >> 8) & 255).to(torch.uint8), (index >> 16).to(torch.uint8)]
+    struct = avifgpu.planes_from_tensors(planes + [None])
+    for full_range in (1, 0):
+        desc = abi.DecodeDesc(w, h, abi.COLORSPACE_YCBCR, abi.CHROMA_444, 8, abi.ALPHA_NONE, 8, cases.NCLX_601(full_range))
+        fast = torch.zeros((h, w * 3), dtype=torch.uint8, device=dev)
+        gpu.decode_device(desc, struct, fast.data_ptr(), fast.stride(0))
+        backing = torch.zeros((h, w * 3 + 8), dtype=torch.uint8, device=dev)
+        exact = backing[:, 1:w * 3 + 1]
+        gpu.decode_device(desc, struct, exact.data_ptr(), exact.stride(0))
+        torch.cuda.synchronize(dev)
+        assert int((fast != exact).sum().item()) == 0
