@@ -146,23 +146,77 @@ struct Rgb16Params
     ForwardMatrix matrix;
     float chromaOffset;
     int32_t topLeft;
+    uint32_t maxCode;
 };
 
-// Host sample (0..32768, or beyond: the formula is defined to continue) -> 2^23 + code, as a float.
-__device__ __forceinline__ float SampleToBiasedCode(uint32_t v, const Rgb16Params& p)
+// Host sample -> 2^23 + code, as a float.
+//   16-bit host (0..32768, or beyond: the formula is defined to continue)  WriteHeifImage.cpp:140-166:
+//       (int)((v / 32768f) * max + 0.5f), clamped -- v / 32768f is exact as a multiplication;
+//   8-bit host, 8-bit image   the sample is the code                        WriteHeifImage.cpp:743-747
+//   8-bit host, deeper image  (int)((v / 255f) * max + 0.5f): a true division, so the 256 results are tabulated in
+//                             shared memory at kernel start (the reference builds the same table, :87-112).
+template <typename HostT, typename PlaneT>
+__device__ __forceinline__ float SampleToBiasedCode(uint32_t v, const Rgb16Params& p, const float* __restrict__ hostLut)
 {
-    // WriteHeifImage.cpp:140-166: (int)((v / 32768f) * max + 0.5f), clamped
-    const float t = ((UintToFloatExact(v) * (1.0f / 32768.0f)) * p.maxCodeFloat) + 0.5f;
-    return BiasedTrunc(t, p.biasedMax);
+    if (sizeof(HostT) == 2)
+    {
+        const float t = ((UintToFloatExact(v) * (1.0f / 32768.0f)) * p.maxCodeFloat) + 0.5f;
+        return BiasedTrunc(t, p.biasedMax);
+    }
+    if (sizeof(PlaneT) == 1)
+    {
+        return __uint_as_float(0x4b000000u | v);
+    }
+    return hostLut[v];
 }
 
 __device__ __forceinline__ uint32_t BiasedToCode(float biased) { return __float_as_uint(biased) & 0x7fffffu; }
 
-template <int CHANNELS, int XS, int YS>
-__global__ void __launch_bounds__(kRgbThreads) EncodeRgb16PlanarKernel(const Rgb16Params p)
+// 8 (4) consecutive plane samples in one vector store.
+template <typename PlaneT>
+__device__ __forceinline__ void StoreEight(uint8_t* address, const uint32_t (&c)[8])
+{
+    if (sizeof(PlaneT) == 2)
+    {
+        __stcs(reinterpret_cast<uint4*>(address), make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), c[4] | (c[5] << 16), c[6] | (c[7] << 16)));
+    }
+    else
+    {
+        __stcs(reinterpret_cast<uint2*>(address),
+               make_uint2(c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24), c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24)));
+    }
+}
+
+template <typename PlaneT>
+__device__ __forceinline__ void StoreFour(uint8_t* address, const uint32_t (&c)[4])
+{
+    if (sizeof(PlaneT) == 2)
+    {
+        __stcs(reinterpret_cast<uint2*>(address), make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16)));
+    }
+    else
+    {
+        __stcs(reinterpret_cast<uint32_t*>(address), c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24));
+    }
+}
+
+// HostT: uint8_t / uint16_t host samples; PlaneT: uint8_t (8-bit image) / uint16_t (10 / 12-bit image) plane samples.
+template <typename HostT, typename PlaneT, int CHANNELS, int XS, int YS>
+__global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rgb16Params p)
 {
     constexpr int kRows = 1 + YS;
-    constexpr int kWordsPerRow = CHANNELS * 4; // 8 pixels x CHANNELS x 2 bytes / 4
+    constexpr int kWordsPerRow = CHANNELS * 2 * static_cast<int>(sizeof(HostT)); // 8 pixels x CHANNELS samples / 4 bytes
+    constexpr int kVectorWords = (kWordsPerRow % 4 == 0) ? 4 : 2;                 // 128-bit loads where the row chunk allows
+    constexpr int kPlaneBytes = static_cast<int>(sizeof(PlaneT));
+    __shared__ float hostLut[(sizeof(HostT) == 1 && sizeof(PlaneT) == 2) ? 256 : 1];
+    if (sizeof(HostT) == 1 && sizeof(PlaneT) == 2)
+    {
+        for (uint32_t v = threadIdx.x; v < 256; v += blockDim.x)
+        {
+            hostLut[v] = __uint_as_float(0x4b000000u | DepthLutEntry(v, 255.0f, p.maxCode));
+        }
+        __syncthreads();
+    }
     const long long groups = static_cast<long long>(p.groupsPerRow) * ((p.rowCount + YS) >> YS);
     for (long long group = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; group < groups;
          group += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -175,15 +229,24 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgb16PlanarKernel(const Rgb
 #pragma unroll
         for (int r = 0; r < kRows; ++r)
         {
-            const uint4* source = reinterpret_cast<const uint4*>(p.rows + (y0 + r) * p.rowStride + static_cast<long long>(column) * (kWordsPerRow * 4));
+            const uint8_t* source = p.rows + (y0 + r) * p.rowStride + static_cast<long long>(column) * (kWordsPerRow * 4);
 #pragma unroll
-            for (int q = 0; q < kWordsPerRow / 4; ++q)
+            for (int q = 0; q < kWordsPerRow / kVectorWords; ++q)
             {
-                const uint4 w = __ldcs(source + q);
-                words[r][4 * q + 0] = w.x;
-                words[r][4 * q + 1] = w.y;
-                words[r][4 * q + 2] = w.z;
-                words[r][4 * q + 3] = w.w;
+                if (kVectorWords == 4)
+                {
+                    const uint4 w = __ldcs(reinterpret_cast<const uint4*>(source) + q);
+                    words[r][4 * q + 0] = w.x;
+                    words[r][4 * q + 1] = w.y;
+                    words[r][4 * q + 2] = w.z;
+                    words[r][4 * q + 3] = w.w;
+                }
+                else
+                {
+                    const uint2 w = __ldcs(reinterpret_cast<const uint2*>(source) + q);
+                    words[r][2 * q + 0] = w.x;
+                    words[r][2 * q + 1] = w.y;
+                }
             }
         }
 
@@ -196,15 +259,19 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgb16PlanarKernel(const Rgb
 #pragma unroll
             for (int i = 0; i < 8; ++i)
             {
-                // sample k of the row sits in half-word k: word k/2, low or high half
+                // sample k of the row sits in half-word (byte) k of the loaded words
                 auto sample = [&](int k) -> uint32_t
                 {
-                    const uint32_t w = words[r][k >> 1];
-                    return (k & 1) ? (w >> 16) : (w & 0xffffu);
+                    if (sizeof(HostT) == 2)
+                    {
+                        const uint32_t w = words[r][k >> 1];
+                        return (k & 1) ? (w >> 16) : (w & 0xffffu);
+                    }
+                    return (words[r][k >> 2] >> (8 * (k & 3))) & 0xffu;
                 };
-                const float rb = SampleToBiasedCode(sample(i * CHANNELS + 0), p);
-                const float gb = SampleToBiasedCode(sample(i * CHANNELS + 1), p);
-                const float bb = SampleToBiasedCode(sample(i * CHANNELS + 2), p);
+                const float rb = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 0), p, hostLut);
+                const float gb = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 1), p, hostLut);
+                const float bb = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 2), p, hostLut);
                 const float rf = rb - kTwo23, gf = gb - kTwo23, bf = bb - kTwo23;
                 float yf;
                 if (p.matrix.identity)
@@ -222,16 +289,13 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgb16PlanarKernel(const Rgb
                 yCodes[i] = BiasedToCode(BiasedTrunc(yf + 0.5f, p.biasedMax));
                 if (CHANNELS == 4)
                 {
-                    aCodes[i] = BiasedToCode(SampleToBiasedCode(sample(i * CHANNELS + 3), p));
+                    aCodes[i] = BiasedToCode(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 3), p, hostLut));
                 }
             }
-            const long long offset = (y0 + r) * p.stride[0] + static_cast<long long>(column) * 16;
-            __stcs(reinterpret_cast<uint4*>(p.plane[0] + offset),
-                   make_uint4(yCodes[0] | (yCodes[1] << 16), yCodes[2] | (yCodes[3] << 16), yCodes[4] | (yCodes[5] << 16), yCodes[6] | (yCodes[7] << 16)));
+            StoreEight<PlaneT>(p.plane[0] + (y0 + r) * p.stride[0] + static_cast<long long>(column) * (8 * kPlaneBytes), yCodes);
             if (CHANNELS == 4)
             {
-                __stcs(reinterpret_cast<uint4*>(p.plane[3] + (y0 + r) * p.stride[3] + static_cast<long long>(column) * 16),
-                       make_uint4(aCodes[0] | (aCodes[1] << 16), aCodes[2] | (aCodes[3] << 16), aCodes[4] | (aCodes[5] << 16), aCodes[6] | (aCodes[7] << 16)));
+                StoreEight<PlaneT>(p.plane[3] + (y0 + r) * p.stride[3] + static_cast<long long>(column) * (8 * kPlaneBytes), aCodes);
             }
         }
 
@@ -249,11 +313,9 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgb16PlanarKernel(const Rgb
                     cbCode[i] = quantise(cb[r][i]);
                     crCode[i] = quantise(cr[r][i]);
                 }
-                const long long offset = static_cast<long long>(column) * 16;
-                __stcs(reinterpret_cast<uint4*>(p.plane[1] + (y0 + r) * p.stride[1] + offset),
-                       make_uint4(cbCode[0] | (cbCode[1] << 16), cbCode[2] | (cbCode[3] << 16), cbCode[4] | (cbCode[5] << 16), cbCode[6] | (cbCode[7] << 16)));
-                __stcs(reinterpret_cast<uint4*>(p.plane[2] + (y0 + r) * p.stride[2] + offset),
-                       make_uint4(crCode[0] | (crCode[1] << 16), crCode[2] | (crCode[3] << 16), crCode[4] | (crCode[5] << 16), crCode[6] | (crCode[7] << 16)));
+                const long long offset = static_cast<long long>(column) * (8 * kPlaneBytes);
+                StoreEight<PlaneT>(p.plane[1] + (y0 + r) * p.stride[1] + offset, cbCode);
+                StoreEight<PlaneT>(p.plane[2] + (y0 + r) * p.stride[2] + offset, crCode);
             }
         }
         else
@@ -281,10 +343,10 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgb16PlanarKernel(const Rgb
                 cbCode[s] = quantise(cbv);
                 crCode[s] = quantise(crv);
             }
-            const long long offset = static_cast<long long>(column) * 8;
+            const long long offset = static_cast<long long>(column) * (4 * kPlaneBytes);
             const long long chromaRow = YS ? rowPair : y0;
-            __stcs(reinterpret_cast<uint2*>(p.plane[1] + chromaRow * p.stride[1] + offset), make_uint2(cbCode[0] | (cbCode[1] << 16), cbCode[2] | (cbCode[3] << 16)));
-            __stcs(reinterpret_cast<uint2*>(p.plane[2] + chromaRow * p.stride[2] + offset), make_uint2(crCode[0] | (crCode[1] << 16), crCode[2] | (crCode[3] << 16)));
+            StoreFour<PlaneT>(p.plane[1] + chromaRow * p.stride[1] + offset, cbCode);
+            StoreFour<PlaneT>(p.plane[2] + chromaRow * p.stride[2] + offset, crCode);
         }
     }
 }
@@ -294,8 +356,8 @@ bool Aligned(const void* p, int64_t stride, int alignment)
     return (reinterpret_cast<uintptr_t>(p) % alignment) == 0 && (stride % alignment) == 0;
 }
 
-template <int CHANNELS>
-cudaError_t LaunchRgb16(const Rgb16Params& rp, int xs, int ys, int smCount, cudaStream_t stream)
+template <typename HostT, typename PlaneT, int CHANNELS>
+cudaError_t LaunchRgbInt(const Rgb16Params& rp, int xs, int ys, int smCount, cudaStream_t stream)
 {
     const long long groups = static_cast<long long>(rp.groupsPerRow) * ((rp.rowCount + ys) >> ys);
     long long blocks = (groups + kRgbThreads - 1) / kRgbThreads;
@@ -303,10 +365,16 @@ cudaError_t LaunchRgb16(const Rgb16Params& rp, int xs, int ys, int smCount, cuda
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const unsigned grid = static_cast<unsigned>(blocks);
-    if (xs == 1 && ys == 1) EncodeRgb16PlanarKernel<CHANNELS, 1, 1><<<grid, kRgbThreads, 0, stream>>>(rp);
-    else if (xs == 1) EncodeRgb16PlanarKernel<CHANNELS, 1, 0><<<grid, kRgbThreads, 0, stream>>>(rp);
-    else EncodeRgb16PlanarKernel<CHANNELS, 0, 0><<<grid, kRgbThreads, 0, stream>>>(rp);
+    if (xs == 1 && ys == 1) EncodeRgbIntPlanarKernel<HostT, PlaneT, CHANNELS, 1, 1><<<grid, kRgbThreads, 0, stream>>>(rp);
+    else if (xs == 1) EncodeRgbIntPlanarKernel<HostT, PlaneT, CHANNELS, 1, 0><<<grid, kRgbThreads, 0, stream>>>(rp);
+    else EncodeRgbIntPlanarKernel<HostT, PlaneT, CHANNELS, 0, 0><<<grid, kRgbThreads, 0, stream>>>(rp);
     return cudaGetLastError();
+}
+
+template <typename HostT, typename PlaneT>
+cudaError_t LaunchRgbIntChannels(const Rgb16Params& rp, int channels, int xs, int ys, int smCount, cudaStream_t stream)
+{
+    return channels == 4 ? LaunchRgbInt<HostT, PlaneT, 4>(rp, xs, ys, smCount, stream) : LaunchRgbInt<HostT, PlaneT, 3>(rp, xs, ys, smCount, stream);
 }
 
 } // namespace
@@ -323,13 +391,13 @@ cudaError_t BuildGray16Lut(uint16_t* deviceLut, int smpte428, uint32_t maxCode, 
 int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHandle)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
-    if (hostDepth != 16 || p.imageDepth <= 8)
+    if (hostDepth != 16 && hostDepth != 8)
     {
         return 0;
     }
     const int smCount = p.smCount > 0 ? p.smCount : 148;
 
-    if (p.channels == 1 && !p.planar)
+    if (hostDepth == 16 && p.imageDepth > 8 && p.channels == 1 && !p.planar)
     {
         if (p.gray16Lut == nullptr || p.width < 8 || !Aligned(p.rows, p.rowStride, 16) || !Aligned(p.plane[0], p.planeStride[0], 16))
         {
@@ -374,13 +442,17 @@ int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHa
 
     // The biased-truncation trick needs non-negative intermediates: true for every matrix with kr, kg, kb >= 0
     // (all of H.273's); anything else takes the generic kernel.
-    if (p.planar && (p.channels == 3 || p.channels == 4) && !p.premultiply &&
+    if (p.planar && (p.channels == 3 || p.channels == 4) && !p.premultiply && p.imageDepth <= 12 &&
         (p.matrix.identity || (p.matrix.kr >= 0.0f && p.matrix.kg >= 0.0f && p.matrix.kb >= 0.0f && p.matrix.kr < 1.0f && p.matrix.kb < 1.0f)))
     {
-        const int chromaAlign = p.xs ? 8 : 16;
-        if (p.width < 8 || !Aligned(p.rows, p.rowStride, 16) || !Aligned(p.plane[0], p.planeStride[0], 16) ||
+        const int hostBytes = hostDepth / 8;
+        const int planeBytes = p.imageDepth > 8 ? 2 : 1;
+        const int rowAlign = (8 * p.channels * hostBytes) % 16 == 0 ? 16 : 8; // a thread's 8-pixel chunk: 128-bit or 64-bit loads
+        const int lumaAlign = 8 * planeBytes;
+        const int chromaAlign = (p.xs ? 4 : 8) * planeBytes;
+        if (p.width < 8 || !Aligned(p.rows, p.rowStride, rowAlign) || !Aligned(p.plane[0], p.planeStride[0], lumaAlign) ||
             !Aligned(p.plane[1], p.planeStride[1], chromaAlign) || !Aligned(p.plane[2], p.planeStride[2], chromaAlign) ||
-            (p.channels == 4 && !Aligned(p.plane[3], p.planeStride[3], 16)))
+            (p.channels == 4 && !Aligned(p.plane[3], p.planeStride[3], lumaAlign)))
         {
             return 0;
         }
@@ -405,22 +477,33 @@ int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHa
         rp.matrix = p.matrix;
         rp.chromaOffset = p.chromaOffset;
         rp.topLeft = p.topLeft;
-        const cudaError_t e = p.channels == 4 ? LaunchRgb16<4>(rp, p.xs, p.ys, smCount, stream) : LaunchRgb16<3>(rp, p.xs, p.ys, smCount, stream);
+        rp.maxCode = p.maxCode;
+        cudaError_t e;
+        if (hostBytes == 2)
+        {
+            e = planeBytes == 2 ? LaunchRgbIntChannels<uint16_t, uint16_t>(rp, p.channels, p.xs, p.ys, smCount, stream)
+                                : LaunchRgbIntChannels<uint16_t, uint8_t>(rp, p.channels, p.xs, p.ys, smCount, stream);
+        }
+        else
+        {
+            e = planeBytes == 2 ? LaunchRgbIntChannels<uint8_t, uint16_t>(rp, p.channels, p.xs, p.ys, smCount, stream)
+                                : LaunchRgbIntChannels<uint8_t, uint8_t>(rp, p.channels, p.xs, p.ys, smCount, stream);
+        }
         if (e != cudaSuccess)
         {
             return AVIFGPU_ERR_CUDA;
         }
         int launched = 1;
-        const int colBytes = p.channels * 2;
+        const int colBytes = p.channels * hostBytes;
         if (width8 < p.width)
         {
             EncodeParams strip = p;
             strip.rows = static_cast<const uint8_t*>(p.rows) + static_cast<int64_t>(width8) * colBytes;
             strip.width = p.width - width8;
-            strip.plane[0] = static_cast<uint8_t*>(p.plane[0]) + static_cast<int64_t>(width8) * 2;
-            strip.plane[1] = static_cast<uint8_t*>(p.plane[1]) + static_cast<int64_t>(width8 >> p.xs) * 2;
-            strip.plane[2] = static_cast<uint8_t*>(p.plane[2]) + static_cast<int64_t>(width8 >> p.xs) * 2;
-            if (p.channels == 4) strip.plane[3] = static_cast<uint8_t*>(p.plane[3]) + static_cast<int64_t>(width8) * 2;
+            strip.plane[0] = static_cast<uint8_t*>(p.plane[0]) + static_cast<int64_t>(width8) * planeBytes;
+            strip.plane[1] = static_cast<uint8_t*>(p.plane[1]) + static_cast<int64_t>(width8 >> p.xs) * planeBytes;
+            strip.plane[2] = static_cast<uint8_t*>(p.plane[2]) + static_cast<int64_t>(width8 >> p.xs) * planeBytes;
+            if (p.channels == 4) strip.plane[3] = static_cast<uint8_t*>(p.plane[3]) + static_cast<int64_t>(width8) * planeBytes;
             const int n = LaunchEncodeGeneric(strip, hostDepth, streamHandle);
             if (n < 0) return n;
             launched += n;

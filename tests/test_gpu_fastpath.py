@@ -139,6 +139,52 @@ def test_rgb16_planar_fast_kernel(gpu, port, w, h, channels, chroma):
                 assert (g.base[:, g.shape[1]:] == 0xCD).all(), "wrote into the row padding"
 
 
+@pytest.mark.parametrize("w,h", [(8, 2), (9, 3), (16, 1), (67, 5), (256, 17), (1031, 6)])
+@pytest.mark.parametrize("channels", [3, 4])
+@pytest.mark.parametrize("chroma", [abi.CHROMA_420, abi.CHROMA_422, abi.CHROMA_444])
+def test_rgb8_planar_fast_kernel(gpu, port, w, h, channels, chroma):
+    """8-bit hosts (WriteHeifImage.cpp:629-806) into 8-bit planes (the sample is the code) and into 10 / 12-bit planes
+    (the 256-entry depth table), plus 16-bit hosts into 8-bit planes: the same tuned kernel, other sample types."""
+    rng = cases.rng_for(f"rgb8_{w}x{h}_{channels}_{chroma}")
+    alpha = abi.ALPHA_NONE if channels == 3 else abi.ALPHA_STRAIGHT
+    for host_depth, depth, down, nclx in ((8, 8, abi.DOWN_FILTER_BOX, cases.NCLX_601()), (8, 8, abi.DOWN_FILTER_TOP_LEFT, None),
+                                          (8, 10, abi.DOWN_FILTER_BOX, cases.NCLX_709()), (8, 12, abi.DOWN_FILTER_BOX, cases.NCLX_2020_PQ()),
+                                          (8, 8, abi.DOWN_FILTER_BOX, cases.NCLX_GBR() if chroma == abi.CHROMA_444 else cases.NCLX_601()),
+                                          (16, 8, abi.DOWN_FILTER_BOX, cases.NCLX_601())):
+        rows = cases.int_host_rows(rng, h, w, channels, host_depth, beyond=(host_depth == 16))
+        desc = abi.EncodeDesc(w, h, host_depth, channels, alpha, depth, abi.TRANSFER_CLIP, 80, abi.LAYOUT_PLANAR_YCBCR, chroma, down, abi.GRAY16_LUT, nclx)
+        got = gpu.encode(desc, rows, pad=8)
+        assert cases.same_planes(port.encode(desc, rows), got), (host_depth, depth, down)
+        for g in got:
+            if g is not None:
+                assert (g.base[:, g.shape[1]:] == 0xCD).all(), "wrote into the row padding"
+
+
+def test_rgb8_every_triple_through_the_integer_encode_kernel(gpu):
+    """All 2^24 RGB8 triples (4096 x 4096) into 8-bit and 10-bit 4:4:4 planes: tuned kernel == generic kernel (reached
+    through a plane origin that is only 2-byte aligned)."""
+    import torch
+    import avifgpu
+    dev = torch.device("cuda", gpu.device)
+    w = h = 4096
+    index = torch.arange(w * h, dtype=torch.int32, device=dev)
+    rows = torch.stack([index & 255, (index >> 8) & 255, index >> 16], dim=1).to(torch.uint8).view(h, w * 3).contiguous()
+    for depth in (8, 10):
+        desc = abi.EncodeDesc(w, h, 8, 3, abi.ALPHA_NONE, depth, abi.TRANSFER_CLIP, 80, abi.LAYOUT_PLANAR_YCBCR, abi.CHROMA_444,
+                              abi.DOWN_FILTER_BOX, abi.GRAY16_LUT, cases.NCLX_601())
+        dt = torch.uint8 if depth == 8 else torch.int16
+        shapes = abi.encode_plane_shapes(desc)
+        fast = [None if s is None else torch.zeros(s, dtype=dt, device=dev) for s in shapes]
+        gpu.encode_device(desc, rows.data_ptr(), rows.stride(0), avifgpu.planes_from_tensors(fast))
+        backing = [None if s is None else torch.zeros((s[0], s[1] + 8), dtype=dt, device=dev) for s in shapes]
+        exact = [None if t is None else t[:, 1:shapes[k][1] + 1] for k, t in enumerate(backing)]
+        gpu.encode_device(desc, rows.data_ptr(), rows.stride(0), avifgpu.planes_from_tensors(exact))
+        torch.cuda.synchronize(dev)
+        for a, b in zip(fast, exact):
+            if a is not None:
+                assert int((a != b).sum().item()) == 0
+
+
 @pytest.mark.parametrize("w,h", [(8, 1), (13, 3), (64, 9), (4096, 4)])
 @pytest.mark.parametrize("curve", [abi.GRAY16_LUT, abi.GRAY16_SMPTE428])
 @pytest.mark.parametrize("depth", [10, 12])
