@@ -92,7 +92,14 @@ struct avifgpu_context
     Buffer pinnedRows[kPipelineStreams];
     Buffer pinnedPlanes[kPipelineStreams][AVIFGPU_MAX_PLANES];
     Buffer transferScratch[2];
-    std::vector<CurveTable*> curveTables; // exact step tables, built on first use per (curve, param, depth)
+    std::vector<CurveTable*> curveTables; // exact step tables, built per (curve, param, depth): explicitly or once they pay off
+    struct PendingTable
+    {
+        int curve, param, depth;
+        int64_t pixels; // converted with the exact kernel so far
+    };
+    std::vector<PendingTable> pendingTables;
+    int64_t tableAutoBuildPixels = AVIFGPU_TABLE_AUTOBUILD_DEFAULT;
     struct Gray16Lut
     {
         int depth = 0;
@@ -151,8 +158,9 @@ struct avifgpu_context
     }
 
     // The verified step table for a float-host encode description, or nullptr when the description does not use
-    // one / the table could not be verified (then the generic exact kernel serves the configuration).
-    CurveTable* CurveTableFor(const avifgpu_encode_desc& d)
+    // one / the table could not be verified / building it has not paid off yet (then the generic exact kernel serves
+    // the call).  `pixels` = the size of the call that asks; `force` = avifgpu_prepare_encode.
+    CurveTable* CurveTableFor(const avifgpu_encode_desc& d, int64_t pixels, bool force)
     {
         if (d.host_depth != 32 || d.layout != AVIFGPU_LAYOUT_PLANAR_YCBCR || d.image_bit_depth > 12)
         {
@@ -180,13 +188,35 @@ struct avifgpu_context
                 return t;
             }
         }
+        if (!force)
+        {
+            // ~40 ms of sweeps buy a ~7x faster kernel: worth it once a configuration has seen enough pixels
+            PendingTable* pending = nullptr;
+            for (PendingTable& candidate : pendingTables)
+            {
+                if (candidate.curve == curve && candidate.param == param && candidate.depth == d.image_bit_depth)
+                {
+                    pending = &candidate;
+                }
+            }
+            if (pending == nullptr)
+            {
+                pendingTables.push_back(PendingTable{ curve, param, d.image_bit_depth, 0 });
+                pending = &pendingTables.back();
+            }
+            pending->pixels += pixels;
+            if (tableAutoBuildPixels < 0 || pending->pixels <= tableAutoBuildPixels)
+            {
+                return nullptr;
+            }
+        }
         CurveTable* t = new (std::nothrow) CurveTable();
         if (t == nullptr)
         {
             return nullptr;
         }
         BuildCurveTable(curve, param, d.image_bit_depth, streams[0], t);
-        launches += t->stats.sweptInputs ? 2 : 0;
+        launches += t->stats.sweptInputs ? (t->stats.bandBitmapBytes ? 3 : 2) : 0; // sweep, (band bitmap,) verify
         curveTables.push_back(t);
         return t;
     }
@@ -590,7 +620,7 @@ AVIFGPU_EXPORT int avifgpu_encode_rows_device(avifgpu_context* ctx, const avifgp
     }
     DeviceGuard guard(ctx->device);
     p.smCount = ctx->smCount;
-    if (CurveTable* table = ctx->CurveTableFor(*desc))
+    if (CurveTable* table = ctx->CurveTableFor(*desc, static_cast<int64_t>(desc->width) * nrows, false))
     {
         p.curveTable = table->valid ? &table->view : nullptr;
     }
@@ -719,7 +749,7 @@ AVIFGPU_EXPORT int avifgpu_encode_rows(avifgpu_context* ctx, const avifgpu_encod
 
     DeviceGuard guard(ctx->device);
     base.smCount = ctx->smCount;
-    if (CurveTable* table = ctx->CurveTableFor(*desc))
+    if (CurveTable* table = ctx->CurveTableFor(*desc, static_cast<int64_t>(desc->width) * nrows, false))
     {
         base.curveTable = table->valid ? &table->view : nullptr;
     }
@@ -983,7 +1013,7 @@ AVIFGPU_EXPORT int avifgpu_prepare_encode(avifgpu_context* ctx, const avifgpu_en
         return ctx->Fail(status, error);
     }
     DeviceGuard guard(ctx->device);
-    CurveTable* table = ctx->CurveTableFor(*desc);
+    CurveTable* table = ctx->CurveTableFor(*desc, 0, true);
     ctx->Gray16LutFor(*desc);
     if (out_stats != nullptr)
     {
@@ -1006,6 +1036,16 @@ AVIFGPU_EXPORT int avifgpu_prepare_encode(avifgpu_context* ctx, const avifgpu_en
     {
         ctx->lastError = "step table not used (generic exact kernel serves this configuration): " + table->error;
     }
+    return AVIFGPU_OK;
+}
+
+AVIFGPU_EXPORT int avifgpu_set_table_autobuild(avifgpu_context* ctx, int64_t pixels)
+{
+    if (ctx == nullptr)
+    {
+        return AVIFGPU_ERR_BAD_PARAM;
+    }
+    ctx->tableAutoBuildPixels = pixels;
     return AVIFGPU_OK;
 }
 

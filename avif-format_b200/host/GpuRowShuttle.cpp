@@ -227,7 +227,8 @@ namespace
             addPlane(heif_channel_Alpha, 3, imageSize.h, imageSize.v);
         }
 
-        ThrowIfFailed(ctx, avifgpu_prepare_encode(ctx, &desc, nullptr));
+        // No avifgpu_prepare_encode() here: one image goes through the exact kernel (PCIe, not the kernel, bounds a
+        // single save); the library builds its step tables by itself once a context has seen enough pixels.
 
         const int64_t rowBytes = static_cast<int64_t>(imageSize.h) * avifgpu_encode_host_col_bytes(&desc);
         if (rowBytes > std::numeric_limits<int32>::max())

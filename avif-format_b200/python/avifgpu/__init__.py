@@ -70,6 +70,7 @@ def library():
         [ctx_p, C.POINTER(abi.DecodeDesc), C.POINTER(abi.Planes), C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p])
     sig("avifgpu_transfer_f32", C.c_int, [ctx_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t])
     sig("avifgpu_prepare_encode", C.c_int, [ctx_p, C.POINTER(abi.EncodeDesc), C.POINTER(abi.CurveStats)])
+    sig("avifgpu_set_table_autobuild", C.c_int, [ctx_p, C.c_int64])
     _lib = lib
     return lib
 
@@ -80,7 +81,7 @@ EXPORTED_SYMBOLS = [
     "avifgpu_encode_host_col_bytes", "avifgpu_decode_host_col_bytes", "avifgpu_encode_plane_geometry",
     "avifgpu_decode_plane_geometry", "avifgpu_get_yuv_coefficients", "avifgpu_get_hlg_luma_coefficients",
     "avifgpu_build_yuv_tables", "avifgpu_encode_rows", "avifgpu_decode_rows", "avifgpu_encode_rows_device",
-    "avifgpu_decode_rows_device", "avifgpu_transfer_f32", "avifgpu_prepare_encode",
+    "avifgpu_decode_rows_device", "avifgpu_transfer_f32", "avifgpu_prepare_encode", "avifgpu_set_table_autobuild",
 ]
 
 
@@ -191,6 +192,11 @@ class Context:
         self._check(self.lib.avifgpu_decode_rows(self.handle, C.byref(desc), C.byref(p), y0, nrows, out.ctypes.data,
                                                  out.strides[0]))
         return out
+
+    def set_table_autobuild(self, pixels):
+        """After how many pixels of one configuration the step tables are built automatically (0 = at first use,
+        negative = never); see avifgpu_set_table_autobuild."""
+        self._check(self.lib.avifgpu_set_table_autobuild(self.handle, int(pixels)))
 
     def prepare_encode(self, desc):
         """Builds the device tables `desc` needs and returns their statistics (abi.CurveStats)."""

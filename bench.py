@@ -340,6 +340,8 @@ def run_b200(args, workload, rank, world, local_rank):
 
     gpu = avifgpu.Context(local_rank)
     wl = workload
+    if wl.direction == "encode":
+        gpu.prepare_encode(wl.enc)  # a frame pipeline builds its step tables up front (one-off, ~40 ms)
     copies = 3  # rotate distinct frames so nothing of a previous step survives in the 126 MB L2
     seed0 = {"c2": 2, "c3": 3, "c4": 4, "c5": 5}[wl.key] * 1000 + 1234
     inputs = [wl.make_device_input(torch, device, seed0 + 17 * i + 101 * rank) for i in range(copies)]

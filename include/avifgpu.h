@@ -288,10 +288,20 @@ typedef struct avifgpu_curve_stats
     double build_ms;
 } avifgpu_curve_stats;
 
-/* Builds whatever device-side tables `desc` needs so that the first avifgpu_encode_rows* call does not pay for
- * it (the *_device entry points otherwise build them synchronously on first use).  out_stats may be NULL. */
+/* Builds whatever device-side tables `desc` needs, now.  out_stats may be NULL.
+ * The exact step tables of the float PQ / SMPTE 428 encode path cost about 40 ms to build and verify (once per
+ * context and configuration) and make that path several times faster, which pays off after roughly two gigapixels:
+ * frame pipelines call this up front; a caller that converts one image does not need to (see
+ * avifgpu_set_table_autobuild). */
 AVIFGPU_EXPORT int avifgpu_prepare_encode(avifgpu_context* ctx, const avifgpu_encode_desc* desc,
                                           avifgpu_curve_stats* out_stats);
+
+/* Without avifgpu_prepare_encode() the encode calls convert with the exact kernel (glibc-identical powf per sample)
+ * until `pixels` pixels of one configuration have gone through this context, and build the step tables then.
+ * Default AVIFGPU_TABLE_AUTOBUILD_DEFAULT; 0 = build at first use; negative = never build automatically.
+ * Results are bit-identical either way. */
+#define AVIFGPU_TABLE_AUTOBUILD_DEFAULT (((int64_t)1) << 31)
+AVIFGPU_EXPORT int avifgpu_set_table_autobuild(avifgpu_context* ctx, int64_t pixels);
 
 /* ---- primitive-level entry points (parity gates G2/G5; not on the plug-in's call path) -------------- */
 

@@ -44,5 +44,6 @@ def checker():
 def gpu():
     import avifgpu
     ctx = avifgpu.Context(0)
+    ctx.set_table_autobuild(0)  # the tests exercise the step tables: build them at first use, whatever the image size
     yield ctx
     ctx.close()

@@ -341,3 +341,34 @@ def test_every_8bit_triple_through_the_integer_decode_kernel(gpu):
         gpu.decode_device(desc, struct, exact.data_ptr(), exact.stride(0))
         torch.cuda.synchronize(dev)
         assert int((fast != exact).sum().item()) == 0
+
+
+# ---- when the step tables get built ---------------------------------------------------------------------------------------
+
+def test_step_tables_are_built_when_they_pay_off(port):
+    """A fresh context converts with the exact kernel (one launch, no 40 ms table build) until one configuration has
+    seen more pixels than the auto-build threshold, or until avifgpu_prepare_encode(); the planes never change."""
+    import avifgpu
+    w, h = 256, 64
+    desc = planar_desc(w, h)
+    rows = cases.float_host_rows(np.random.default_rng(99), h, w, 3)
+    expected = port.encode(desc, rows)
+    with avifgpu.Context(0) as ctx:
+        assert cases.same_planes(expected, ctx.encode(desc, rows))
+        per_call = ctx.launch_count()
+        assert per_call == 1, "a single small image must not pay for table construction"
+        ctx.set_table_autobuild(3 * w * h)  # pixels of this configuration before the tables are worth building
+        assert cases.same_planes(expected, ctx.encode(desc, rows))
+        assert cases.same_planes(expected, ctx.encode(desc, rows))
+        assert ctx.launch_count() == 3 * per_call
+        assert cases.same_planes(expected, ctx.encode(desc, rows))  # 4 * w * h > threshold: sweep + bitmap + verify + kernel
+        assert ctx.launch_count() == 4 * per_call + 3
+        assert cases.same_planes(expected, ctx.encode(desc, rows))
+        assert ctx.launch_count() == 5 * per_call + 3
+    with avifgpu.Context(0) as ctx:
+        ctx.set_table_autobuild(-1)
+        for _ in range(3):
+            assert cases.same_planes(expected, ctx.encode(desc, rows))
+        assert ctx.launch_count() == 3
+        assert ctx.prepare_encode(desc).as_dict()["valid"] == 1  # explicit request still builds
+        assert cases.same_planes(expected, ctx.encode(desc, rows))
