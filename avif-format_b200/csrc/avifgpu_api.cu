@@ -162,7 +162,7 @@ struct avifgpu_context
     // the call).  `pixels` = the size of the call that asks; `force` = avifgpu_prepare_encode.
     CurveTable* CurveTableFor(const avifgpu_encode_desc& d, int64_t pixels, bool force)
     {
-        if (d.host_depth != 32 || d.layout != AVIFGPU_LAYOUT_PLANAR_YCBCR || d.image_bit_depth > 12)
+        if (d.host_depth != 32 || d.image_bit_depth > 12)
         {
             return nullptr;
         }

@@ -37,6 +37,10 @@ struct EncodeParams
     int32_t topLeft;       // AVIFGPU_DOWN_FILTER_TOP_LEFT
     avifpix::ForwardMatrix matrix;
     float chromaOffset;
+    // Float hosts with a transfer curve: the flat step table + band bitmap in global memory (a by-value copy of
+    // *curveTable made by the generic launcher), or useCurveView = 0 -> every sample takes the exact powf.
+    CurveTableView curveView;
+    int32_t useCurveView;
     // Host-side extras for the launcher (ignored by the kernels):
     const CurveTableView* curveTable; // verified exact step table for `transfer`, or nullptr
     const uint16_t* gray16Lut;        // 65536-entry code table for Gray16 hosts (device memory), or nullptr

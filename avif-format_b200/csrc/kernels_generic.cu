@@ -4,6 +4,7 @@
 // BASELINE.json measures and fall back to these for everything else.  Both sets share pixel_math.cuh, so
 // they cannot disagree on arithmetic.
 #include "kernel_params.h"
+#include "curve_lookup.cuh"
 #include "../../include/avifgpu.h"
 
 #include <cuda_runtime.h>
@@ -91,6 +92,14 @@ __device__ __forceinline__ void HostPixelToCodes(const EncodeParams& p, const Ho
         {
             if (i < colors)
             {
+                // A built and verified step table (curve_tables.h) answers every finite sample from global memory: one
+                // 64-bit gather, plus one bit of the band bitmap for the ~1.5 % of samples inside a fuzzy band.
+                if (p.useCurveView && static_cast<int32_t>(__float_as_uint(color[i])) <= 0x7f7fffff)
+                {
+                    bool inBand;
+                    codes[i] = LookupCurveCodeFlatResolved(__float_as_uint(color[i]), p.curveView, inBand);
+                    continue;
+                }
                 float curved;
                 switch (p.transfer)
                 {
@@ -534,12 +543,20 @@ __global__ void __launch_bounds__(kThreads) TransferKernel(int function, float p
 
 } // namespace
 
-int LaunchEncodeGeneric(const EncodeParams& p, int hostDepth, void* streamHandle)
+int LaunchEncodeGeneric(const EncodeParams& params, int hostDepth, void* streamHandle)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
-    if (p.width <= 0 || p.rowCount <= 0)
+    if (params.width <= 0 || params.rowCount <= 0)
     {
         return 0;
+    }
+    EncodeParams p = params;
+    p.useCurveView = 0;
+    if (hostDepth == 32 && p.curveTable != nullptr && p.curveTable->flat != nullptr && p.curveTable->bandBits != nullptr &&
+        (p.transfer == AVIFGPU_TRANSFER_PQ || p.transfer == AVIFGPU_TRANSFER_SMPTE428))
+    {
+        p.curveView = *p.curveTable;
+        p.useCurveView = 1;
     }
     if (p.planar)
     {

@@ -79,6 +79,32 @@ def encode_case(name, host_depth, channels, image_depth, chroma, nclx, bytes_per
     print(json.dumps({"case": name, "ms": ms, "gpx_s": W * H / ms / 1e6, "gb_s": W * H * bytes_per_px / ms / 1e6}))
 
 
+def float_encode_case(name, channels, layout, bytes_per_px, tables):
+    alpha = abi.ALPHA_STRAIGHT if channels == 4 else abi.ALPHA_NONE
+    nclx = abi.Nclx(1, abi.PRIMARIES_BT2020, abi.TRANSFER_CHAR_PQ, abi.MATRIX_BT2020_NCL, 1)
+    desc = abi.EncodeDesc(W, H, 32, channels, alpha, 12, abi.TRANSFER_PQ, 80, layout, abi.CHROMA_420 if layout == abi.LAYOUT_PLANAR_YCBCR else abi.CHROMA_444,
+                          abi.DOWN_FILTER_BOX, abi.GRAY16_LUT, nclx)
+    ctx = avifgpu.Context(0)
+    ctx.set_table_autobuild(-1)
+    if tables:
+        ctx.prepare_encode(desc)
+    shapes = abi.encode_plane_shapes(desc)
+    sets = []
+    for _ in range(3):
+        rows = torch.rand((H, W * channels), generator=g, device=dev)
+        planes = [None if s is None else torch.empty(s, dtype=torch.int16, device=dev) for s in shapes]
+        sets.append((rows, avifgpu.planes_from_tensors(planes), planes))
+    i = [0]
+
+    def run():
+        s = sets[i[0] % 3]
+        i[0] += 1
+        ctx.encode_device(desc, s[0].data_ptr(), s[0].stride(0) * 4, s[1])
+    ms = timed(run, steps=10)
+    print(json.dumps({"case": name, "ms": ms, "gpx_s": W * H / ms / 1e6, "gb_s": W * H * bytes_per_px / ms / 1e6}))
+    ctx.close()
+
+
 n601 = abi.Nclx(1, 1, 13, abi.MATRIX_BT601, 1)
 decode_case("decode 8-bit 4:2:0 -> RGB8 (a15)", 8, 8, abi.CHROMA_420, n601, 1.5 + 3)
 decode_case("decode 8-bit 4:4:4 + alpha -> RGBA8 (a15)", 8, 8, abi.CHROMA_444, n601, 4 + 4, alpha=True)
@@ -87,3 +113,7 @@ decode_case("decode 12-bit 4:4:4 -> RGB16 (a14)", 12, 16, abi.CHROMA_444, n601, 
 encode_case("encode RGB8 -> 8-bit 4:2:0 (a3)", 8, 3, 8, abi.CHROMA_420, n601, 3 + 1.5)
 encode_case("encode RGBA8 -> 8-bit 4:4:4 + A (config 1 at 8K) (a3)", 8, 4, 8, abi.CHROMA_444, n601, 4 + 4, alpha=abi.ALPHA_STRAIGHT)
 encode_case("encode RGB8 -> 10-bit 4:2:0 (a3)", 8, 3, 10, abi.CHROMA_420, n601, 3 + 3)
+for tables in (False, True):
+    tag = "step tables" if tables else "exact powf"
+    float_encode_case(f"encode RGBA32f -> 12-bit PQ 4:2:0 + A, generic kernel, {tag} (a1)", 4, abi.LAYOUT_PLANAR_YCBCR, 16 + 5, tables)
+    float_encode_case(f"encode RGB32f -> interleaved RGB 12-bit PQ (reference layout), generic kernel, {tag} (a1)", 3, abi.LAYOUT_REFERENCE, 12 + 6, tables)

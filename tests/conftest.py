@@ -41,6 +41,16 @@ def checker():
 
 
 @pytest.fixture(scope="session")
+def gpu_exact():
+    """A context that never builds step tables: float encodes run the exact kernel (glibc-identical powf per sample)."""
+    import avifgpu
+    ctx = avifgpu.Context(0)
+    ctx.set_table_autobuild(-1)
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="session")
 def gpu():
     import avifgpu
     ctx = avifgpu.Context(0)

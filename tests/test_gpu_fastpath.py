@@ -229,13 +229,13 @@ def test_ycc_to_rgb32_fast_kernel(gpu, port, w, h, chroma):
 
 # ---- every float through the production kernel ---------------------------------------------------------------------------
 
-def test_every_float_through_the_production_encode_kernel(gpu):
+def test_every_float_through_the_production_encode_kernel(gpu, gpu_exact):
     """The step tables are verified against the exact curve by the builder's own sweep; this runs the PRODUCTION kernel
     (copy-engine staging, table look-up, band bitmap, +inf / NaN route) over an image that contains every bit pattern
     from +0 through the positive NaNs and on into the first negative values -- 2^31 + samples -- with the identity
     (GBR) matrix in 4:4:4, so the three planes ARE the per-sample codes.  The expected planes come from the generic
-    exact kernel (glibc-identical powf per sample; reached by giving it a 2-byte-aligned plane origin), which
-    test_gpu_parity.py pins to the CPU checker."""
+    exact kernel of a context that never builds tables (glibc-identical powf per sample), which test_gpu_parity.py pins
+    to the CPU checker."""
     import torch
     import avifgpu
     dev = torch.device("cuda", gpu.device)
@@ -257,10 +257,10 @@ def test_every_float_through_the_production_encode_kernel(gpu):
     gpu.encode_device(desc, rows.data_ptr(), rows.stride(0) * 4, avifgpu.planes_from_tensors(fast))
     backing = [None if s is None else torch.full((s[0], s[1] + 1), -1, dtype=torch.int16, device=dev) for s in shapes]
     exact = [None if t is None else t[:, 1:] for t in backing]  # 2-byte aligned origins: the launcher takes the generic kernel
-    before = gpu.launch_count()
-    gpu.encode_device(desc, rows.data_ptr(), rows.stride(0) * 4, avifgpu.planes_from_tensors(exact))
+    before = gpu_exact.launch_count()
+    gpu_exact.encode_device(desc, rows.data_ptr(), rows.stride(0) * 4, avifgpu.planes_from_tensors(exact))  # and no tables at all
     torch.cuda.synchronize(dev)
-    assert gpu.launch_count() - before == 1
+    assert gpu_exact.launch_count() - before == 1
     for k in range(3):
         differing = int((fast[k] != exact[k]).sum().item())
         assert differing == 0, f"plane {k}: {differing} of {fast[k].numel()} codes differ"
