@@ -25,6 +25,7 @@ int LaunchEncodeFast(const EncodeParams& params, int hostDepth, void* stream);  
 int LaunchEncodeFastInteger(const EncodeParams& params, int hostDepth, void* stream); // 0 = not applicable
 cudaError_t BuildGray16Lut(uint16_t* deviceLut, int smpte428, uint32_t maxCode, void* stream);
 long long VerifyHlgDivisions(void* stream);
+long long VerifyGreenDivision(const DecodeParams& params, void* stream);
 int LaunchDecodeFast(const DecodeParams& params, void* stream);                  // 0 = not applicable
 int LaunchDecodeFastInteger(const DecodeParams& params, void* stream);           // 0 = not applicable
 
@@ -120,6 +121,39 @@ struct avifgpu_context
             launches += 1;
         }
         return hlgDivisionState;
+    }
+
+    // YuvDecode.cpp:308 divides by the per-image constant kg; the tuned decode kernels use a 3-instruction form after
+    // it has been compared with the IEEE division for every (Cb, Cr) code pair of the configuration, on this device.
+    struct GreenDivision
+    {
+        avifpix::InverseMatrix matrix;
+        avifpix::RangeParams range;
+        uint32_t maxCode;
+        int state;
+    };
+    std::vector<GreenDivision> greenDivisions;
+    int VerifiedGreenDivision(const DecodeParams& p)
+    {
+        if (p.colorspace != AVIFGPU_COLORSPACE_YCBCR || p.bitDepth > 12)
+        {
+            return 0;
+        }
+        for (const GreenDivision& g : greenDivisions)
+        {
+            if (std::memcmp(&g.matrix, &p.matrix, sizeof(g.matrix)) == 0 && std::memcmp(&g.range, &p.range, sizeof(g.range)) == 0 && g.maxCode == p.maxCode)
+            {
+                return g.state;
+            }
+        }
+        GreenDivision g{};
+        g.matrix = p.matrix;
+        g.range = p.range;
+        g.maxCode = p.maxCode;
+        g.state = VerifyGreenDivision(p, streams[0]) == 0 ? 1 : 0;
+        launches += 1;
+        greenDivisions.push_back(g);
+        return g.state;
     }
 
     // The 65536-entry code table of a Gray16 host configuration (built on the device on first use), or nullptr.
@@ -673,6 +707,7 @@ AVIFGPU_EXPORT int avifgpu_decode_rows_device(avifgpu_context* ctx, const avifgp
     p.smCount = ctx->smCount;
     DeviceGuard deviceGuardForTables(ctx->device);
     p.verifiedHlgDivisions = (desc->host_depth == 32 && transfer == AVIFGPU_TRANSFER_HLG) ? ctx->VerifiedHlgDivisions() : 0;
+    p.verifiedGreenDivision = ctx->VerifiedGreenDivision(p);
     for (int k = 0; k < AVIFGPU_MAX_PLANES; ++k)
     {
         const PlaneGeometry g = DecodePlaneGeometry(*desc, k);
@@ -881,6 +916,7 @@ AVIFGPU_EXPORT int avifgpu_decode_rows(avifgpu_context* ctx, const avifgpu_decod
 
     DeviceGuard guard(ctx->device);
     base.verifiedHlgDivisions = (desc->host_depth == 32 && transfer == AVIFGPU_TRANSFER_HLG) ? ctx->VerifiedHlgDivisions() : 0;
+    base.verifiedGreenDivision = ctx->VerifiedGreenDivision(base);
     const int64_t rowPayload = static_cast<int64_t>(desc->width) * DecodeHostColBytes(*desc);
     const int64_t deviceRowStride = (rowPayload + 255) & ~255ll;
     const int sliceRows = SliceRows(nrows, rowPayload);

@@ -73,6 +73,7 @@ struct DecodeParams
     float hlgPeak;
     int32_t smCount;              // host-side extra for the launcher
     int32_t verifiedHlgDivisions; // 1 once the context has verified HLGToLinearUnit's fast divisions on this device
+    int32_t verifiedGreenDivision; // 1 once the context has verified the fast `/ kg` of YuvDecode.cpp:308 for this matrix, depth, range
 };
 
 // Launchers implemented in kernels_*.cu.  They only enqueue work on `stream` and return the number of kernels

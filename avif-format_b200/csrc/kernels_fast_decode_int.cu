@@ -42,6 +42,7 @@ struct IntDecodeParams
     uint32_t maxCode;
     RangeParams range;
     InverseMatrix matrix;
+    int32_t verifiedGreenDivision;
 };
 
 // 8 consecutive samples of a plane as 32-bit codes.
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) DecodeYccToRgbIntKerne
     const float bGain = (2 * (1 - kb));
     const float gCr = kr * (1 - kr);
     const float gCb = kb * (1 - kb);
+    const float kgReciprocal = 1.0f / kg;
     const float outScale = kHost8 ? 255.0f : 32768.0f;
 
     const int lane = threadIdx.x & 31;
@@ -184,7 +186,8 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) DecodeYccToRgbIntKerne
             const float Cr = tableUV[kHost8 ? crCode[s] : min(crCode[s], p.maxCode)];
             rOffset[s] = rGain * Cr;
             bOffset[s] = bGain * Cb;
-            gOffset[s] = ((2 * ((gCr * Cr) + (gCb * Cb))) / kg);
+            const float greenNumerator = 2 * ((gCr * Cr) + (gCb * Cb));
+            gOffset[s] = p.verifiedGreenDivision ? DivideByConstant(greenNumerator, kg, kgReciprocal) : greenNumerator / kg;
         }
 
         // ---- pixels ---------------------------------------------------------------------------------------------------
@@ -353,6 +356,7 @@ int LaunchDecodeFastInteger(const DecodeParams& p, void* streamHandle)
     fp.maxCode = p.maxCode;
     fp.range = p.range;
     fp.matrix = p.matrix;
+    fp.verifiedGreenDivision = p.verifiedGreenDivision;
 
     const int smCount = p.smCount > 0 ? p.smCount : 148;
     cudaError_t e;
