@@ -45,55 +45,69 @@ struct IntDecodeParams
     int32_t verifiedGreenDivision;
 };
 
-// 8 consecutive samples of a plane as 32-bit codes.
+// Eight (four) consecutive samples of a plane as they sit in memory, and their expansion into 32-bit codes.
 template <typename SampleT>
-__device__ __forceinline__ void LoadEight(const uint8_t* address, uint32_t (&codes)[8])
+struct Raw8
 {
+    uint32_t w[sizeof(SampleT) == 1 ? 2 : 4];
+};
+
+template <typename SampleT>
+__device__ __forceinline__ Raw8<SampleT> LoadEight(const uint8_t* address)
+{
+    Raw8<SampleT> raw;
     if (sizeof(SampleT) == 1)
     {
-        const uint2 w = __ldg(reinterpret_cast<const uint2*>(address));
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-        {
-            codes[i] = (w.x >> (8 * i)) & 0xffu;
-            codes[4 + i] = (w.y >> (8 * i)) & 0xffu;
-        }
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(address));
+        raw.w[0] = v.x;
+        raw.w[1] = v.y;
     }
     else
     {
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(address));
-        const uint32_t words[4] = { w.x, w.y, w.z, w.w };
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-        {
-            codes[2 * i] = words[i] & 0xffffu;
-            codes[2 * i + 1] = words[i] >> 16;
-        }
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(address));
+        raw.w[0] = v.x;
+        raw.w[1] = v.y;
+        raw.w[sizeof(SampleT) == 1 ? 0 : 2] = v.z;
+        raw.w[sizeof(SampleT) == 1 ? 1 : 3] = v.w;
     }
+    return raw;
 }
 
-// 4 consecutive samples (horizontally sub-sampled chroma under 8 luma samples).
+// The four samples of the sub-sampled chroma under eight luma samples land in the first half of a Raw8.
 template <typename SampleT>
-__device__ __forceinline__ void LoadFour(const uint8_t* address, uint32_t (&codes)[8])
+__device__ __forceinline__ Raw8<SampleT> LoadFour(const uint8_t* address)
 {
+    Raw8<SampleT> raw = {};
     if (sizeof(SampleT) == 1)
     {
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(address));
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-        {
-            codes[i] = (w >> (8 * i)) & 0xffu;
-        }
+        raw.w[0] = __ldg(reinterpret_cast<const uint32_t*>(address));
     }
     else
     {
-        const uint2 w = __ldg(reinterpret_cast<const uint2*>(address));
-        codes[0] = w.x & 0xffffu;
-        codes[1] = w.x >> 16;
-        codes[2] = w.y & 0xffffu;
-        codes[3] = w.y >> 16;
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(address));
+        raw.w[0] = v.x;
+        raw.w[1] = v.y;
     }
+    return raw;
 }
+
+template <typename SampleT>
+__device__ __forceinline__ uint32_t Sample(const Raw8<SampleT>& raw, int i)
+{
+    if (sizeof(SampleT) == 1)
+    {
+        return (raw.w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+    }
+    return (i & 1) ? (raw.w[i >> 1] >> 16) : (raw.w[i >> 1] & 0xffffu);
+}
+
+constexpr float kTwo23 = 8388608.0f;
+
+// 2^23 + (uint)(0.5f + (c * scale)) as a float, for c in [0, 1]: YuvDecode.cpp:314-316 / 437-439 without the conversion
+// instruction (it issues on the quarter-rate pipe).  The sum 0.5f + c * scale is formed exactly as the reference forms
+// it (two roundings to nearest); adding 2^23 with round-toward-zero then leaves its integer part in the low mantissa
+// bits, which is the truncation of the cast.
+__device__ __forceinline__ uint32_t QuantiseBiased(float c, float scale) { return __float_as_uint(__fadd_rz(0.5f + (c * scale), kTwo23)); }
 
 template <typename SampleT, int XS, int YS, int ALPHA>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSm) DecodeYccToRgbIntKernel(const IntDecodeParams p)
@@ -134,60 +148,112 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) DecodeYccToRgbIntKerne
     const int unitRows = (p.rowCount + kRows - 1) / kRows;
     const long long unitCount = static_cast<long long>(unitsX) * unitRows;
     const int warpCount = static_cast<int>(gridDim.x) * kWarps;
+    // unit coordinates advance incrementally (no division per unit)
+    const long long firstUnit = static_cast<long long>(blockIdx.x) * kWarps + warpInBlock;
+    const int stepRows = warpCount / unitsX;
+    const int stepX = warpCount - stepRows * unitsX;
+    int unitRow = static_cast<int>(firstUnit / unitsX);
+    int unitX = static_cast<int>(firstUnit - static_cast<long long>(unitRow) * unitsX);
 
-#pragma unroll 1
-    for (long long unit = static_cast<long long>(blockIdx.x) * kWarps + warpInBlock; unit < unitCount; unit += warpCount)
+    // Software pipeline: the loads of unit i+1 are issued once unit i's samples have been expanded, so they are in flight
+    // during its arithmetic and stores.
+    Raw8<SampleT> rawY[kRows], rawA[kRows], rawCb, rawCr;
+    auto loadUnit = [&](int row, int column, bool valid)
     {
-        const int unitRow = static_cast<int>(unit / unitsX);
-        const int x0 = static_cast<int>(unit - static_cast<long long>(unitRow) * unitsX) * kUnitPixels + lane * 8;
-        const int y0 = unitRow * kRows;
-        if (x0 >= p.width)
+        const int x = column * kUnitPixels + lane * 8;
+        const int y = row * kRows;
+        if (!valid || x >= p.width)
         {
-            continue;
+            return;
         }
-        const bool secondRow = kRows == 2 && (y0 + 1) < p.rowCount;
-
-        // ---- chroma sites ---------------------------------------------------------------------------------------------
-        uint32_t cbCode[8], crCode[8];
+        const int64_t chromaRow = YS ? row : y;
+        const int64_t chromaColumn = static_cast<int64_t>(XS ? (x >> 1) : x) * sizeof(SampleT);
+        if (XS)
         {
-            const int64_t chromaRow = YS ? unitRow : y0;
-            const int64_t chromaColumn = static_cast<int64_t>(XS ? (x0 >> 1) : x0) * sizeof(SampleT);
-            if (XS)
-            {
-                LoadFour<SampleT>(p.plane[1] + chromaRow * p.planeStride[1] + chromaColumn, cbCode);
-                LoadFour<SampleT>(p.plane[2] + chromaRow * p.planeStride[2] + chromaColumn, crCode);
-            }
-            else
-            {
-                LoadEight<SampleT>(p.plane[1] + chromaRow * p.planeStride[1] + chromaColumn, cbCode);
-                LoadEight<SampleT>(p.plane[2] + chromaRow * p.planeStride[2] + chromaColumn, crCode);
-            }
+            rawCb = LoadFour<SampleT>(p.plane[1] + chromaRow * p.planeStride[1] + chromaColumn);
+            rawCr = LoadFour<SampleT>(p.plane[2] + chromaRow * p.planeStride[2] + chromaColumn);
         }
-        uint32_t yCode[kRows][8];
-        uint32_t aCode[kRows][8];
+        else
+        {
+            rawCb = LoadEight<SampleT>(p.plane[1] + chromaRow * p.planeStride[1] + chromaColumn);
+            rawCr = LoadEight<SampleT>(p.plane[2] + chromaRow * p.planeStride[2] + chromaColumn);
+        }
 #pragma unroll
         for (int r = 0; r < kRows; ++r)
         {
-            if (r == 1 && !secondRow)
+            if (y + r < p.rowCount)
             {
-                break;
+                rawY[r] = LoadEight<SampleT>(p.plane[0] + static_cast<int64_t>(y + r) * p.planeStride[0] + static_cast<int64_t>(x) * sizeof(SampleT));
+                if (ALPHA)
+                {
+                    rawA[r] = LoadEight<SampleT>(p.plane[3] + static_cast<int64_t>(y + r) * p.planeStride[3] + static_cast<int64_t>(x) * sizeof(SampleT));
+                }
             }
-            LoadEight<SampleT>(p.plane[0] + static_cast<int64_t>(y0 + r) * p.planeStride[0] + static_cast<int64_t>(x0) * sizeof(SampleT), yCode[r]);
-            if (ALPHA)
+        }
+    };
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+    {
+        rawY[r] = {};
+        rawA[r] = {};
+    }
+    rawCb = {};
+    rawCr = {};
+    loadUnit(unitRow, unitX, firstUnit < unitCount);
+
+#pragma unroll 1
+    for (long long unit = firstUnit; unit < unitCount; unit += warpCount)
+    {
+        const int x0 = unitX * kUnitPixels + lane * 8;
+        const int y0 = unitRow * kRows;
+        const bool laneActive = x0 < p.width;
+        const bool secondRow = kRows == 2 && (y0 + 1) < p.rowCount;
+        int nextRow = unitRow + stepRows;
+        int nextX = unitX + stepX;
+        if (nextX >= unitsX)
+        {
+            nextX -= unitsX;
+            ++nextRow;
+        }
+
+        // ---- samples -> floats through the shared-memory tables; chroma terms once per site -----------------------------
+        float Yf[kRows][8];
+        uint32_t alphaOut[kRows][8];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+        {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
             {
-                LoadEight<SampleT>(p.plane[3] + static_cast<int64_t>(y0 + r) * p.planeStride[3] + static_cast<int64_t>(x0) * sizeof(SampleT), aCode[r]);
+                const uint32_t code = Sample<SampleT>(rawY[r], i);
+                Yf[r][i] = tableY[kHost8 ? code : min(code, p.maxCode)];
+                if (ALPHA)
+                {
+                    const uint32_t a = Sample<SampleT>(rawA[r], i);
+                    alphaOut[r][i] = kHost8 ? a : tableAlpha[min(a, p.maxCode)];
+                }
             }
         }
         float rOffset[kSites], bOffset[kSites], gOffset[kSites];
 #pragma unroll
         for (int s = 0; s < kSites; ++s)
         {
-            const float Cb = tableUV[kHost8 ? cbCode[s] : min(cbCode[s], p.maxCode)];
-            const float Cr = tableUV[kHost8 ? crCode[s] : min(crCode[s], p.maxCode)];
+            const uint32_t cbCode = Sample<SampleT>(rawCb, s);
+            const uint32_t crCode = Sample<SampleT>(rawCr, s);
+            const float Cb = tableUV[kHost8 ? cbCode : min(cbCode, p.maxCode)];
+            const float Cr = tableUV[kHost8 ? crCode : min(crCode, p.maxCode)];
             rOffset[s] = rGain * Cr;
             bOffset[s] = bGain * Cb;
             const float greenNumerator = 2 * ((gCr * Cr) + (gCb * Cb));
             gOffset[s] = p.verifiedGreenDivision ? DivideByConstant(greenNumerator, kg, kgReciprocal) : greenNumerator / kg;
+        }
+
+        loadUnit(nextRow, nextX, unit + warpCount < unitCount);
+        unitRow = nextRow;
+        unitX = nextX;
+        if (!laneActive)
+        {
+            continue;
         }
 
         // ---- pixels ---------------------------------------------------------------------------------------------------
@@ -198,41 +264,40 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) DecodeYccToRgbIntKerne
             {
                 break;
             }
-            uint32_t out[8][kChannels];
+            uint32_t out[8][kChannels]; // colour channels: 2^23-biased float bit patterns (the code is in the low bits)
 #pragma unroll
             for (int i = 0; i < 8; ++i)
             {
                 const int s = XS ? (i >> 1) : i;
-                const float Y = tableY[kHost8 ? yCode[r][i] : min(yCode[r][i], p.maxCode)];
                 // std::clamp(v, 0, 1) as the add's saturation modifier: the table entries are finite and Y >= +0, so the
                 // sums are never NaN or -0.0 and the two agree for every input.
-                const float R = __saturatef(Y + rOffset[s]);
-                const float B = __saturatef(Y + bOffset[s]);
-                const float G = __saturatef(Y - gOffset[s]);
-                out[i][0] = __float2uint_rz(0.5f + (R * outScale)); // YuvDecode.cpp:314-316 / 437-439
-                out[i][1] = __float2uint_rz(0.5f + (G * outScale));
-                out[i][2] = __float2uint_rz(0.5f + (B * outScale));
+                const float R = __saturatef(Yf[r][i] + rOffset[s]);
+                const float B = __saturatef(Yf[r][i] + bOffset[s]);
+                const float G = __saturatef(Yf[r][i] - gOffset[s]);
+                out[i][0] = QuantiseBiased(R, outScale);
+                out[i][1] = QuantiseBiased(G, outScale);
+                out[i][2] = QuantiseBiased(B, outScale);
                 if (ALPHA)
                 {
-                    out[i][3] = kHost8 ? aCode[r][i] : tableAlpha[min(aCode[r][i], p.maxCode)];
+                    out[i][3] = alphaOut[r][i];
                 }
             }
             uint8_t* target = p.rows + static_cast<int64_t>(y0 + r) * p.rowStride + static_cast<int64_t>(x0) * (kChannels * sizeof(SampleT));
             if (kHost8)
             {
-                // 8 pixels x kChannels bytes
+                // 8 pixels x kChannels bytes: byte 0 of every value, four to a word
                 uint32_t words[2 * kChannels];
 #pragma unroll
                 for (int w = 0; w < 2 * kChannels; ++w)
                 {
-                    uint32_t word = 0;
+                    uint32_t v[4];
 #pragma unroll
                     for (int b = 0; b < 4; ++b)
                     {
                         const int byteIndex = 4 * w + b;
-                        word |= out[byteIndex / kChannels][byteIndex % kChannels] << (8 * b);
+                        v[b] = out[byteIndex / kChannels][byteIndex % kChannels];
                     }
-                    words[w] = word;
+                    words[w] = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
                 }
                 if (ALPHA)
                 {
@@ -250,13 +315,13 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) DecodeYccToRgbIntKerne
             }
             else
             {
-                // 8 pixels x kChannels 16-bit samples
+                // 8 pixels x kChannels 16-bit samples: the low half of every value, two to a word
                 uint32_t words[4 * kChannels];
 #pragma unroll
                 for (int w = 0; w < 4 * kChannels; ++w)
                 {
                     const int first = 2 * w;
-                    words[w] = out[first / kChannels][first % kChannels] | (out[(first + 1) / kChannels][(first + 1) % kChannels] << 16);
+                    words[w] = __byte_perm(out[first / kChannels][first % kChannels], out[(first + 1) / kChannels][(first + 1) % kChannels], 0x5410);
                 }
 #pragma unroll
                 for (int q = 0; q < kChannels; ++q)
