@@ -9,11 +9,39 @@
 
 #include <stdint.h>
 
+#include <atomic>
+
 #include "curve_tables.h"
 #include "pixel_math.cuh"
 
 namespace avifgpu
 {
+
+#if defined(__CUDACC__)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting; `configuredDevices` (one static per kernel
+// instantiation) remembers the devices it has been made on, so a process that drives several GPUs configures each.
+template <typename Kernel>
+inline cudaError_t AllowDynamicShared(Kernel kernel, int bytes, std::atomic<uint64_t>& configuredDevices)
+{
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess)
+    {
+        return e;
+    }
+    const uint64_t bit = 1ull << (device & 63);
+    if (configuredDevices.load(std::memory_order_acquire) & bit)
+    {
+        return cudaSuccess;
+    }
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess)
+    {
+        configuredDevices.fetch_or(bit, std::memory_order_release);
+    }
+    return e;
+}
+#endif
 
 struct EncodeParams
 {

@@ -254,16 +254,13 @@ cudaError_t LaunchFastEncodeKernel(const FastEncodeParams& fp, int smCount, cuda
 {
     using Config = FastConfig;
     const size_t shared = FastEncodeSharedBytes<CURVE, XS, YS>(fp);
-    static bool configured = false; // per instantiation
-    if (!configured)
+    static std::atomic<uint64_t> configuredDevices{ 0 }; // per instantiation
     {
-        const cudaError_t e = cudaFuncSetAttribute(EncodeRgbF32PlanarKernel<CURVE, XS, YS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   Config::sharedLimit);
+        const cudaError_t e = AllowDynamicShared(EncodeRgbF32PlanarKernel<CURVE, XS, YS>, Config::sharedLimit, configuredDevices);
         if (e != cudaSuccess)
         {
             return e;
         }
-        configured = true;
     }
     if (shared > static_cast<size_t>(Config::sharedLimit))
     {

@@ -338,15 +338,13 @@ cudaError_t LaunchOne(const IntDecodeParams& fp, int smCount, cudaStream_t strea
 {
     const size_t entries = static_cast<size_t>(1) << fp.bitDepth;
     const size_t shared = 2 * sizeof(float) * entries + ((ALPHA && sizeof(SampleT) == 2) ? sizeof(uint16_t) * entries : 0);
-    static bool configured = false;
-    if (!configured)
+    static std::atomic<uint64_t> configuredDevices{ 0 }; // per instantiation
     {
-        const cudaError_t e = cudaFuncSetAttribute(DecodeYccToRgbIntKernel<SampleT, XS, YS, ALPHA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        const cudaError_t e = AllowDynamicShared(DecodeYccToRgbIntKernel<SampleT, XS, YS, ALPHA>, 64 * 1024, configuredDevices);
         if (e != cudaSuccess)
         {
             return e;
         }
-        configured = true;
     }
     constexpr int rowsPerUnit = YS ? 2 : 1;
     const long long units = static_cast<long long>((fp.width + kUnitPixels - 1) / kUnitPixels) * ((fp.rowCount + rowsPerUnit - 1) / rowsPerUnit);

@@ -299,15 +299,13 @@ template <int CURVE, int XS, int YS>
 cudaError_t LaunchFlatKernel(const FastEncodeParams& fp, int smCount, cudaStream_t stream)
 {
     const size_t shared = static_cast<size_t>(FlatFixedBytes()) + static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
-    static bool configured = false; // per instantiation
-    if (!configured)
+    static std::atomic<uint64_t> configuredDevices{ 0 }; // per instantiation
     {
-        const cudaError_t e = cudaFuncSetAttribute(EncodeRgbF32FlatKernel<CURVE, XS, YS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSharedLimit);
+        const cudaError_t e = AllowDynamicShared(EncodeRgbF32FlatKernel<CURVE, XS, YS>, kSharedLimit, configuredDevices);
         if (e != cudaSuccess)
         {
             return e;
         }
-        configured = true;
     }
     const long long tiles = static_cast<long long>((fp.width + kTilePixels - 1) / kTilePixels) * ((fp.rowCount + 1) / 2);
     if (tiles > 0x7fffffffll || shared > static_cast<size_t>(kSharedLimit))

@@ -403,14 +403,10 @@ int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHa
         {
             return 0;
         }
-        static bool configured = false;
-        if (!configured)
+        static std::atomic<uint64_t> configuredDevices{ 0 };
+        if (AllowDynamicShared(EncodeGray16LutKernel, kLutEntries * 2, configuredDevices) != cudaSuccess)
         {
-            if (cudaFuncSetAttribute(EncodeGray16LutKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutEntries * 2) != cudaSuccess)
-            {
-                return AVIFGPU_ERR_CUDA;
-            }
-            configured = true;
+            return AVIFGPU_ERR_CUDA;
         }
         Gray16Params gp{};
         gp.rows = static_cast<const uint8_t*>(p.rows);

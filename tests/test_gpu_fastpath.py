@@ -372,3 +372,24 @@ def test_step_tables_are_built_when_they_pay_off(port):
         assert ctx.launch_count() == 3
         assert ctx.prepare_encode(desc).as_dict()["valid"] == 1  # explicit request still builds
         assert cases.same_planes(expected, ctx.encode(desc, rows))
+
+
+def test_two_devices_in_one_process(port):
+    """The C ABI lets one process drive several GPUs (avifgpu_create(device)); per-device kernel attributes and tables
+    must follow.  Needs two visible GPUs."""
+    import torch
+    import avifgpu
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w, h = 512, 32
+    desc = planar_desc(w, h)
+    rows = cases.float_host_rows(np.random.default_rng(5), h, w, 3)
+    expected = port.encode(desc, rows)
+    ddesc = abi.DecodeDesc(w, h, abi.COLORSPACE_YCBCR, abi.CHROMA_420, 10, abi.ALPHA_NONE, 32, cases.NCLX_2020_HLG())
+    planes = cases.code_planes(np.random.default_rng(6), ddesc)
+    decoded = port.decode(ddesc, planes)
+    for device in (1, 0, 1):
+        with avifgpu.Context(device) as ctx:
+            ctx.set_table_autobuild(0)
+            assert cases.same_planes(expected, ctx.encode(desc, rows))
+            assert cases.same_bits(decoded, ctx.decode(ddesc, planes))
