@@ -28,6 +28,7 @@ long long VerifyHlgDivisions(void* stream);
 long long VerifyGreenDivision(const DecodeParams& params, void* stream);
 int LaunchDecodeFast(const DecodeParams& params, void* stream);                  // 0 = not applicable
 int LaunchDecodeFastInteger(const DecodeParams& params, void* stream);           // 0 = not applicable
+int LaunchHlgOotf(int inverse, const float luma[3], float displayGamma, float peak, const float* in, float* out, size_t pixels, void* stream);
 
 int LaunchEncode(const EncodeParams& params, int hostDepth, void* stream)
 {
@@ -1120,6 +1121,44 @@ AVIFGPU_EXPORT int avifgpu_transfer_f32(avifgpu_context* ctx, int32_t function, 
     }
     ctx->launches += launched;
     if ((status = ctx->Cuda(cudaMemcpyAsync(out, ctx->transferScratch[1].ptr, bytes, cudaMemcpyDeviceToHost, stream), "D2H")) != AVIFGPU_OK) return status;
+    return ctx->Cuda(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+}
+
+AVIFGPU_EXPORT int avifgpu_hlg_ootf_f32(avifgpu_context* ctx, int32_t inverse, int32_t color_primaries, float display_gamma,
+                                        float nominal_peak_nits, const float* rgb_in, float* rgb_out, size_t pixels)
+{
+    if (ctx == nullptr)
+    {
+        return AVIFGPU_ERR_BAD_PARAM;
+    }
+    float luma[3];
+    if (!GetHlgLumaCoefficients(color_primaries, luma))
+    {
+        return ctx->Fail(AVIFGPU_ERR_UNSUPPORTED, "no HLG luma coefficients for these colour primaries");
+    }
+    if (pixels == 0)
+    {
+        return AVIFGPU_OK;
+    }
+    if (rgb_in == nullptr || rgb_out == nullptr)
+    {
+        return ctx->Fail(AVIFGPU_ERR_BAD_PARAM, "NULL buffer");
+    }
+    DeviceGuard guard(ctx->device);
+    int status;
+    const size_t bytes = pixels * 3 * sizeof(float);
+    if ((status = ctx->EnsureDevice(ctx->transferScratch[0], bytes)) != AVIFGPU_OK) return status;
+    if ((status = ctx->EnsureDevice(ctx->transferScratch[1], bytes)) != AVIFGPU_OK) return status;
+    cudaStream_t stream = ctx->streams[0];
+    if ((status = ctx->Cuda(cudaMemcpyAsync(ctx->transferScratch[0].ptr, rgb_in, bytes, cudaMemcpyHostToDevice, stream), "H2D")) != AVIFGPU_OK) return status;
+    const int launched = LaunchHlgOotf(inverse != 0, luma, display_gamma, nominal_peak_nits, static_cast<const float*>(ctx->transferScratch[0].ptr),
+                                       static_cast<float*>(ctx->transferScratch[1].ptr), pixels, stream);
+    if (launched < 0)
+    {
+        return ctx->Cuda(cudaGetLastError(), "OOTF kernel launch");
+    }
+    ctx->launches += launched;
+    if ((status = ctx->Cuda(cudaMemcpyAsync(rgb_out, ctx->transferScratch[1].ptr, bytes, cudaMemcpyDeviceToHost, stream), "D2H")) != AVIFGPU_OK) return status;
     return ctx->Cuda(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
 }
 

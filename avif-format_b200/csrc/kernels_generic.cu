@@ -616,4 +616,47 @@ int LaunchTransfer(int function, float param, const float* in, float* out, size_
     return cudaGetLastError() == cudaSuccess ? 1 : AVIFGPU_ERR_CUDA;
 }
 
+namespace
+{
+// ColorTransfer.cpp:192-220 over `pixels` RGB triples.
+__global__ void __launch_bounds__(kThreads) HlgOotfKernel(int inverse, float lumaR, float lumaG, float lumaB, float displayGamma, float peak,
+                                                          const float* __restrict__ in, float* __restrict__ out, size_t pixels)
+{
+    __shared__ uint64_t libmStorage[96];
+    const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
+    __syncthreads();
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < pixels; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    {
+        float r = in[3 * i], g = in[3 * i + 1], b = in[3 * i + 2];
+        if (inverse)
+        {
+            ApplyInverseHLGOOTF(r, g, b, lumaR, lumaG, lumaB, displayGamma, peak, t);
+        }
+        else
+        {
+            ApplyHLGOOTF(r, g, b, lumaR, lumaG, lumaB, displayGamma - 1.0f, peak, t);
+        }
+        out[3 * i] = r;
+        out[3 * i + 1] = g;
+        out[3 * i + 2] = b;
+    }
+}
+} // namespace
+
+int LaunchHlgOotf(int inverse, const float luma[3], float displayGamma, float peak, const float* in, float* out, size_t pixels, void* streamHandle)
+{
+    if (pixels == 0)
+    {
+        return 0;
+    }
+    size_t blocks = (pixels + kThreads - 1) / kThreads;
+    if (blocks > 148 * 16)
+    {
+        blocks = 148 * 16;
+    }
+    HlgOotfKernel<<<static_cast<unsigned>(blocks), kThreads, 0, static_cast<cudaStream_t>(streamHandle)>>>(inverse, luma[0], luma[1], luma[2], displayGamma, peak, in,
+                                                                                                      out, pixels);
+    return cudaGetLastError() == cudaSuccess ? 1 : AVIFGPU_ERR_CUDA;
+}
+
 } // namespace avifgpu

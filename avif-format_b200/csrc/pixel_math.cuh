@@ -173,6 +173,18 @@ AVIF_HD void ApplyHLGOOTF(float& r, float& g, float& b, float lumaR, float lumaG
     b *= factor;
 }
 
+// ColorTransfer.cpp:207-220 (the reference never calls it; kept at parity as a primitive, and the seam an HLG save path
+// would use).
+AVIF_HD void ApplyInverseHLGOOTF(float& r, float& g, float& b, float lumaR, float lumaG, float lumaB, float displayGamma,
+                                 float nominalPeakBrightness, const LibmTables& t)
+{
+    const float luma = (r * lumaR) + (g * lumaG) + (b * lumaB);
+    const float factor = avifmath::Powf(luma / nominalPeakBrightness, (displayGamma - 1.0f) / displayGamma, t) / nominalPeakBrightness;
+    r *= factor;
+    g *= factor;
+    b *= factor;
+}
+
 // ---- alpha: PremultipliedAlpha.cpp ------------------------------------------------------------------------
 
 // PremultipliedAlpha.cpp:49-52

@@ -71,6 +71,7 @@ def library():
     sig("avifgpu_transfer_f32", C.c_int, [ctx_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t])
     sig("avifgpu_prepare_encode", C.c_int, [ctx_p, C.POINTER(abi.EncodeDesc), C.POINTER(abi.CurveStats)])
     sig("avifgpu_set_table_autobuild", C.c_int, [ctx_p, C.c_int64])
+    sig("avifgpu_hlg_ootf_f32", C.c_int, [ctx_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t])
     _lib = lib
     return lib
 
@@ -82,6 +83,7 @@ EXPORTED_SYMBOLS = [
     "avifgpu_decode_plane_geometry", "avifgpu_get_yuv_coefficients", "avifgpu_get_hlg_luma_coefficients",
     "avifgpu_build_yuv_tables", "avifgpu_encode_rows", "avifgpu_decode_rows", "avifgpu_encode_rows_device",
     "avifgpu_decode_rows_device", "avifgpu_transfer_f32", "avifgpu_prepare_encode", "avifgpu_set_table_autobuild",
+    "avifgpu_hlg_ootf_f32",
 ]
 
 
@@ -212,6 +214,13 @@ class Context:
         return out
 
     # ---- device-pointer entry points (raw pointers; torch tensors via .data_ptr()) -------------------------------
+    def hlg_ootf(self, rgb, primaries, gamma, peak, inverse=False):
+        """ApplyHLGOOTF / ApplyInverseHLGOOTF over an array of RGB float triples."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        out = np.empty_like(rgb)
+        self._check(self.lib.avifgpu_hlg_ootf_f32(self.handle, int(inverse), primaries, gamma, peak, rgb.ctypes.data, out.ctypes.data, rgb.size // 3))
+        return out
+
     def encode_device(self, desc, rows_ptr, row_stride, planes_struct, y0=0, nrows=None, stream=0):
         nrows = desc.height - y0 if nrows is None else nrows
         self._check(self.lib.avifgpu_encode_rows_device(self.handle, C.byref(desc), rows_ptr, row_stride, y0, nrows,

@@ -322,6 +322,12 @@ typedef enum avifgpu_function
 AVIFGPU_EXPORT int avifgpu_transfer_f32(avifgpu_context* ctx, int32_t function, float param,
                                         const float* in, float* out, size_t n);
 
+/* ApplyHLGOOTF (ColorTransfer.cpp:192-205; inverse = 0) or ApplyInverseHLGOOTF (ColorTransfer.cpp:207-220; inverse = 1)
+ * over `pixels` interleaved RGB float triples, luma coefficients from GetHLGLumaCoefficients(color_primaries)
+ * (ColorTransfer.cpp:31-45).  rgb_in / rgb_out are HOST pointers (may alias). */
+AVIFGPU_EXPORT int avifgpu_hlg_ootf_f32(avifgpu_context* ctx, int32_t inverse, int32_t color_primaries, float display_gamma,
+                                        float nominal_peak_nits, const float* rgb_in, float* rgb_out, size_t pixels);
+
 #ifdef __cplusplus
 }
 #endif

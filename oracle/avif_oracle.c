@@ -156,6 +156,16 @@ static void apply_hlg_ootf(float* rgb, const float luma_coefficients[3], float d
     rgb[2] *= factor;
 }
 
+/* ColorTransfer.cpp:207-220 (no caller in the reference; kept at parity as a primitive) */
+static void apply_inverse_hlg_ootf(float* rgb, const float luma_coefficients[3], float display_gamma, float peak)
+{
+    const float luma = (rgb[0] * luma_coefficients[0]) + (rgb[1] * luma_coefficients[1]) + (rgb[2] * luma_coefficients[2]);
+    const float factor = powf(luma / peak, (display_gamma - 1.0f) / display_gamma) / peak;
+    rgb[0] *= factor;
+    rgb[1] *= factor;
+    rgb[2] *= factor;
+}
+
 /* ColorTransfer.cpp:31-45 */
 int avif_oracle_get_hlg_luma_coefficients(int32_t primaries, float* out)
 {
@@ -207,6 +217,22 @@ int avif_oracle_hlg_ootf(float* rgb, size_t pixels, int32_t primaries, float dis
     for (i = 0; i < pixels; ++i)
     {
         apply_hlg_ootf(rgb + 3 * i, luma, display_gamma, peak);
+    }
+    return AVIFGPU_OK;
+}
+
+int avif_oracle_hlg_inverse_ootf(float* rgb, size_t pixels, int32_t primaries, float display_gamma, float peak)
+{
+    float luma[3];
+    size_t i;
+    const int status = avif_oracle_get_hlg_luma_coefficients(primaries, luma);
+    if (status != AVIFGPU_OK)
+    {
+        return status;
+    }
+    for (i = 0; i < pixels; ++i)
+    {
+        apply_inverse_hlg_ootf(rgb + 3 * i, luma, display_gamma, peak);
     }
     return AVIFGPU_OK;
 }

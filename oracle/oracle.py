@@ -54,6 +54,7 @@ class CpuChecker:
         f("libm_version", C.c_char_p, [])
         f("transfer_f32", C.c_int, [C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t])
         f("hlg_ootf", C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_float, C.c_float])
+        f("hlg_inverse_ootf", C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_float, C.c_float])
         f("premultiply_u8", C.c_uint8, [C.c_uint8, C.c_uint8])
         f("premultiply_u16", C.c_uint16, [C.c_uint16, C.c_uint16, C.c_uint16])
         f("premultiply_f32", C.c_float, [C.c_float, C.c_float, C.c_float])
@@ -96,6 +97,11 @@ class CpuChecker:
     def hlg_ootf(self, rgb, primaries, gamma, peak):
         rgb = np.ascontiguousarray(rgb, dtype=np.float32).copy()
         self._check(self._hlg_ootf(rgb.ctypes.data, rgb.size // 3, primaries, gamma, peak))
+        return rgb
+
+    def hlg_inverse_ootf(self, rgb, primaries, gamma, peak):
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32).copy()
+        self._check(self._hlg_inverse_ootf(rgb.ctypes.data, rgb.size // 3, primaries, gamma, peak))
         return rgb
 
     def premultiply_table(self, max_value, unpremultiply=False):

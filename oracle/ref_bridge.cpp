@@ -473,6 +473,18 @@ AVIFREF_EXPORT int avifref_hlg_ootf(float* rgb, size_t pixels, int32_t colorPrim
     });
 }
 
+AVIFREF_EXPORT int avifref_hlg_inverse_ootf(float* rgb, size_t pixels, int32_t colorPrimaries, float displayGamma, float peakNits)
+{
+    return Guarded([&]
+    {
+        const HLGLumaCoefficiants luma = GetHLGLumaCoefficients(static_cast<heif_color_primaries>(colorPrimaries));
+        for (size_t i = 0; i < pixels; ++i)
+        {
+            ApplyInverseHLGOOTF(rgb + 3 * i, luma, displayGamma, peakNits);
+        }
+    });
+}
+
 AVIFREF_EXPORT uint8_t avifref_premultiply_u8(uint8_t color, uint8_t alpha) { return PremultiplyColor(color, alpha); }
 AVIFREF_EXPORT uint16_t avifref_premultiply_u16(uint16_t color, uint16_t alpha, uint16_t maxValue) { return PremultiplyColor(color, alpha, maxValue); }
 AVIFREF_EXPORT float avifref_premultiply_f32(float color, float alpha, float maxValue) { return PremultiplyColor(color, alpha, maxValue); }

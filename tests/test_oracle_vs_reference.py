@@ -59,6 +59,17 @@ def test_transfer_functions_match(ref, port, function, param, lo, hi):
     assert cases.same_bits(ref.transfer(function, x, param), port.transfer(function, x, param))
 
 
+@pytest.mark.parametrize("primaries", [abi.PRIMARIES_BT709, abi.PRIMARIES_BT2020])
+def test_hlg_ootfs_match(ref, port, primaries):
+    """ApplyHLGOOTF and the (uncalled) ApplyInverseHLGOOTF, ColorTransfer.cpp:192-220."""
+    rng = np.random.default_rng(primaries)
+    rgb = np.concatenate([rng.uniform(0.0, 1.0, (20000, 3)), np.exp(rng.uniform(np.log(1e-9), np.log(1000.0), (20000, 3))),
+                          [[0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [np.inf, 0.1, 0.2], [np.nan, 0.3, 0.3], [-0.1, 0.2, 0.3]]]).astype(np.float32)
+    for gamma, peak in ((1.2, 1000.0), (1.0, 400.0), (1.5, 4000.0)):
+        assert cases.same_bits(ref.hlg_ootf(rgb, primaries, gamma, peak), port.hlg_ootf(rgb, primaries, gamma, peak))
+        assert cases.same_bits(ref.hlg_inverse_ootf(rgb, primaries, gamma, peak), port.hlg_inverse_ootf(rgb, primaries, gamma, peak))
+
+
 def test_premultiply_tables_exhaustive(ref, port):
     for max_value in (255, 1023):
         for un in (False, True):
