@@ -212,6 +212,10 @@ struct avifgpu_context
         {
             curve = kCurveLinearToSMPTE428;
         }
+        else if (d.transfer == AVIFGPU_TRANSFER_HLG)
+        {
+            curve = kCurveLinearToHLG;
+        }
         else
         {
             return nullptr;

@@ -18,9 +18,13 @@ __device__ __forceinline__ uint32_t ExactCurveCode(float x, float pqMultiplier, 
     {
         curved = avifpix::LinearToPQ(x, pqMultiplier, t);
     }
-    else
+    else if (CURVE == kCurveLinearToSMPTE428)
     {
         curved = avifpix::LinearToSMPTE428(x, t);
+    }
+    else
+    {
+        curved = avifpix::LinearToHLG(x, t);
     }
     return avifpix::FloatToCode(curved, maxCodeFloat);
 }

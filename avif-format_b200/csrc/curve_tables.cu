@@ -222,9 +222,13 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     {
         SweepKernel<kCurveLinearToPQ><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, dMin, dMax);
     }
-    else
+    else if (curve == kCurveLinearToSMPTE428)
     {
         SweepKernel<kCurveLinearToSMPTE428><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, dMin, dMax);
+    }
+    else
+    {
+        SweepKernel<kCurveLinearToHLG><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, dMin, dMax);
     }
     std::vector<uint32_t> minBits(codeCount), maxBits(codeCount);
     bool ok = Check(cudaMemcpyAsync(minBits.data(), dMin, codeCount * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "D2H", &table->error) &&
@@ -502,9 +506,13 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
                 {
                     FillBandBitsKernel<kCurveLinearToPQ><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, dBands, bandCount, bandStrideLog2, bitsOut);
                 }
-                else
+                else if (curve == kCurveLinearToSMPTE428)
                 {
                     FillBandBitsKernel<kCurveLinearToSMPTE428><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, dBands, bandCount, bandStrideLog2, bitsOut);
+                }
+                else
+                {
+                    FillBandBitsKernel<kCurveLinearToHLG><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, dBands, bandCount, bandStrideLog2, bitsOut);
                 }
                 filled = Check(cudaStreamSynchronize(stream), "band bitmap", &table->error);
             }
@@ -535,9 +543,13 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     {
         VerifyKernel<kCurveLinearToPQ><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, table->view, dCounters);
     }
-    else
+    else if (curve == kCurveLinearToSMPTE428)
     {
         VerifyKernel<kCurveLinearToSMPTE428><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, table->view, dCounters);
+    }
+    else
+    {
+        VerifyKernel<kCurveLinearToHLG><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, table->view, dCounters);
     }
     unsigned long long counters[3] = { 0, 0, 0 };
     ok = Check(cudaMemcpyAsync(counters, dCounters, sizeof(counters), cudaMemcpyDeviceToHost, stream), "D2H", &table->error) &&

@@ -41,7 +41,8 @@ namespace avifgpu
 enum CurveId
 {
     kCurveLinearToPQ = 0,
-    kCurveLinearToSMPTE428 = 1
+    kCurveLinearToSMPTE428 = 1,
+    kCurveLinearToHLG = 2 // the HLG save extension (ColorTransfer.cpp:141-164); served by the generic kernels only
 };
 
 constexpr uint32_t kBucketOffsetBits = 20;          // low bits of a bucket word: quantised band-start offset

@@ -179,9 +179,24 @@ int ValidateEncodeDesc(const avifgpu_encode_desc* d, std::string* error)
         if (d->image_bit_depth == 8) return Fail(error, AVIFGPU_ERR_UNSUPPORTED, "32-bit hosts require a 10- or 12-bit image");
         // WriteHeifImage.cpp:578-588 (gray: PQ, Clip), :1079-1091 (colour: PQ, SMPTE428, Clip)
         const bool gray = d->host_channels <= 2;
+        // plus, only on request, the HLG save path the reference has the functions for but never calls (avifgpu.h)
+        const bool hlg = !gray && d->transfer == AVIFGPU_TRANSFER_HLG &&
+                         (d->hlg_extension == AVIFGPU_HLG_OETF || d->hlg_extension == AVIFGPU_HLG_INVERSE_OOTF_THEN_OETF);
         const bool ok = d->transfer == AVIFGPU_TRANSFER_PQ || d->transfer == AVIFGPU_TRANSFER_CLIP ||
-                        (!gray && d->transfer == AVIFGPU_TRANSFER_SMPTE428);
+                        (!gray && d->transfer == AVIFGPU_TRANSFER_SMPTE428) || hlg;
         if (!ok) return Fail(error, AVIFGPU_ERR_UNSUPPORTED, "Unsupported color transfer function.");
+        if (hlg && d->hlg_extension == AVIFGPU_HLG_INVERSE_OOTF_THEN_OETF)
+        {
+            float luma[3];
+            if (!d->nclx.present || !GetHlgLumaCoefficients(d->nclx.color_primaries, luma))
+            {
+                return Fail(error, AVIFGPU_ERR_UNSUPPORTED, "the inverse HLG OOTF needs nclx colour primaries with known luma coefficients");
+            }
+            if (!(d->hlg_display_gamma > 0.0f) || d->hlg_peak_nits <= 0)
+            {
+                return Fail(error, AVIFGPU_ERR_BAD_PARAM, "bad HLG display gamma / peak brightness");
+            }
+        }
     }
     if (d->layout == AVIFGPU_LAYOUT_PLANAR_YCBCR)
     {
@@ -332,6 +347,13 @@ void FillEncodeParams(const avifgpu_encode_desc& d, EncodeParams* p)
     p->transfer = d.transfer;
     p->pqMultiplier = static_cast<float>(d.pq_peak_nits) / 10000.0f; // ColorTransfer.cpp:86
     p->gray16Smpte428 = (d.host_depth == 16 && d.host_channels <= 2 && d.gray16_curve == AVIFGPU_GRAY16_SMPTE428) ? 1 : 0;
+    if (d.host_depth == 32 && d.transfer == AVIFGPU_TRANSFER_HLG && d.hlg_extension == AVIFGPU_HLG_INVERSE_OOTF_THEN_OETF)
+    {
+        p->hlgInverseOotf = 1;
+        GetHlgLumaCoefficients(d.nclx.color_primaries, p->hlgLuma);
+        p->hlgDisplayGamma = d.hlg_display_gamma;
+        p->hlgPeak = static_cast<float>(d.hlg_peak_nits);
+    }
     p->planar = d.layout == AVIFGPU_LAYOUT_PLANAR_YCBCR;
     if (p->planar)
     {

@@ -65,6 +65,10 @@ struct EncodeParams
     int32_t topLeft;       // AVIFGPU_DOWN_FILTER_TOP_LEFT
     avifpix::ForwardMatrix matrix;
     float chromaOffset;
+    int32_t hlgInverseOotf; // AVIFGPU_HLG_INVERSE_OOTF_THEN_OETF: ApplyInverseHLGOOTF on the pixel before LinearToHLG
+    float hlgLuma[3];
+    float hlgDisplayGamma;
+    float hlgPeak;
     // Float hosts with a transfer curve: the flat step table + band bitmap in global memory (a by-value copy of
     // *curveTable made by the generic launcher), or useCurveView = 0 -> every sample takes the exact powf.
     CurveTableView curveView;

@@ -319,7 +319,8 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
     int curve;
     if (p.transfer == AVIFGPU_TRANSFER_PQ) curve = kCurveLinearToPQ;
     else if (p.transfer == AVIFGPU_TRANSFER_SMPTE428) curve = kCurveLinearToSMPTE428;
-    else curve = kCurveClip;
+    else if (p.transfer == AVIFGPU_TRANSFER_CLIP) curve = kCurveClip;
+    else return 0; // HLG save path: the generic kernel (with the context's step table when it has one)
     if (curve != kCurveClip && (p.curveTable == nullptr || p.curveTable->buckets == nullptr))
     {
         return 0; // no verified table for this curve: the generic exact kernel serves it

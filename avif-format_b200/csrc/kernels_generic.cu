@@ -87,6 +87,10 @@ __device__ __forceinline__ void HostPixelToCodes(const EncodeParams& p, const Ho
         {
             color[0] = ClampF(color[0], 0.0f, 1.0f); // WriteHeifImage.cpp:602
         }
+        if (p.hlgInverseOotf)
+        {
+            ApplyInverseHLGOOTF(color[0], color[1], color[2], p.hlgLuma[0], p.hlgLuma[1], p.hlgLuma[2], p.hlgDisplayGamma, p.hlgPeak, t);
+        }
 #pragma unroll
         for (int i = 0; i < 3; ++i)
         {
@@ -105,6 +109,7 @@ __device__ __forceinline__ void HostPixelToCodes(const EncodeParams& p, const Ho
                 {
                 case AVIFGPU_TRANSFER_PQ: curved = LinearToPQ(color[i], p.pqMultiplier, t); break;
                 case AVIFGPU_TRANSFER_SMPTE428: curved = LinearToSMPTE428(color[i], t); break;
+                case AVIFGPU_TRANSFER_HLG: curved = LinearToHLG(color[i], t); break;
                 default: curved = color[i]; break;
                 }
                 codes[i] = FloatToCode(curved, p.maxCodeFloat);
@@ -553,7 +558,7 @@ int LaunchEncodeGeneric(const EncodeParams& params, int hostDepth, void* streamH
     EncodeParams p = params;
     p.useCurveView = 0;
     if (hostDepth == 32 && p.curveTable != nullptr && p.curveTable->flat != nullptr && p.curveTable->bandBits != nullptr &&
-        (p.transfer == AVIFGPU_TRANSFER_PQ || p.transfer == AVIFGPU_TRANSFER_SMPTE428))
+        (p.transfer == AVIFGPU_TRANSFER_PQ || p.transfer == AVIFGPU_TRANSFER_SMPTE428 || p.transfer == AVIFGPU_TRANSFER_HLG))
     {
         p.curveView = *p.curveTable;
         p.useCurveView = 1;

@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-API_VERSION = 1
+API_VERSION = 2
 
 # avifgpu_status
 OK = 0
@@ -21,6 +21,7 @@ ERR_CANCELED = -6
 
 # avifgpu_alpha_state (AlphaState.h:24-29)
 ALPHA_NONE, ALPHA_STRAIGHT, ALPHA_PREMULTIPLIED = 0, 1, 2
+HLG_REJECT, HLG_OETF, HLG_INVERSE_OOTF_THEN_OETF = 0, 1, 2
 # avifgpu_transfer (ColorTransfer.h:28-34)
 TRANSFER_PQ, TRANSFER_HLG, TRANSFER_SMPTE428, TRANSFER_CLIP = 0, 1, 2, 3
 # avifgpu_chroma (= heif_chroma)
@@ -82,11 +83,15 @@ class EncodeDesc(C.Structure):
         ("down_filter", C.c_int32),
         ("gray16_curve", C.c_int32),
         ("nclx", Nclx),
+        ("hlg_extension", C.c_int32),
+        ("hlg_display_gamma", C.c_float),
+        ("hlg_peak_nits", C.c_int32),
     ]
 
     def __init__(self, width, height, host_depth, host_channels, alpha_state=ALPHA_NONE, image_bit_depth=8,
                  transfer=TRANSFER_CLIP, pq_peak_nits=80, layout=LAYOUT_REFERENCE, chroma=CHROMA_444,
-                 down_filter=DOWN_FILTER_BOX, gray16_curve=GRAY16_LUT, nclx=None):
+                 down_filter=DOWN_FILTER_BOX, gray16_curve=GRAY16_LUT, nclx=None, hlg_extension=0, hlg_display_gamma=1.2,
+                 hlg_peak_nits=1000):
         super().__init__()
         self.struct_size = C.sizeof(EncodeDesc)
         self.width, self.height = width, height
@@ -100,6 +105,9 @@ class EncodeDesc(C.Structure):
         self.down_filter = down_filter
         self.gray16_curve = gray16_curve
         self.nclx = nclx if nclx is not None else Nclx()
+        self.hlg_extension = hlg_extension
+        self.hlg_display_gamma = hlg_display_gamma
+        self.hlg_peak_nits = hlg_peak_nits
 
     def copy(self, **changes):
         out = EncodeDesc(self.width, self.height, self.host_depth, self.host_channels)

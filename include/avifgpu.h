@@ -48,7 +48,7 @@ extern "C" {
 #define AVIFGPU_EXPORT __attribute__((visibility("default")))
 #endif
 
-#define AVIFGPU_API_VERSION 1
+#define AVIFGPU_API_VERSION 2
 
 typedef enum avifgpu_status
 {
@@ -143,6 +143,13 @@ typedef struct avifgpu_planes
 
 /* Parameter block of the encode direction = FormatRecord fields + SaveUIOptions fields the loops read
  * (AvifFormat.h:87-101, Write.cpp:229-258 fix-ups are the CALLER's job and are mirrored in host/). */
+typedef enum avifgpu_hlg_extension
+{
+    AVIFGPU_HLG_REJECT = 0,                /* what the reference does */
+    AVIFGPU_HLG_OETF = 1,                  /* scene-referred input: code = quantise(LinearToHLG(c)) */
+    AVIFGPU_HLG_INVERSE_OOTF_THEN_OETF = 2 /* display-referred input: ApplyInverseHLGOOTF(rgb) first; needs nclx primaries */
+} avifgpu_hlg_extension;
+
 typedef struct avifgpu_encode_desc
 {
     uint32_t struct_size;    /* sizeof(avifgpu_encode_desc) */
@@ -159,6 +166,12 @@ typedef struct avifgpu_encode_desc
     int32_t down_filter;     /* avifgpu_down_filter */
     int32_t gray16_curve;    /* avifgpu_gray16_curve, Gray16 hosts only */
     avifgpu_nclx nclx;       /* matrix for PLANAR_YCBCR (WriteMetadata.cpp:113-146); full range only */
+    /* HLG save path.  The reference ships LinearToHLG and ApplyInverseHLGOOTF (ColorTransfer.cpp:141-164,
+     * 207-220) but no caller: with hlg_extension = 0 transfer = AVIFGPU_TRANSFER_HLG is rejected with the reference's own
+     * "Unsupported color transfer function." (WriteHeifImage.cpp:1085-1087).  Colour float hosts only. */
+    int32_t hlg_extension;       /* avifgpu_hlg_extension */
+    float hlg_display_gamma;     /* for AVIFGPU_HLG_INVERSE_OOTF_THEN_OETF (LoadUIOptions.hlg.displayGamma's counterpart) */
+    int32_t hlg_peak_nits;       /* nominal peak brightness of the display-referred input */
 } avifgpu_encode_desc;
 
 /* Parameter block of the decode direction = heif_image properties + nclx + LoadUIOptions

@@ -611,11 +611,16 @@ static uint16_t premultiply_code(uint16_t color, uint16_t alpha, int image_depth
     return color;
 }
 
-/* WriteHeifImage.cpp:1079-1091 (colour) / 578-588 (gray): the OETF switch. */
-static int apply_oetf(int transfer, float peak, int is_gray, float v, float* out)
+/* WriteHeifImage.cpp:1079-1091 (colour) / 578-588 (gray): the OETF switch.  hlg_extension != 0 adds the HLG save path
+ * this project defines on top of the reference's uncalled LinearToHLG (include/avifgpu.h). */
+static int apply_oetf(int transfer, float peak, int is_gray, int hlg_extension, float v, float* out)
 {
     switch (transfer)
     {
+    case AVIFGPU_TRANSFER_HLG:
+        if (is_gray || (hlg_extension != AVIFGPU_HLG_OETF && hlg_extension != AVIFGPU_HLG_INVERSE_OOTF_THEN_OETF)) return 0;
+        *out = linear_to_hlg(v);
+        return 1;
     case AVIFGPU_TRANSFER_PQ:
         *out = linear_to_pq(v, peak);
         return 1;
@@ -677,10 +682,20 @@ static int host_pixel_to_codes(const avifgpu_encode_desc* d, const void* pixel, 
             /* WriteHeifImage.cpp:602: the gray no-alpha path clamps to [0,1] before the transfer curve. */
             color[0] = clamp_f(color[0], 0.0f, 1.0f);
         }
+        if (colors == 3 && d->transfer == AVIFGPU_TRANSFER_HLG && d->hlg_extension == AVIFGPU_HLG_INVERSE_OOTF_THEN_OETF)
+        {
+            /* display-referred input: ColorTransfer.cpp:207-220 on the pixel, then the OETF per channel */
+            float luma[3];
+            if (!d->nclx.present || avif_oracle_get_hlg_luma_coefficients(d->nclx.color_primaries, luma) != AVIFGPU_OK)
+            {
+                return 0;
+            }
+            apply_inverse_hlg_ootf(color, luma, d->hlg_display_gamma, (float)d->hlg_peak_nits);
+        }
         for (i = 0; i < colors; ++i)
         {
             float curved;
-            if (!apply_oetf(d->transfer, peak, colors == 1, color[i], &curved))
+            if (!apply_oetf(d->transfer, peak, colors == 1, d->hlg_extension, color[i], &curved))
             {
                 return 0;
             }

@@ -125,6 +125,16 @@ def encode_cases(sizes=None, full=True):
                                   abi.GRAY16_LUT, nclx)
             rows = float_host_rows(rng, h, w, channels) if host_depth == 32 else int_host_rows(rng, h, w, channels, host_depth)
             yield name, desc, rows, False
+        # -- HLG save path (the reference has LinearToHLG / ApplyInverseHLGOOTF but no caller: restatement only)
+        for channels, extension, layout, depth in itertools.product((3, 4), (abi.HLG_OETF, abi.HLG_INVERSE_OOTF_THEN_OETF),
+                                                                    (abi.LAYOUT_REFERENCE, abi.LAYOUT_PLANAR_YCBCR), (10, 12)):
+            alphas = [abi.ALPHA_NONE] if channels == 3 else [abi.ALPHA_STRAIGHT, abi.ALPHA_PREMULTIPLIED]
+            for alpha in alphas:
+                name = f"enc_hlg_c{channels}_a{alpha}_x{extension}_l{layout}_d{depth}_{w}x{h}"
+                rng = rng_for(name)
+                desc = abi.EncodeDesc(w, h, 32, channels, alpha, depth, abi.TRANSFER_HLG, 80, layout, abi.CHROMA_420, abi.DOWN_FILTER_BOX,
+                                      abi.GRAY16_LUT, NCLX_2020_HLG(), hlg_extension=extension, hlg_display_gamma=1.2, hlg_peak_nits=1000)
+                yield name, desc, float_host_rows(rng, h, w, channels), False
         # -- gray16 -> SMPTE 428 (BASELINE config 5, this project's composition)
         for channels in (1, 2):
             alpha = abi.ALPHA_NONE if channels == 1 else abi.ALPHA_STRAIGHT
