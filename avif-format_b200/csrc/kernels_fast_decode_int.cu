@@ -366,6 +366,134 @@ cudaError_t DispatchChroma(const IntDecodeParams& fp, int xs, int ys, int smCoun
     return LaunchOne<SampleT, 0, 0, ALPHA>(fp, smCount, stream);
 }
 
+// ---- monochrome and planar-RGB images: pure streaming ------------------------------------------------------------------
+//
+// Monochrome (ReadHeifImage.cpp:418-559 driving YuvDecode.cpp:55-203): out = round(table[Y]) -- no matrix, so the whole
+// per-sample result is tabulated in shared memory; alpha is copied (8-bit) or tabulated (16-bit).
+// Planar RGB (ReadHeifImage.cpp:561-861): the samples are interleaved as they are; 16-bit hosts mask them with the
+// image's maximum (:789-792).  A thread moves 8 pixels: one vector load per plane, CH * 8 samples stored as 64/128-bit words.
+struct StreamDecodeParams
+{
+    const uint8_t* plane[4];
+    int64_t planeStride[4];
+    uint8_t* rows;
+    int64_t rowStride;
+    int32_t groupsPerRow; // 8 pixels each
+    int32_t rowCount;
+    int32_t bitDepth;
+    uint32_t maxCode;
+    RangeParams range;
+};
+
+constexpr int kStreamThreads = 256;
+
+template <typename SampleT, int CHANNELS, bool MONO>
+__global__ void __launch_bounds__(kStreamThreads) StreamDecodeKernel(const StreamDecodeParams p)
+{
+    constexpr bool kHost8 = sizeof(SampleT) == 1;
+    extern __shared__ __align__(16) uint8_t sharedBytes[];
+    uint16_t* lutY = reinterpret_cast<uint16_t*>(sharedBytes);
+    uint16_t* lutA = lutY + (1u << p.bitDepth);
+    if (MONO)
+    {
+        for (uint32_t i = threadIdx.x; i <= p.maxCode; i += blockDim.x)
+        {
+            const float y = UnormToFloatY(i, p.range); // YuvLookupTables.cpp:157-171
+            lutY[i] = static_cast<uint16_t>(0.5f + (y * (kHost8 ? 255.0f : 32768.0f))); // YuvDecode.cpp:76, 150
+            lutA[i] = static_cast<uint16_t>(0.5f + (UnormToFloatPlain(i, p.range.maxChannelFloat) * 32768.0f)); // YuvDecode.cpp:197
+        }
+        __syncthreads();
+    }
+    // source planes: mono -> Y (, A at index 3); RGB -> R, G, B (, A)
+    constexpr int kColours = MONO ? 1 : 3;
+    constexpr bool kAlpha = CHANNELS > kColours;
+    const long long groups = static_cast<long long>(p.groupsPerRow) * p.rowCount;
+    for (long long group = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; group < groups;
+         group += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const long long row = group / p.groupsPerRow;
+        const long long column = (group - row * p.groupsPerRow) * 8;
+        Raw8<SampleT> raw[CHANNELS];
+#pragma unroll
+        for (int c = 0; c < CHANNELS; ++c)
+        {
+            const int planeIndex = (kAlpha && c == CHANNELS - 1) ? 3 : c;
+            raw[c] = LoadEight<SampleT>(p.plane[planeIndex] + row * p.planeStride[planeIndex] + column * static_cast<long long>(sizeof(SampleT)));
+        }
+        uint32_t samples[8 * CHANNELS];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+#pragma unroll
+            for (int c = 0; c < CHANNELS; ++c)
+            {
+                uint32_t v = Sample<SampleT>(raw[c], i);
+                if (MONO)
+                {
+                    const bool isAlpha = kAlpha && c == CHANNELS - 1;
+                    if (!isAlpha)
+                    {
+                        v = lutY[kHost8 ? v : min(v, p.maxCode)];
+                    }
+                    else if (!kHost8)
+                    {
+                        v = lutA[min(v, p.maxCode)];
+                    }
+                }
+                else if (!kHost8)
+                {
+                    v &= p.maxCode;
+                }
+                samples[i * CHANNELS + c] = v;
+            }
+        }
+        constexpr int kWords = 8 * CHANNELS * static_cast<int>(sizeof(SampleT)) / 4;
+        uint32_t words[kWords];
+#pragma unroll
+        for (int w = 0; w < kWords; ++w)
+        {
+            if (kHost8)
+            {
+                words[w] = samples[4 * w] | (samples[4 * w + 1] << 8) | (samples[4 * w + 2] << 16) | (samples[4 * w + 3] << 24);
+            }
+            else
+            {
+                words[w] = samples[2 * w] | (samples[2 * w + 1] << 16);
+            }
+        }
+        uint8_t* target = p.rows + row * p.rowStride + column * static_cast<long long>(CHANNELS * sizeof(SampleT));
+        if (kWords % 4 == 0)
+        {
+#pragma unroll
+            for (int q = 0; q < kWords / 4; ++q)
+            {
+                __stcs(reinterpret_cast<uint4*>(target) + q, make_uint4(words[4 * q], words[4 * q + 1], words[4 * q + 2], words[4 * q + 3]));
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int q = 0; q < kWords / 2; ++q)
+            {
+                __stcs(reinterpret_cast<uint2*>(target) + q, make_uint2(words[2 * q], words[2 * q + 1]));
+            }
+        }
+    }
+}
+
+template <typename SampleT, int CHANNELS, bool MONO>
+cudaError_t LaunchStream(const StreamDecodeParams& sp, int smCount, cudaStream_t stream)
+{
+    const long long groups = static_cast<long long>(sp.groupsPerRow) * sp.rowCount;
+    long long blocks = (groups + kStreamThreads - 1) / kStreamThreads;
+    const long long cap = static_cast<long long>(smCount) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const size_t shared = MONO ? 2 * sizeof(uint16_t) * (static_cast<size_t>(1) << sp.bitDepth) : 0;
+    StreamDecodeKernel<SampleT, CHANNELS, MONO><<<static_cast<unsigned>(blocks), kStreamThreads, shared, stream>>>(sp);
+    return cudaGetLastError();
+}
+
 bool Aligned(const void* p, int64_t stride, int alignment)
 {
     return (reinterpret_cast<uintptr_t>(p) % alignment) == 0 && (stride % alignment) == 0;
@@ -375,12 +503,98 @@ bool Aligned(const void* p, int64_t stride, int alignment)
 
 int LaunchDecodeGeneric(const DecodeParams& params, void* stream);
 
+// Monochrome and planar-RGB images for the integer hosts (no premultiplied alpha, depth <= 12: checked by the caller).
+static int LaunchDecodeStream(const DecodeParams& p, void* streamHandle)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
+    const int sampleBytes = p.hostDepth == 8 ? 1 : 2;
+    if ((sampleBytes == 1) != (p.bitDepth <= 8))
+    {
+        return 0;
+    }
+    const bool mono = p.colorspace == AVIFGPU_COLORSPACE_MONOCHROME;
+    const int colours = mono ? 1 : 3;
+    const int channels = colours + (p.hasAlpha ? 1 : 0);
+    const int planeAlign = 8 * sampleBytes;
+    const int rowAlign = (8 * channels * sampleBytes) % 16 == 0 ? 16 : 8;
+    for (int c = 0; c < colours; ++c)
+    {
+        if (!Aligned(p.plane[c], p.planeStride[c], planeAlign))
+        {
+            return 0;
+        }
+    }
+    if ((p.hasAlpha && !Aligned(p.plane[3], p.planeStride[3], planeAlign)) || !Aligned(p.rows, p.rowStride, rowAlign))
+    {
+        return 0;
+    }
+    const int width8 = p.width & ~7;
+    if (width8 < 8 || p.rowCount < 1)
+    {
+        return 0;
+    }
+    StreamDecodeParams sp{};
+    for (int k = 0; k < 4; ++k)
+    {
+        sp.plane[k] = static_cast<const uint8_t*>(p.plane[k]);
+        sp.planeStride[k] = p.planeStride[k];
+    }
+    sp.rows = static_cast<uint8_t*>(p.rows);
+    sp.rowStride = p.rowStride;
+    sp.groupsPerRow = width8 / 8;
+    sp.rowCount = p.rowCount;
+    sp.bitDepth = p.bitDepth;
+    sp.maxCode = p.maxCode;
+    sp.range = p.range;
+    const int smCount = p.smCount > 0 ? p.smCount : 148;
+    cudaError_t e;
+    if (sampleBytes == 1)
+    {
+        if (mono) e = p.hasAlpha ? LaunchStream<uint8_t, 2, true>(sp, smCount, stream) : LaunchStream<uint8_t, 1, true>(sp, smCount, stream);
+        else e = p.hasAlpha ? LaunchStream<uint8_t, 4, false>(sp, smCount, stream) : LaunchStream<uint8_t, 3, false>(sp, smCount, stream);
+    }
+    else
+    {
+        if (mono) e = p.hasAlpha ? LaunchStream<uint16_t, 2, true>(sp, smCount, stream) : LaunchStream<uint16_t, 1, true>(sp, smCount, stream);
+        else e = p.hasAlpha ? LaunchStream<uint16_t, 4, false>(sp, smCount, stream) : LaunchStream<uint16_t, 3, false>(sp, smCount, stream);
+    }
+    if (e != cudaSuccess)
+    {
+        return AVIFGPU_ERR_CUDA;
+    }
+    int launched = 1;
+    if (width8 < p.width)
+    {
+        DecodeParams strip = p;
+        strip.width = p.width - width8;
+        for (int k = 0; k < 4; ++k)
+        {
+            if (p.plane[k] != nullptr)
+            {
+                strip.plane[k] = static_cast<const uint8_t*>(p.plane[k]) + static_cast<int64_t>(width8) * sampleBytes;
+            }
+        }
+        strip.rows = static_cast<uint8_t*>(p.rows) + static_cast<int64_t>(width8) * channels * sampleBytes;
+        const int n = LaunchDecodeGeneric(strip, streamHandle);
+        if (n < 0) return n;
+        launched += n;
+    }
+    return launched;
+}
+
 // Returns the number of kernels launched, 0 if this configuration is not covered, or a negative status.
 int LaunchDecodeFastInteger(const DecodeParams& p, void* streamHandle)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
-    if (p.colorspace != AVIFGPU_COLORSPACE_YCBCR || (p.hostDepth != 8 && p.hostDepth != 16) || p.bitDepth > 12 || p.yPhase != 0 ||
-        (p.hasAlpha && p.premultiplied))
+    if ((p.hostDepth != 8 && p.hostDepth != 16) || p.bitDepth > 12 || (p.hasAlpha && p.premultiplied))
+    {
+        return 0;
+    }
+    if (p.colorspace != AVIFGPU_COLORSPACE_YCBCR)
+    {
+        return LaunchDecodeStream(p, streamHandle);
+    }
+    if (p.yPhase != 0)
     {
         return 0;
     }

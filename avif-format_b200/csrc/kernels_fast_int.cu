@@ -351,6 +351,90 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
     }
 }
 
+// ---- Gray(+A) 8/16-bit hosts -> Y (+A) planes (WriteHeifImage.cpp:169-500 without premultiplication) ------------------------
+// The same depth mapping as the colour kernel, no matrix: a thread converts 8 pixels.
+template <typename HostT, typename PlaneT, int CHANNELS>
+__global__ void __launch_bounds__(kRgbThreads) EncodeGrayIntKernel(const Rgb16Params p)
+{
+    constexpr int kWordsPerRow = CHANNELS * 2 * static_cast<int>(sizeof(HostT)); // 8 pixels x CHANNELS samples / 4 bytes
+    constexpr int kVectorWords = (kWordsPerRow % 4 == 0) ? 4 : 2;
+    constexpr int kPlaneBytes = static_cast<int>(sizeof(PlaneT));
+    __shared__ float hostLut[(sizeof(HostT) == 1 && sizeof(PlaneT) == 2) ? 256 : 1];
+    if (sizeof(HostT) == 1 && sizeof(PlaneT) == 2)
+    {
+        for (uint32_t v = threadIdx.x; v < 256; v += blockDim.x)
+        {
+            hostLut[v] = __uint_as_float(0x4b000000u | DepthLutEntry(v, 255.0f, p.maxCode));
+        }
+        __syncthreads();
+    }
+    const long long groups = static_cast<long long>(p.groupsPerRow) * p.rowCount;
+    for (long long group = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; group < groups;
+         group += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const long long row = group / p.groupsPerRow;
+        const long long column = group - row * p.groupsPerRow;
+        uint32_t words[kWordsPerRow];
+        const uint8_t* source = p.rows + row * p.rowStride + column * (kWordsPerRow * 4);
+#pragma unroll
+        for (int q = 0; q < kWordsPerRow / kVectorWords; ++q)
+        {
+            if (kVectorWords == 4)
+            {
+                const uint4 w = __ldcs(reinterpret_cast<const uint4*>(source) + q);
+                words[4 * q + 0] = w.x;
+                words[4 * q + 1] = w.y;
+                words[4 * q + 2] = w.z;
+                words[4 * q + 3] = w.w;
+            }
+            else
+            {
+                const uint2 w = __ldcs(reinterpret_cast<const uint2*>(source) + q);
+                words[2 * q + 0] = w.x;
+                words[2 * q + 1] = w.y;
+            }
+        }
+        auto sample = [&](int k) -> uint32_t
+        {
+            if (sizeof(HostT) == 2)
+            {
+                const uint32_t w = words[k >> 1];
+                return (k & 1) ? (w >> 16) : (w & 0xffffu);
+            }
+            return (words[k >> 2] >> (8 * (k & 3))) & 0xffu;
+        };
+        uint32_t yCodes[8], aCodes[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            yCodes[i] = BiasedToCode(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS), p, hostLut));
+            if (CHANNELS == 2)
+            {
+                aCodes[i] = BiasedToCode(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 1), p, hostLut));
+            }
+        }
+        StoreEight<PlaneT>(p.plane[0] + row * p.stride[0] + column * (8 * kPlaneBytes), yCodes);
+        if (CHANNELS == 2)
+        {
+            StoreEight<PlaneT>(p.plane[3] + row * p.stride[3] + column * (8 * kPlaneBytes), aCodes);
+        }
+    }
+}
+
+template <typename HostT, typename PlaneT>
+cudaError_t LaunchGrayInt(const Rgb16Params& rp, int channels, int smCount, cudaStream_t stream)
+{
+    const long long groups = static_cast<long long>(rp.groupsPerRow) * rp.rowCount;
+    long long blocks = (groups + kRgbThreads - 1) / kRgbThreads;
+    const long long cap = static_cast<long long>(smCount) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const unsigned grid = static_cast<unsigned>(blocks);
+    if (channels == 2) EncodeGrayIntKernel<HostT, PlaneT, 2><<<grid, kRgbThreads, 0, stream>>>(rp);
+    else EncodeGrayIntKernel<HostT, PlaneT, 1><<<grid, kRgbThreads, 0, stream>>>(rp);
+    return cudaGetLastError();
+}
+
 bool Aligned(const void* p, int64_t stride, int alignment)
 {
     return (reinterpret_cast<uintptr_t>(p) % alignment) == 0 && (stride % alignment) == 0;
@@ -429,6 +513,60 @@ int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHa
             strip.rows = static_cast<const uint8_t*>(p.rows) + static_cast<int64_t>(covered) * 2;
             strip.width = p.width - covered;
             strip.plane[0] = static_cast<uint8_t*>(p.plane[0]) + static_cast<int64_t>(covered) * 2;
+            const int n = LaunchEncodeGeneric(strip, hostDepth, streamHandle);
+            if (n < 0) return n;
+            launched += n;
+        }
+        return launched;
+    }
+
+    // Gray(+A) hosts in the reference layout (Y plane [0], alpha plane [3]); premultiplication and the Gray16 SMPTE 428
+    // composition stay with the generic kernel (the latter has its own table kernel above for one channel).
+    if (!p.planar && (p.channels == 1 || p.channels == 2) && !p.premultiply && !p.gray16Smpte428 && p.imageDepth <= 12)
+    {
+        const int hostBytes = hostDepth / 8;
+        const int planeBytes = p.imageDepth > 8 ? 2 : 1;
+        const int rowAlign = (8 * p.channels * hostBytes) % 16 == 0 ? 16 : 8;
+        if (p.width < 8 || p.rowCount < 1 || !Aligned(p.rows, p.rowStride, rowAlign) || !Aligned(p.plane[0], p.planeStride[0], 8 * planeBytes) ||
+            (p.channels == 2 && !Aligned(p.plane[3], p.planeStride[3], 8 * planeBytes)))
+        {
+            return 0;
+        }
+        const int width8 = p.width & ~7;
+        Rgb16Params rp{};
+        rp.rows = static_cast<const uint8_t*>(p.rows);
+        rp.rowStride = p.rowStride;
+        for (int k = 0; k < 4; ++k)
+        {
+            rp.plane[k] = static_cast<uint8_t*>(p.plane[k]);
+            rp.stride[k] = p.planeStride[k];
+        }
+        rp.groupsPerRow = width8 / 8;
+        rp.rowCount = p.rowCount;
+        rp.maxCodeFloat = p.maxCodeFloat;
+        rp.biasedMax = 8388608.0f + p.maxCodeFloat;
+        rp.maxCode = p.maxCode;
+        cudaError_t e;
+        if (hostBytes == 2)
+        {
+            e = planeBytes == 2 ? LaunchGrayInt<uint16_t, uint16_t>(rp, p.channels, smCount, stream) : LaunchGrayInt<uint16_t, uint8_t>(rp, p.channels, smCount, stream);
+        }
+        else
+        {
+            e = planeBytes == 2 ? LaunchGrayInt<uint8_t, uint16_t>(rp, p.channels, smCount, stream) : LaunchGrayInt<uint8_t, uint8_t>(rp, p.channels, smCount, stream);
+        }
+        if (e != cudaSuccess)
+        {
+            return AVIFGPU_ERR_CUDA;
+        }
+        int launched = 1;
+        if (width8 < p.width)
+        {
+            EncodeParams strip = p;
+            strip.rows = static_cast<const uint8_t*>(p.rows) + static_cast<int64_t>(width8) * p.channels * hostBytes;
+            strip.width = p.width - width8;
+            strip.plane[0] = static_cast<uint8_t*>(p.plane[0]) + static_cast<int64_t>(width8) * planeBytes;
+            if (p.channels == 2) strip.plane[3] = static_cast<uint8_t*>(p.plane[3]) + static_cast<int64_t>(width8) * planeBytes;
             const int n = LaunchEncodeGeneric(strip, hostDepth, streamHandle);
             if (n < 0) return n;
             launched += n;

@@ -113,6 +113,47 @@ decode_case("decode 12-bit 4:4:4 -> RGB16 (a14)", 12, 16, abi.CHROMA_444, n601, 
 encode_case("encode RGB8 -> 8-bit 4:2:0 (a3)", 8, 3, 8, abi.CHROMA_420, n601, 3 + 1.5)
 encode_case("encode RGBA8 -> 8-bit 4:4:4 + A (config 1 at 8K) (a3)", 8, 4, 8, abi.CHROMA_444, n601, 4 + 4, alpha=abi.ALPHA_STRAIGHT)
 encode_case("encode RGB8 -> 10-bit 4:2:0 (a3)", 8, 3, 10, abi.CHROMA_420, n601, 3 + 3)
+def mono_rgb_cases():
+    # monochrome and planar-RGB images (rows a4 / a16 / a18 / a19): still the generic kernels
+    for name, colorspace, bit_depth, host_depth, bpp in (("decode mono 8-bit -> Gray8 (a16)", abi.COLORSPACE_MONOCHROME, 8, 8, 2),
+                                                         ("decode mono 10-bit -> Gray16 (a16)", abi.COLORSPACE_MONOCHROME, 10, 16, 4),
+                                                         ("decode planar RGB 8-bit -> RGB8 (a18)", abi.COLORSPACE_RGB, 8, 8, 6),
+                                                         ("decode planar RGB 10-bit -> RGB16 (a18)", abi.COLORSPACE_RGB, 10, 16, 12)):
+        desc = abi.DecodeDesc(W, H, colorspace, abi.CHROMA_444, bit_depth, abi.ALPHA_NONE, host_depth, abi.Nclx(1, 1, 13, 0 if colorspace == abi.COLORSPACE_RGB else 6, 1))
+        shapes = abi.decode_plane_shapes(desc)
+        dt = torch.uint8 if bit_depth == 8 else torch.int16
+        ch = abi.decode_host_channels(desc)
+        sets = []
+        for _ in range(4):  # rotate frames so that nothing survives in the 126 MB L2
+            planes = [None if s is None else torch.randint(0, 1 << bit_depth, s, generator=g, device=dev, dtype=torch.int32).to(dt) for s in shapes]
+            out = torch.empty((H, W * ch), dtype={8: torch.uint8, 16: torch.int16}[host_depth], device=dev)
+            sets.append((avifgpu.planes_from_tensors(planes), planes, out))
+        i = [0]
+
+        def run():
+            s_ = sets[i[0] % 4]
+            i[0] += 1
+            gpu.decode_device(desc, s_[0], s_[2].data_ptr(), s_[2].stride(0) * s_[2].element_size())
+        ms = timed(run)
+        print(json.dumps({"case": name, "ms": ms, "gpx_s": W * H / ms / 1e6, "gb_s": W * H * bpp / ms / 1e6}))
+    for name, host_depth, depth, bpp in (("encode Gray8 -> 8-bit Y (a4)", 8, 8, 2), ("encode Gray8 -> 10-bit Y (a4)", 8, 10, 3)):
+        desc = abi.EncodeDesc(W, H, host_depth, 1, abi.ALPHA_NONE, depth)
+        shapes = abi.encode_plane_shapes(desc)
+        sets = []
+        for _ in range(4):
+            rows = torch.randint(0, 256, (H, W), generator=g, device=dev, dtype=torch.int32).to(torch.uint8)
+            planes = [None if s is None else torch.empty(s, dtype=torch.uint8 if depth == 8 else torch.int16, device=dev) for s in shapes]
+            sets.append((rows, avifgpu.planes_from_tensors(planes), planes))
+        i = [0]
+
+        def run():
+            s_ = sets[i[0] % 4]
+            i[0] += 1
+            gpu.encode_device(desc, s_[0].data_ptr(), s_[0].stride(0), s_[1])
+        ms = timed(run)
+        print(json.dumps({"case": name, "ms": ms, "gpx_s": W * H / ms / 1e6, "gb_s": W * H * bpp / ms / 1e6}))
+
+mono_rgb_cases()
 for tables in (False, True):
     tag = "step tables" if tables else "exact powf"
     float_encode_case(f"encode RGBA32f -> 12-bit PQ 4:2:0 + A, generic kernel, {tag} (a1)", 4, abi.LAYOUT_PLANAR_YCBCR, 16 + 5, tables)
