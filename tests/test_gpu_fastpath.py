@@ -219,6 +219,10 @@ def test_ycc_to_rgb32_fast_kernel(gpu, port, w, h, chroma):
         expected = port.decode(desc, planes, threads=4)
         got = gpu.decode(desc, planes)
         assert cases.same_bits(expected, got), (bit_depth, kwargs, int((expected.view(np.uint32) != got.view(np.uint32)).sum()))
+        for alpha in (abi.ALPHA_STRAIGHT, abi.ALPHA_PREMULTIPLIED):  # straight: the tuned kernel's RGBA variant; premultiplied: generic
+            adesc = desc.copy(alpha_state=alpha)
+            aplanes = cases.code_planes(cases.rng_for(f"dec32a_{w}x{h}_{chroma}_{bit_depth}_{alpha}"), adesc, overshoot=True)
+            assert cases.same_bits(port.decode(adesc, aplanes, threads=4), gpu.decode(adesc, aplanes)), (bit_depth, kwargs, alpha)
         # odd first rows (4:2:0 blocks may start anywhere on decode) must still agree
         if h > 3:
             out = np.zeros_like(expected)
