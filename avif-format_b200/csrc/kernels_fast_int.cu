@@ -269,10 +269,22 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
                     }
                     return (words[r][k >> 2] >> (8 * (k & 3))) & 0xffu;
                 };
-                const float rb = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 0), p, hostLut);
-                const float gb = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 1), p, hostLut);
-                const float bb = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 2), p, hostLut);
-                const float rf = rb - kTwo23, gf = gb - kTwo23, bf = bb - kTwo23;
+                float rf, gf, bf;
+                if (sizeof(HostT) == 1 && sizeof(PlaneT) == 1)
+                {
+                    // 8-bit host into an 8-bit image: the sample is the code.  Byte -> float is one conversion instruction
+                    // (it takes the byte lane as an operand modifier); at 4.5 bytes per pixel this kernel is bound by
+                    // instruction issue, not by the conversion pipe that config 4's 14 bytes per pixel has to avoid.
+                    rf = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 0)));
+                    gf = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 1)));
+                    bf = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 2)));
+                }
+                else
+                {
+                    rf = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 0), p, hostLut) - kTwo23;
+                    gf = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 1), p, hostLut) - kTwo23;
+                    bf = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 2), p, hostLut) - kTwo23;
+                }
                 float yf;
                 if (p.matrix.identity)
                 {
@@ -289,7 +301,8 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
                 yCodes[i] = BiasedToCode(BiasedTrunc(yf + 0.5f, p.biasedMax));
                 if (CHANNELS == 4)
                 {
-                    aCodes[i] = BiasedToCode(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 3), p, hostLut));
+                    aCodes[i] = (sizeof(HostT) == 1 && sizeof(PlaneT) == 1) ? sample(i * CHANNELS + 3)
+                                                                            : BiasedToCode(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 3), p, hostLut));
                 }
             }
             StoreEight<PlaneT>(p.plane[0] + (y0 + r) * p.stride[0] + static_cast<long long>(column) * (8 * kPlaneBytes), yCodes);
