@@ -59,7 +59,7 @@ constexpr uint32_t kOffsetResolutionBits = 19;      // offsets inside a bucket a
 // code = kUpper - (bits < .x), delivered as a float (the forward matrix wants floats); the sample is in band iff
 // 0 <= bits - .x < bandWidth, and then bit ((kUpper << bandStrideLog2) + bits - .x) of bandBits says whether the
 // exact code is kUpper (1) or kUpper - 1 (0).
-constexpr uint32_t kFlatMaxShift = 14;
+constexpr uint32_t kFlatMaxShift = 16;
 constexpr uint32_t kFlatMaxBytes = 132 * 1024;
 constexpr uint32_t kFlatWidthBits = 12;
 constexpr uint32_t kFlatWidthMask = (1u << kFlatWidthBits) - 1u;
