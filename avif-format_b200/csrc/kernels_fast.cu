@@ -312,7 +312,8 @@ int LaunchEncodeGeneric(const EncodeParams& params, int hostDepth, void* stream)
 int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
-    if (hostDepth != 32 || !p.planar || p.channels != 3 || p.hasAlpha || p.imageDepth <= 8)
+    const bool rgba = p.channels == 4 && p.hasAlpha;
+    if (hostDepth != 32 || !p.planar || (p.channels != 3 && !rgba) || (p.channels == 3 && p.hasAlpha) || p.imageDepth <= 8)
     {
         return 0;
     }
@@ -330,9 +331,14 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
         return 0; // an exotic matrix: the generic kernel clamps
     }
     if (!Aligned(p.rows, p.rowStride, 16) || !Aligned(p.plane[0], p.planeStride[0], 8) ||
-        !Aligned(p.plane[1], p.planeStride[1], p.xs ? 4 : 8) || !Aligned(p.plane[2], p.planeStride[2], p.xs ? 4 : 8))
+        !Aligned(p.plane[1], p.planeStride[1], p.xs ? 4 : 8) || !Aligned(p.plane[2], p.planeStride[2], p.xs ? 4 : 8) ||
+        (rgba && !Aligned(p.plane[3], p.planeStride[3], 8)))
     {
         return 0;
+    }
+    if (rgba && (curve == kCurveClip || p.curveTable->flat == nullptr || p.curveTable->bandBits == nullptr))
+    {
+        return 0; // the RGBA kernel is built on the flat table + band bitmap; everything else with alpha: generic
     }
     const int width4 = p.width & ~3;
     const int evenRows = p.ys ? (p.rowCount & ~1) : p.rowCount;
@@ -362,10 +368,24 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
     {
         fp.table = *p.curveTable;
     }
+    if (rgba)
+    {
+        fp.planeA = static_cast<uint8_t*>(p.plane[3]);
+        fp.strideA = p.planeStride[3];
+        fp.premultiply = p.premultiply;
+    }
 
     const int smCount = p.smCount > 0 ? p.smCount : 148;
     cudaError_t e;
-    if (curve == kCurveLinearToPQ) e = DispatchTable<kCurveLinearToPQ>(fp, p.xs, p.ys, smCount, stream);
+    if (rgba)
+    {
+        if (!RgbaEncodeApplies(fp))
+        {
+            return 0;
+        }
+        e = LaunchFastEncodeRgba(fp, curve, p.xs, p.ys, smCount, stream);
+    }
+    else if (curve == kCurveLinearToPQ) e = DispatchTable<kCurveLinearToPQ>(fp, p.xs, p.ys, smCount, stream);
     else if (curve == kCurveLinearToSMPTE428) e = DispatchTable<kCurveLinearToSMPTE428>(fp, p.xs, p.ys, smCount, stream);
     else e = DispatchChroma<kCurveClip>(fp, p.xs, p.ys, smCount, stream);
     if (e != cudaSuccess)
@@ -379,11 +399,12 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
     if (width4 < p.width)
     {
         EncodeParams strip = p;
-        strip.rows = static_cast<const uint8_t*>(p.rows) + static_cast<int64_t>(width4) * 12;
+        strip.rows = static_cast<const uint8_t*>(p.rows) + static_cast<int64_t>(width4) * (rgba ? 16 : 12);
         strip.width = p.width - width4;
         strip.plane[0] = static_cast<uint8_t*>(p.plane[0]) + static_cast<int64_t>(width4) * 2;
         strip.plane[1] = static_cast<uint8_t*>(p.plane[1]) + static_cast<int64_t>(width4 >> p.xs) * 2;
         strip.plane[2] = static_cast<uint8_t*>(p.plane[2]) + static_cast<int64_t>(width4 >> p.xs) * 2;
+        if (rgba) strip.plane[3] = static_cast<uint8_t*>(p.plane[3]) + static_cast<int64_t>(width4) * 2;
         const int n = LaunchEncodeGeneric(strip, hostDepth, streamHandle);
         if (n < 0) return n;
         launched += n;
@@ -397,6 +418,7 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
         strip.plane[0] = static_cast<uint8_t*>(p.plane[0]) + static_cast<int64_t>(evenRows) * p.planeStride[0];
         strip.plane[1] = static_cast<uint8_t*>(p.plane[1]) + static_cast<int64_t>(evenRows >> p.ys) * p.planeStride[1];
         strip.plane[2] = static_cast<uint8_t*>(p.plane[2]) + static_cast<int64_t>(evenRows >> p.ys) * p.planeStride[2];
+        if (rgba) strip.plane[3] = static_cast<uint8_t*>(p.plane[3]) + static_cast<int64_t>(evenRows) * p.planeStride[3];
         const int n = LaunchEncodeGeneric(strip, hostDepth, streamHandle);
         if (n < 0) return n;
         launched += n;

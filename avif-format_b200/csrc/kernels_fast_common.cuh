@@ -30,6 +30,9 @@ struct FastEncodeParams
     int64_t strideCb;
     uint8_t* planeCr;
     int64_t strideCr;
+    uint8_t* planeA;  // RGBA hosts (kernels_fast_rgba.cu)
+    int64_t strideA;
+    int32_t premultiply;
     int32_t width;    // multiple of 4
     int32_t rowCount; // even when the chroma is vertically sub-sampled
     float pqMultiplier;
@@ -134,6 +137,10 @@ __device__ __forceinline__ void StoreTile(const FastEncodeParams& p, const float
 }
 
 } // namespace fastenc
+
+// kernels_fast_rgba.cu
+bool RgbaEncodeApplies(const fastenc::FastEncodeParams& fp);
+cudaError_t LaunchFastEncodeRgba(const fastenc::FastEncodeParams& fp, int curve, int xs, int ys, int smCount, cudaStream_t stream);
 
 // kernels_fast_flat.cu
 bool FlatEncodeApplies(const fastenc::FastEncodeParams& fp);

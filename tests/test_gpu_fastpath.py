@@ -99,6 +99,24 @@ def test_edges_and_chroma_modes(gpu, port, w, h, chroma):
                 assert (g.base[:, g.shape[1]:] == 0xCD).all(), "wrote into the row padding"
 
 
+@pytest.mark.parametrize("w,h", [(4, 2), (5, 3), (128, 2), (131, 5), (260, 8), (1024, 33)])
+@pytest.mark.parametrize("chroma", [abi.CHROMA_420, abi.CHROMA_422, abi.CHROMA_444])
+@pytest.mark.parametrize("alpha", [abi.ALPHA_STRAIGHT, abi.ALPHA_PREMULTIPLIED])
+def test_rgba32f_fast_kernel(gpu, gpu_exact, port, w, h, chroma, alpha):
+    """Float RGBA hosts (kernels_fast_rgba.cu): clamp / premultiplication before the curve, alpha plane beside Y/Cb/Cr."""
+    rng = cases.rng_for(f"rgba32_{w}x{h}_{chroma}_{alpha}")
+    rows = cases.float_host_rows(rng, h, w, 4, specials=True)
+    for depth, peak, nclx in ((12, 80, cases.NCLX_2020_PQ()), (10, 1000, None)):
+        desc = abi.EncodeDesc(w, h, 32, 4, alpha, depth, abi.TRANSFER_PQ, peak, abi.LAYOUT_PLANAR_YCBCR, chroma, abi.DOWN_FILTER_BOX, abi.GRAY16_LUT, nclx)
+        expected = port.encode(desc, rows)
+        for ctx in (gpu, gpu_exact):
+            got = ctx.encode(desc, rows, pad=5)
+            assert cases.same_planes(expected, got), (depth, peak)
+            for g in got:
+                if g is not None:
+                    assert (g.base[:, g.shape[1]:] == 0xCD).all(), "wrote into the row padding"
+
+
 def test_unaligned_device_buffers_fall_back_correctly(gpu, port):
     """Odd strides / offsets defeat the 128-bit loads: the launcher must route those calls to the generic kernel."""
     import torch
