@@ -79,10 +79,10 @@ def encode_case(name, host_depth, channels, image_depth, chroma, nclx, bytes_per
     print(json.dumps({"case": name, "ms": ms, "gpx_s": W * H / ms / 1e6, "gb_s": W * H * bytes_per_px / ms / 1e6}))
 
 
-def float_encode_case(name, channels, layout, bytes_per_px, tables, depth=12, peak=80):
+def float_encode_case(name, channels, layout, bytes_per_px, tables, depth=12, peak=80, transfer=abi.TRANSFER_PQ):
     alpha = abi.ALPHA_STRAIGHT if channels == 4 else abi.ALPHA_NONE
     nclx = abi.Nclx(1, abi.PRIMARIES_BT2020, abi.TRANSFER_CHAR_PQ, abi.MATRIX_BT2020_NCL, 1)
-    desc = abi.EncodeDesc(W, H, 32, channels, alpha, depth, abi.TRANSFER_PQ, peak, layout, abi.CHROMA_420 if layout == abi.LAYOUT_PLANAR_YCBCR else abi.CHROMA_444,
+    desc = abi.EncodeDesc(W, H, 32, channels, alpha, depth, transfer, peak, layout, abi.CHROMA_420 if layout == abi.LAYOUT_PLANAR_YCBCR else abi.CHROMA_444,
                           abi.DOWN_FILTER_BOX, abi.GRAY16_LUT, nclx)
     ctx = avifgpu.Context(0)
     ctx.set_table_autobuild(-1)
@@ -160,3 +160,5 @@ for tables in (False, True):
     float_encode_case(f"encode RGB32f -> interleaved RGB 12-bit PQ (reference layout), generic kernel, {tag} (a1)", 3, abi.LAYOUT_REFERENCE, 12 + 6, tables)
 float_encode_case("encode RGB32f -> 10-bit PQ 4:2:0, tuned kernel (config 2 at 10 bits)", 3, abi.LAYOUT_PLANAR_YCBCR, 15, True, depth=10)
 float_encode_case("encode RGB32f -> 12-bit PQ @ 1000 nit 4:2:0, tuned kernel (config 2 at another peak)", 3, abi.LAYOUT_PLANAR_YCBCR, 15, True, peak=1000)
+float_encode_case("encode RGB32f -> 12-bit SMPTE 428 4:2:0 (two-level table kernel)", 3, abi.LAYOUT_PLANAR_YCBCR, 15, True, transfer=abi.TRANSFER_SMPTE428)
+float_encode_case("encode RGB32f -> 12-bit clip 4:2:0 (no curve)", 3, abi.LAYOUT_PLANAR_YCBCR, 15, True, transfer=abi.TRANSFER_CLIP)
