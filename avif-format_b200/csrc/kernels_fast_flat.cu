@@ -91,7 +91,9 @@ __device__ __forceinline__ void BarrierWait(uint32_t barrier, uint32_t parity)
         : "memory");
 }
 
-template <int CURVE, int XS, int YS>
+// TWO_LEVEL = 0: the flat table + band bitmap.  TWO_LEVEL = 1: the per-binade two-level table (curves whose steps are too
+// dense for one bucket size, e.g. 12-bit SMPTE 428); its rare in-band samples take the exact evaluation in place.
+template <int CURVE, int XS, int YS, int TWO_LEVEL>
 __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const FastEncodeParams p, const FlatSchedule schedule)
 {
     extern __shared__ __align__(128) uint8_t sharedBytes[];
@@ -99,6 +101,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     uint64_t* barriers = reinterpret_cast<uint64_t*>(sharedBytes + kSharedLibm);
     uint8_t* stageAll = sharedBytes + kSharedLibm + kSharedBarriers;
     uint2* flatEntries = reinterpret_cast<uint2*>(sharedBytes + FlatFixedBytes());
+    uint2* octaves = reinterpret_cast<uint2*>(sharedBytes + FlatFixedBytes());            // TWO_LEVEL: 256 entries ...
+    uint32_t* bucketWords = reinterpret_cast<uint32_t*>(sharedBytes + FlatFixedBytes() + 2048); // ... then the bucket words
 
     const int lane = threadIdx.x & 31;
     // Read through a shuffle so the compiler knows the warp index (and everything derived from it: tile coordinates,
@@ -150,6 +154,18 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     }
 
     const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
+    if (TWO_LEVEL)
+    {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        {
+            octaves[i] = p.table.octaves[i];
+        }
+        for (int i = threadIdx.x; i < p.table.bucketCount; i += blockDim.x)
+        {
+            bucketWords[i] = p.table.buckets[i];
+        }
+    }
+    else
     {
         // 128 KB from L2: 128-bit copies, eight in flight per thread (the table is 16-byte aligned, count is even-padded)
         const uint4* source = reinterpret_cast<const uint4*>(p.table.flat);
@@ -203,16 +219,27 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
             {
                 const int j = 4 * q + e;
                 bool inBand;
-                codeF[j] = LookupCurveFlat(bits[e], flatEntries, flatShift, negativeLow, span, inBand);
+                if (TWO_LEVEL)
+                {
+                    codeF[j] = CodeToFloat(LookupCurveCode(bits[e], octaves, bucketWords, inBand)); // reports +inf / NaN in band itself
+                }
+                else
+                {
+                    codeF[j] = LookupCurveFlat(bits[e], flatEntries, flatShift, negativeLow, span, inBand);
+                }
                 asm("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p or.b32 %0, %0, %2; }" : "+r"(bandMask) : "r"(static_cast<uint32_t>(inBand)), "r"(1u << j));
             }
-            largest = max(largest, __vimax3_s32(static_cast<int32_t>(w.x), static_cast<int32_t>(w.y), static_cast<int32_t>(w.z)));
-            largest = max(largest, static_cast<int32_t>(w.w));
+            if (!TWO_LEVEL)
+            {
+                largest = max(largest, __vimax3_s32(static_cast<int32_t>(w.x), static_cast<int32_t>(w.y), static_cast<int32_t>(w.z)));
+                largest = max(largest, static_cast<int32_t>(w.w));
+            }
         }
 
         // ---- in-band samples: one bit of the band bitmap each, two loads in flight per lane ---------------------------
         auto stagedBits = [&](int j) { return myStage[j + (j >= 12 ? kRowSegmentWords - 12 : 0)]; };
         uint32_t lowerMask = 0; // samples whose exact code is one below the table's
+        if (!TWO_LEVEL)
         {
             uint32_t pending = bandMask;
             while (pending != 0)
@@ -246,12 +273,12 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
         }
 
         // ---- +inf / NaN (never in real frames): the exact evaluation, lane by lane ------------------------------------
-        if (__any_sync(0xffffffffu, largest > 0x7f7fffff))
+        if (__any_sync(0xffffffffu, TWO_LEVEL ? bandMask != 0 : largest > 0x7f7fffff))
         {
             for (int j = 0; j < kValuesPerLane; ++j)
             {
                 const uint32_t bits = stagedBits(j);
-                if (static_cast<int32_t>(bits) > 0x7f7fffff)
+                if (TWO_LEVEL ? ((bandMask >> j) & 1u) != 0 : static_cast<int32_t>(bits) > 0x7f7fffff)
                 {
                     const float exact = CodeToFloat(ExactCurveCode<CURVE>(__uint_as_float(bits), p.pqMultiplier, p.maxCodeFloat, t));
 #pragma unroll
@@ -295,13 +322,18 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     }
 }
 
-template <int CURVE, int XS, int YS>
+inline size_t TableSharedBytes(const FastEncodeParams& fp, bool twoLevel)
+{
+    return twoLevel ? 2048 + static_cast<size_t>(fp.table.bucketCount) * sizeof(uint32_t) : static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
+}
+
+template <int CURVE, int XS, int YS, int TWO_LEVEL>
 cudaError_t LaunchFlatKernel(const FastEncodeParams& fp, int smCount, cudaStream_t stream)
 {
-    const size_t shared = static_cast<size_t>(FlatFixedBytes()) + static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
+    const size_t shared = static_cast<size_t>(FlatFixedBytes()) + TableSharedBytes(fp, TWO_LEVEL != 0);
     static std::atomic<uint64_t> configuredDevices{ 0 }; // per instantiation
     {
-        const cudaError_t e = AllowDynamicShared(EncodeRgbF32FlatKernel<CURVE, XS, YS>, kSharedLimit, configuredDevices);
+        const cudaError_t e = AllowDynamicShared(EncodeRgbF32FlatKernel<CURVE, XS, YS, TWO_LEVEL>, kSharedLimit, configuredDevices);
         if (e != cudaSuccess)
         {
             return e;
@@ -336,31 +368,48 @@ cudaError_t LaunchFlatKernel(const FastEncodeParams& fp, int smCount, cudaStream
     advance(2 * fp.strideY, 2 * kTilePixels, schedule.advanceY);
     advance(chromaRowsPerTile * fp.strideCb, chromaTileBytes, schedule.advanceCb);
     advance(chromaRowsPerTile * fp.strideCr, chromaTileBytes, schedule.advanceCr);
-    EncodeRgbF32FlatKernel<CURVE, XS, YS><<<static_cast<unsigned>(blocks), kFlatThreads, shared, stream>>>(fp, schedule);
+    EncodeRgbF32FlatKernel<CURVE, XS, YS, TWO_LEVEL><<<static_cast<unsigned>(blocks), kFlatThreads, shared, stream>>>(fp, schedule);
     return cudaGetLastError();
 }
 
-template <int CURVE>
+template <int CURVE, int TWO_LEVEL>
 cudaError_t DispatchFlatChroma(const FastEncodeParams& fp, int xs, int ys, int smCount, cudaStream_t stream)
 {
-    if (xs == 1 && ys == 1) return LaunchFlatKernel<CURVE, 1, 1>(fp, smCount, stream);
-    if (xs == 1) return LaunchFlatKernel<CURVE, 1, 0>(fp, smCount, stream);
-    return LaunchFlatKernel<CURVE, 0, 0>(fp, smCount, stream);
+    if (xs == 1 && ys == 1) return LaunchFlatKernel<CURVE, 1, 1, TWO_LEVEL>(fp, smCount, stream);
+    if (xs == 1) return LaunchFlatKernel<CURVE, 1, 0, TWO_LEVEL>(fp, smCount, stream);
+    return LaunchFlatKernel<CURVE, 0, 0, TWO_LEVEL>(fp, smCount, stream);
 }
 
 } // namespace
 
-// True when the flat kernel can serve this table (flat variant present, bitmap built, everything fits in shared memory).
-bool FlatEncodeApplies(const FastEncodeParams& fp)
+static bool FlatTableFits(const FastEncodeParams& fp)
 {
     return fp.table.flat != nullptr && fp.table.bandBits != nullptr &&
-           static_cast<size_t>(FlatFixedBytes()) + static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4) <= static_cast<size_t>(kSharedLimit);
+           static_cast<size_t>(FlatFixedBytes()) + TableSharedBytes(fp, false) <= static_cast<size_t>(kSharedLimit);
+}
+
+static bool TwoLevelTableFits(const FastEncodeParams& fp)
+{
+    return fp.table.buckets != nullptr && fp.table.octaves != nullptr &&
+           static_cast<size_t>(FlatFixedBytes()) + TableSharedBytes(fp, true) <= static_cast<size_t>(kSharedLimit);
+}
+
+// True when the copy-engine kernel can serve this table: the flat form with its bitmap, else the two-level form, in
+// shared memory next to the staging buffers.
+bool FlatEncodeApplies(const FastEncodeParams& fp)
+{
+    return FlatTableFits(fp) || TwoLevelTableFits(fp);
 }
 
 cudaError_t LaunchFastEncodeFlat(const FastEncodeParams& fp, int curve, int xs, int ys, int smCount, cudaStream_t stream)
 {
-    if (curve == kCurveLinearToPQ) return DispatchFlatChroma<kCurveLinearToPQ>(fp, xs, ys, smCount, stream);
-    return DispatchFlatChroma<kCurveLinearToSMPTE428>(fp, xs, ys, smCount, stream);
+    if (FlatTableFits(fp))
+    {
+        if (curve == kCurveLinearToPQ) return DispatchFlatChroma<kCurveLinearToPQ, 0>(fp, xs, ys, smCount, stream);
+        return DispatchFlatChroma<kCurveLinearToSMPTE428, 0>(fp, xs, ys, smCount, stream);
+    }
+    if (curve == kCurveLinearToPQ) return DispatchFlatChroma<kCurveLinearToPQ, 1>(fp, xs, ys, smCount, stream);
+    return DispatchFlatChroma<kCurveLinearToSMPTE428, 1>(fp, xs, ys, smCount, stream);
 }
 
 } // namespace avifgpu
