@@ -14,9 +14,9 @@
 //     a two-level table: per binade (octave) a bucket size 2^S chosen so that no bucket meets two steps, per
 //     bucket one 32-bit word {k-1, offset of the band start};
 //   * the conversion kernel does two shared-memory look-ups and a handful of integer instructions per sample;
-//     samples that fall inside a (conservatively widened) band -- about 2 % of typical data -- are handed to the
-//     exact evaluation, compacted across the warp so the exact code runs at full lane occupancy;
-//   * the flat variant goes one step further: inside the band of step k the exact code is k-1 or k (neighbouring
+//     samples that fall inside a (conservatively widened) band are handed to the exact evaluation (rare for the
+//     curves that need this form: a single powf is monotone, so only the quantisation of the table itself widens);
+//   * the flat variant (one bucket size for all binades, PQ) goes one step further: inside the band of step k the exact code is k-1 or k (neighbouring
 //     bands never overlap, the builder checks), so ONE BIT per in-band float records the exact answer.  A fill
 //     kernel evaluates the exact curve for every in-band float (a few million) into a bitmap that lives in L2
 //     (1 MB for 12 bits); the conversion kernel resolves an in-band sample with one 32-bit load instead of ~150

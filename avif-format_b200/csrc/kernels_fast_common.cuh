@@ -1,5 +1,5 @@
-// kernels_fast_common.cuh -- pieces shared by the tuned float-RGB encode kernels (kernels_fast.cu: clip and two-level
-// table variants; kernels_fast_flat.cu: flat table + band bitmap + bulk-copy staging).
+// kernels_fast_common.cuh -- pieces shared by the tuned float-RGB(A) encode kernels (kernels_fast.cu: no curve;
+// kernels_fast_flat.cu: step tables + band bitmap + bulk-copy staging; kernels_fast_rgba.cu: the same look-up for RGBA).
 #ifndef AVIF_KERNELS_FAST_COMMON_CUH
 #define AVIF_KERNELS_FAST_COMMON_CUH
 
