@@ -103,11 +103,12 @@ __device__ __forceinline__ uint32_t Sample(const Raw8<SampleT>& raw, int i)
 
 constexpr float kTwo23 = 8388608.0f;
 
-// 2^23 + (uint)(0.5f + (c * scale)) as a float, for c in [0, 1]: YuvDecode.cpp:314-316 / 437-439 without the conversion
-// instruction (it issues on the quarter-rate pipe).  The sum 0.5f + c * scale is formed exactly as the reference forms
-// it (two roundings to nearest); adding 2^23 with round-toward-zero then leaves its integer part in the low mantissa
-// bits, which is the truncation of the cast.
-__device__ __forceinline__ uint32_t QuantiseBiased(float c, float scale) { return __float_as_uint(__fadd_rz(0.5f + (c * scale), kTwo23)); }
+// 2^23 + (uint)(0.5f + (c * scale)) as a float, for c in [0, 1]: YuvDecode.cpp:314-316 / 437-439 in two instructions and
+// without the conversion pipe.  The reference forms the sum with two roundings (multiply, then add); for every float c in
+// [0, 1] and scale = 255 or 32768 the single-rounding fmaf(c, scale, 0.5f) truncates to the same integer -- proven by
+// enumeration, tools/check_fused_quantiser.py -- so the sum is one FMA; adding 2^23 with round-toward-zero then leaves
+// its integer part in the low mantissa bits, which is the truncation of the cast.
+__device__ __forceinline__ uint32_t QuantiseBiased(float c, float scale) { return __float_as_uint(__fadd_rz(__fmaf_rn(c, scale, 0.5f), kTwo23)); }
 
 template <typename SampleT, int XS, int YS, int ALPHA>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSm) DecodeYccToRgbIntKernel(const IntDecodeParams p)

@@ -415,3 +415,30 @@ def test_two_devices_in_one_process(port):
             ctx.set_table_autobuild(0)
             assert cases.same_planes(expected, ctx.encode(desc, rows))
             assert cases.same_bits(decoded, ctx.decode(ddesc, planes))
+
+
+def test_every_10bit_triple_through_the_integer_decode_kernel(gpu):
+    """All 2^30 (Y, Cb, Cr) triples of 10-bit codes (32768 x 32768, 4:4:4, BT.2020 full range) -> RGB16 through the tuned
+    kernel and through the generic kernel (unaligned row pointer): identical samples.  Covers the fused-quantiser proof
+    (tools/check_fused_quantiser.py) on the device for the 32768 scale; the 8-bit sibling above covers 255."""
+    import torch
+    import avifgpu
+    dev = torch.device("cuda", gpu.device)
+    if torch.cuda.get_device_properties(dev).total_memory < 60 * 2**30:
+        pytest.skip("needs ~25 GB of device memory")
+    w = h = 1 << 15
+    desc = abi.DecodeDesc(w, h, abi.COLORSPACE_YCBCR, abi.CHROMA_444, 10, abi.ALPHA_NONE, 16, cases.NCLX_2020_PQ(1))
+    index = torch.arange(w * h, dtype=torch.int32, device=dev).view(h, w)
+    planes = [(index & 1023).to(torch.int16), ((index >> 10) & 1023).to(torch.int16), (index >> 20).to(torch.int16)]
+    del index
+    struct = avifgpu.planes_from_tensors(planes + [None])
+    fast = torch.empty((h, w * 3), dtype=torch.int16, device=dev)
+    gpu.decode_device(desc, struct, fast.data_ptr(), fast.stride(0) * 2)
+    backing = torch.empty((h, w * 3 + 8), dtype=torch.int16, device=dev)
+    exact = backing[:, 1:w * 3 + 1]
+    gpu.decode_device(desc, struct, exact.data_ptr(), exact.stride(0) * 2)
+    torch.cuda.synchronize(dev)
+    differing = 0
+    for y in range(0, h, 4096):
+        differing += int((fast[y:y + 4096] != exact[y:y + 4096]).sum().item())
+    assert differing == 0
