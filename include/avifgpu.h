@@ -42,8 +42,10 @@
 extern "C" {
 #endif
 
-#if defined(_WIN32)
+#if defined(_WIN32) && defined(AVIFGPU_BUILDING_LIBRARY)
 #define AVIFGPU_EXPORT __declspec(dllexport)
+#elif defined(_WIN32)
+#define AVIFGPU_EXPORT __declspec(dllimport) /* the plug-in (an MSVC project) consuming avifgpu.dll */
 #else
 #define AVIFGPU_EXPORT __attribute__((visibility("default")))
 #endif
