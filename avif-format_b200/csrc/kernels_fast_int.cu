@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
                     cb[r][i] = (bf - yf) * p.matrix.cbScale;
                     cr[r][i] = (rf - yf) * p.matrix.crScale;
                 }
-                yCodes[i] = BiasedToCode(BiasedTrunc(yf + 0.5f, p.biasedMax));
+                yCodes[i] = BiasedToCode(__fadd_rz(yf + 0.5f, kTwo23)); // no upper clamp: ForwardMatrixStaysInRange (launcher)
                 if (CHANNELS == 4)
                 {
                     aCodes[i] = (sizeof(HostT) == 1 && sizeof(PlaneT) == 1) ? sample(i * CHANNELS + 3)
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
         }
 
         // chroma: down-filter in float, then quantise (the offset is 0 for the identity matrix)
-        auto quantise = [&](float c) -> uint32_t { return BiasedToCode(BiasedTrunc((c + p.chromaOffset) + 0.5f, p.biasedMax)); };
+        auto quantise = [&](float c) -> uint32_t { return BiasedToCode(__fadd_rz((c + p.chromaOffset) + 0.5f, kTwo23)); };
         if (XS == 0)
         {
 #pragma unroll
@@ -590,7 +590,8 @@ int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHa
     // The biased-truncation trick needs non-negative intermediates: true for every matrix with kr, kg, kb >= 0
     // (all of H.273's); anything else takes the generic kernel.
     if (p.planar && (p.channels == 3 || p.channels == 4) && !p.premultiply && p.imageDepth <= 12 &&
-        (p.matrix.identity || (p.matrix.kr >= 0.0f && p.matrix.kg >= 0.0f && p.matrix.kb >= 0.0f && p.matrix.kr < 1.0f && p.matrix.kb < 1.0f)))
+        (p.matrix.identity || (p.matrix.kr >= 0.0f && p.matrix.kg >= 0.0f && p.matrix.kb >= 0.0f && p.matrix.kr < 1.0f && p.matrix.kb < 1.0f)) &&
+        ForwardMatrixStaysInRange(p.matrix, p.chromaOffset, static_cast<int>(p.maxCode)))
     {
         const int hostBytes = hostDepth / 8;
         const int planeBytes = p.imageDepth > 8 ? 2 : 1;
