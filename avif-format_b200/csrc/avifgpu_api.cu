@@ -30,6 +30,24 @@ int LaunchDecodeFast(const DecodeParams& params, void* stream);                 
 int LaunchDecodeFastInteger(const DecodeParams& params, void* stream);           // 0 = not applicable
 int LaunchHlgOotf(int inverse, const float luma[3], float displayGamma, float peak, const float* in, float* out, size_t pixels, void* stream);
 
+namespace
+{
+    thread_local int g_launchFailure = 0; // cudaError_t of the last failed launch on this thread, 0 = none
+}
+
+int ReportLaunchFailure(int cudaErrorCode)
+{
+    g_launchFailure = cudaErrorCode;
+    return AVIFGPU_ERR_CUDA;
+}
+
+static int TakeLaunchFailure()
+{
+    const int code = g_launchFailure;
+    g_launchFailure = 0;
+    return code;
+}
+
 int LaunchEncode(const EncodeParams& params, int hostDepth, void* stream)
 {
     int fast = LaunchEncodeFast(params, hostDepth, stream);
@@ -263,6 +281,38 @@ struct avifgpu_context
     int Fail(int status, const std::string& message)
     {
         lastError = message;
+        return status;
+    }
+
+    // A launcher returned a negative status: report the CUDA error it recorded (it has already cleared CUDA's own
+    // slot), after draining the pipeline streams so that no copy of an earlier slice is still writing into caller memory
+    // when the entry point returns.
+    int LaunchFailed(int status, const char* what)
+    {
+        const int code = TakeLaunchFailure();
+        for (cudaStream_t stream : streams)
+        {
+            if (stream)
+            {
+                cudaStreamSynchronize(stream);
+            }
+        }
+        cudaGetLastError();
+        lastError = std::string(what) + " failed: " + (code != 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : avifgpu_status_string(status));
+        return status;
+    }
+
+    // Any failure in the middle of a host-pointer call: same draining, then the status.
+    int Abandon(int status)
+    {
+        for (cudaStream_t stream : streams)
+        {
+            if (stream)
+            {
+                cudaStreamSynchronize(stream);
+            }
+        }
+        cudaGetLastError();
         return status;
     }
 
@@ -667,7 +717,7 @@ AVIFGPU_EXPORT int avifgpu_encode_rows_device(avifgpu_context* ctx, const avifgp
     const int launched = LaunchEncode(p, desc->host_depth, cuda_stream);
     if (launched < 0)
     {
-        return ctx->Cuda(cudaGetLastError(), "encode kernel launch");
+        return ctx->LaunchFailed(launched, "encode kernel launch");
     }
     ctx->launches += launched;
     return AVIFGPU_OK;
@@ -731,7 +781,7 @@ AVIFGPU_EXPORT int avifgpu_decode_rows_device(avifgpu_context* ctx, const avifgp
     const int launched = LaunchDecode(p, cuda_stream);
     if (launched < 0)
     {
-        return ctx->Cuda(cudaGetLastError(), "decode kernel launch");
+        return ctx->LaunchFailed(launched, "decode kernel launch");
     }
     ctx->launches += launched;
     return AVIFGPU_OK;
@@ -852,7 +902,7 @@ AVIFGPU_EXPORT int avifgpu_encode_rows(avifgpu_context* ctx, const avifgpu_encod
         const int launched = LaunchEncode(p, desc->host_depth, stream);
         if (launched < 0)
         {
-            return ctx->Cuda(cudaGetLastError(), "encode kernel launch");
+            return ctx->LaunchFailed(launched, "encode kernel launch");
         }
         ctx->launches += launched;
 
@@ -1010,7 +1060,7 @@ AVIFGPU_EXPORT int avifgpu_decode_rows(avifgpu_context* ctx, const avifgpu_decod
         const int launched = LaunchDecode(p, stream);
         if (launched < 0)
         {
-            return ctx->Cuda(cudaGetLastError(), "decode kernel launch");
+            return ctx->LaunchFailed(launched, "decode kernel launch");
         }
         ctx->launches += launched;
 
@@ -1121,7 +1171,7 @@ AVIFGPU_EXPORT int avifgpu_transfer_f32(avifgpu_context* ctx, int32_t function, 
                                         static_cast<float*>(ctx->transferScratch[1].ptr), n, stream);
     if (launched < 0)
     {
-        return ctx->Cuda(cudaGetLastError(), "transfer kernel launch");
+        return ctx->LaunchFailed(launched, "transfer kernel launch");
     }
     ctx->launches += launched;
     if ((status = ctx->Cuda(cudaMemcpyAsync(out, ctx->transferScratch[1].ptr, bytes, cudaMemcpyDeviceToHost, stream), "D2H")) != AVIFGPU_OK) return status;
@@ -1159,7 +1209,7 @@ AVIFGPU_EXPORT int avifgpu_hlg_ootf_f32(avifgpu_context* ctx, int32_t inverse, i
                                        static_cast<float*>(ctx->transferScratch[1].ptr), pixels, stream);
     if (launched < 0)
     {
-        return ctx->Cuda(cudaGetLastError(), "OOTF kernel launch");
+        return ctx->LaunchFailed(launched, "OOTF kernel launch");
     }
     ctx->launches += launched;
     if ((status = ctx->Cuda(cudaMemcpyAsync(rgb_out, ctx->transferScratch[1].ptr, bytes, cudaMemcpyDeviceToHost, stream), "D2H")) != AVIFGPU_OK) return status;

@@ -370,8 +370,9 @@ void FillEncodeParams(const avifgpu_encode_desc& d, EncodeParams* p)
         p->matrix.cbScale = 0.5f / (1.0f - k[2]);
         p->matrix.crScale = 0.5f / (1.0f - k[0]);
         p->matrix.identity = (d.nclx.present && d.nclx.matrix_coefficients == 0) ? 1 : 0;
-        // the decoder's chroma zero sits at max/2 (unormFloatTableUV[i] = i/max - 0.5f, YuvLookupTables.cpp:183)
-        p->chromaOffset = p->matrix.identity ? 0.0f : p->maxCodeFloat * 0.5f;
+        // H.273 full range (and libheif's RGB->YCbCr): Ccode = Clip(Round(C) + 2^(depth-1)); neutral grey sits on 2^(depth-1).
+        // (The reference DEcoder's chroma zero is max/2, YuvLookupTables.cpp:183: half a code lower -- its own business.)
+        p->chromaOffset = p->matrix.identity ? 0.0f : static_cast<float>(1u << (d.image_bit_depth - 1));
     }
 }
 

@@ -108,6 +108,11 @@ struct DecodeParams
     int32_t verifiedGreenDivision; // 1 once the context has verified the fast `/ kg` of YuvDecode.cpp:308 for this matrix, depth, range
 };
 
+// A launcher that sees a CUDA error has already consumed it (cudaGetLastError clears the slot), so it leaves the code
+// here -- a thread-local slot in avifgpu_api.cu -- and returns AVIFGPU_ERR_CUDA; the API reports it from there instead
+// of asking CUDA a second time (which would answer cudaSuccess and turn a failed launch into AVIFGPU_OK).
+int ReportLaunchFailure(int cudaErrorCode);
+
 // Launchers implemented in kernels_*.cu.  They only enqueue work on `stream` and return the number of kernels
 // launched (>= 1) or a negative avifgpu_status.
 int LaunchEncode(const EncodeParams& params, int hostDepth, void* stream);

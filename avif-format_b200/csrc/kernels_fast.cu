@@ -229,7 +229,7 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
     }
     if (e != cudaSuccess)
     {
-        return AVIFGPU_ERR_CUDA;
+        return ReportLaunchFailure(static_cast<int>(e));
     }
     int launched = 1;
 

@@ -561,7 +561,7 @@ static int LaunchDecodeStream(const DecodeParams& p, void* streamHandle)
     }
     if (e != cudaSuccess)
     {
-        return AVIFGPU_ERR_CUDA;
+        return ReportLaunchFailure(static_cast<int>(e));
     }
     int launched = 1;
     if (width8 < p.width)
@@ -648,7 +648,7 @@ int LaunchDecodeFastInteger(const DecodeParams& p, void* streamHandle)
     }
     if (e != cudaSuccess)
     {
-        return AVIFGPU_ERR_CUDA;
+        return ReportLaunchFailure(static_cast<int>(e));
     }
     int launched = 1;
     // Edges go through the generic kernel as sub-rectangles: the right strip (width % 8 columns) and, for vertically

@@ -38,15 +38,17 @@ constexpr int kSharedBarriers = 256;                     // kFlatWarps x 8 bytes
 constexpr int kSharedLimit = 227 * 1024;
 __host__ __device__ constexpr int FlatFixedBytes() { return kSharedLibm + kSharedBarriers + kFlatWarps * kStageBytesPerWarp; }
 
-// How the persistent warps walk the tiles, worked out once on the host (the grid is known at launch) so that the
-// kernel's per-tile bookkeeping is additions of launch constants.
+// How the persistent warps share the tiles, worked out once on the host (the grid is known at launch).  The image is cut
+// into `items` = tilesX columns x `segments` runs of consecutive tile rows (run lengths differ by at most one), one item
+// per warp when the grid has at least tilesX warps -- so a warp walks straight down one tile column and its per-tile
+// bookkeeping is four pointer increments by launch constants: no column wrap, no division, no per-tile schedule state.
 struct FlatSchedule
 {
-    int32_t tilesX, tileCount, warpCount;
-    int32_t stepRows, stepX;          // warpCount tiles further = stepRows tile rows down and stepX columns right ...
+    int32_t tilesX, tileRows, warpCount;
+    int32_t segments, items;          // items = tilesX * segments
+    int32_t segmentRows, longSegments; // segment s holds segmentRows (+ 1 if s < longSegments) tile rows
     int32_t lastColumnBytes;          // row-segment bytes of the last tile column (width need not be a multiple of 128)
     int32_t unpairedTileRow;          // tile row whose second image row does not exist (odd row count), or -1
-    int64_t advanceSource[2], advanceY[2], advanceCb[2], advanceCr[2]; // byte advance per step: [0] plain, [1] with a column wrap
 };
 
 __device__ __forceinline__ uint32_t SharedAddress(const void* pointer) { return static_cast<uint32_t>(__cvta_generic_to_shared(pointer)); }
@@ -114,25 +116,22 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     const uint32_t* myStage = stage + lane * 12; // row 0; row 1 is kRowSegmentWords further
 
     const int tilesX = schedule.tilesX;
-    const int tileCount = schedule.tileCount;
     const int warpCount = schedule.warpCount;
-    const int firstTile = static_cast<int>(blockIdx.x) * kFlatWarps + warpInBlock;
-    int tileRow = firstTile / tilesX;
-    int tileX = firstTile - tileRow * tilesX;
-
-    // The tile's origin in the source rows (warp-uniform byte offset) and the lane's first sample in the three planes;
-    // all advanced by launch constants.
+    const int firstItem = static_cast<int>(blockIdx.x) * kFlatWarps + warpInBlock;
     constexpr int kChromaRowsPerTile = YS ? 1 : 2;
     constexpr int kChromaTileBytes = XS ? kTilePixels : 2 * kTilePixels;
-    int64_t sourceOffset = static_cast<int64_t>(tileRow) * 2 * p.rowStride + static_cast<int64_t>(tileX) * kRowSegmentBytes;
-    uint8_t* yPointer = p.planeY + static_cast<int64_t>(tileRow) * 2 * p.strideY + static_cast<int64_t>(tileX) * (2 * kTilePixels) + lane * 8;
-    uint8_t* cbPointer = p.planeCb + static_cast<int64_t>(tileRow) * kChromaRowsPerTile * p.strideCb + static_cast<int64_t>(tileX) * kChromaTileBytes + lane * (XS ? 4 : 8);
-    uint8_t* crPointer = p.planeCr + static_cast<int64_t>(tileRow) * kChromaRowsPerTile * p.strideCr + static_cast<int64_t>(tileX) * kChromaTileBytes + lane * (XS ? 4 : 8);
 
-    // One elected lane asks the copy engine for a tile's row segments.
-    auto fetchTile = [&](int row, int column, int64_t offset)
+    // An item's tile column and its run of tile rows [rowBegin, rowEnd).
+    auto itemRows = [&](int item, int& column, int& rowBegin, int& rowEnd)
     {
-        const uint32_t bytes = column == tilesX - 1 ? static_cast<uint32_t>(schedule.lastColumnBytes) : static_cast<uint32_t>(kRowSegmentBytes);
+        const int segment = item / tilesX;
+        column = item - segment * tilesX;
+        rowBegin = segment * schedule.segmentRows + min(segment, schedule.longSegments);
+        rowEnd = rowBegin + schedule.segmentRows + (segment < schedule.longSegments ? 1 : 0);
+    };
+    // One elected lane asks the copy engine for a tile's row segments (warp-uniform arguments).
+    auto fetchTile = [&](int row, uint32_t bytes, int64_t offset)
+    {
         const bool second = row != schedule.unpairedTileRow;
         const uint8_t* source = p.rows + offset;
         BarrierExpect(barrier, second ? 2u * bytes : bytes);
@@ -142,14 +141,21 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
             BulkCopyToShared(stageAddress + kRowSegmentBytes, source + p.rowStride, bytes, barrier);
         }
     };
+    auto columnBytes = [&](int column) { return column == tilesX - 1 ? static_cast<uint32_t>(schedule.lastColumnBytes) : static_cast<uint32_t>(kRowSegmentBytes); };
+    auto sourceOffsetOf = [&](int row, int column) { return static_cast<int64_t>(row) * 2 * p.rowStride + static_cast<int64_t>(column) * kRowSegmentBytes; };
 
     if (ElectOne())
     {
         BarrierInit(barrier, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (firstTile < tileCount)
+        if (firstItem < schedule.items)
         {
-            fetchTile(tileRow, tileX, sourceOffset); // in flight while the table is staged
+            int column, rowBegin, rowEnd;
+            itemRows(firstItem, column, rowBegin, rowEnd);
+            if (rowBegin < rowEnd)
+            {
+                fetchTile(rowBegin, columnBytes(column), sourceOffsetOf(rowBegin, column)); // in flight while the table is staged
+            }
         }
     }
 
@@ -187,20 +193,26 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     uint32_t parity = 0;
 
 #pragma unroll 1
-    for (int tile = firstTile; tile < tileCount; tile += warpCount)
+    for (int item = firstItem; item < schedule.items; item += warpCount)
     {
-        const bool laneActive = tileX * kTilePixels + lane * 4 < p.width;
-        const bool secondRow = tileRow != schedule.unpairedTileRow;
-        // where this warp goes next
-        int nextRow = tileRow + schedule.stepRows;
-        int nextX = tileX + schedule.stepX;
-        const bool wraps = nextX >= tilesX;
-        if (wraps)
+        int column, rowBegin, rowEnd;
+        itemRows(item, column, rowBegin, rowEnd);
+        if (item != firstItem && rowBegin < rowEnd && ElectOne())
         {
-            nextX -= tilesX;
-            ++nextRow;
+            fetchTile(rowBegin, columnBytes(column), sourceOffsetOf(rowBegin, column)); // only grids smaller than tilesX warps get here
         }
-        const int64_t nextSourceOffset = sourceOffset + (wraps ? schedule.advanceSource[1] : schedule.advanceSource[0]);
+        const uint32_t tileBytes = columnBytes(column);
+        const bool laneActive = column * kTilePixels + lane * 4 < p.width;
+        int64_t sourceOffset = sourceOffsetOf(rowBegin, column);
+        uint8_t* yPointer = p.planeY + static_cast<int64_t>(rowBegin) * 2 * p.strideY + static_cast<int64_t>(column) * (2 * kTilePixels) + lane * 8;
+        uint8_t* cbPointer = p.planeCb + static_cast<int64_t>(rowBegin) * kChromaRowsPerTile * p.strideCb + static_cast<int64_t>(column) * kChromaTileBytes + lane * (XS ? 4 : 8);
+        uint8_t* crPointer = p.planeCr + static_cast<int64_t>(rowBegin) * kChromaRowsPerTile * p.strideCr + static_cast<int64_t>(column) * kChromaTileBytes + lane * (XS ? 4 : 8);
+
+#pragma unroll 1
+    for (int tileRow = rowBegin; tileRow < rowEnd; ++tileRow)
+    {
+        const bool secondRow = tileRow != schedule.unpairedTileRow;
+        sourceOffset += 2 * p.rowStride; // the next tile of this column
 
         BarrierWait(barrier, parity);
         parity ^= 1u;
@@ -295,9 +307,9 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
 
         // The staging buffer is free: fetch the next tile while this one goes through the matrix and the stores.
         __syncwarp();
-        if (tile + warpCount < tileCount && ElectOne())
+        if (tileRow + 1 < rowEnd && ElectOne())
         {
-            fetchTile(nextRow, nextX, nextSourceOffset);
+            fetchTile(tileRow + 1, tileBytes, sourceOffset);
         }
 
 #pragma unroll
@@ -313,12 +325,10 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
         {
             StoreTile<XS, YS>(p, codeF, yPointer, cbPointer, crPointer, secondRow);
         }
-        tileRow = nextRow;
-        tileX = nextX;
-        sourceOffset = nextSourceOffset;
-        yPointer += wraps ? schedule.advanceY[1] : schedule.advanceY[0];
-        cbPointer += wraps ? schedule.advanceCb[1] : schedule.advanceCb[0];
-        crPointer += wraps ? schedule.advanceCr[1] : schedule.advanceCr[0];
+        yPointer += 2 * p.strideY;
+        cbPointer += kChromaRowsPerTile * p.strideCb;
+        crPointer += kChromaRowsPerTile * p.strideCr;
+    }
     }
 }
 
@@ -349,25 +359,18 @@ cudaError_t LaunchFlatKernel(const FastEncodeParams& fp, int smCount, cudaStream
     {
         blocks = smCount;
     }
-    constexpr int64_t chromaRowsPerTile = YS ? 1 : 2;
-    constexpr int64_t chromaTileBytes = XS ? kTilePixels : 2 * kTilePixels;
     FlatSchedule schedule{};
     schedule.tilesX = (fp.width + kTilePixels - 1) / kTilePixels;
-    schedule.tileCount = static_cast<int32_t>(tiles);
+    schedule.tileRows = (fp.rowCount + 1) / 2;
     schedule.warpCount = static_cast<int32_t>(blocks) * kFlatWarps;
-    schedule.stepRows = schedule.warpCount / schedule.tilesX;
-    schedule.stepX = schedule.warpCount % schedule.tilesX;
+    schedule.segments = schedule.warpCount / schedule.tilesX;
+    if (schedule.segments < 1) schedule.segments = 1;
+    if (schedule.segments > schedule.tileRows) schedule.segments = schedule.tileRows;
+    schedule.items = schedule.tilesX * schedule.segments;
+    schedule.segmentRows = schedule.tileRows / schedule.segments;
+    schedule.longSegments = schedule.tileRows % schedule.segments;
     schedule.lastColumnBytes = (fp.width - (schedule.tilesX - 1) * kTilePixels) * 12;
     schedule.unpairedTileRow = (fp.rowCount & 1) ? fp.rowCount / 2 : -1;
-    const auto advance = [&](int64_t rowBytes, int64_t tileBytes, int64_t out[2])
-    {
-        out[0] = schedule.stepRows * rowBytes + schedule.stepX * tileBytes;
-        out[1] = out[0] + rowBytes - schedule.tilesX * tileBytes;
-    };
-    advance(2 * fp.rowStride, kRowSegmentBytes, schedule.advanceSource);
-    advance(2 * fp.strideY, 2 * kTilePixels, schedule.advanceY);
-    advance(chromaRowsPerTile * fp.strideCb, chromaTileBytes, schedule.advanceCb);
-    advance(chromaRowsPerTile * fp.strideCr, chromaTileBytes, schedule.advanceCr);
     EncodeRgbF32FlatKernel<CURVE, XS, YS, TWO_LEVEL><<<static_cast<unsigned>(blocks), kFlatThreads, shared, stream>>>(fp, schedule);
     return cudaGetLastError();
 }

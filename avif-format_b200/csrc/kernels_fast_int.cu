@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
         }
 
         // chroma: down-filter in float, then quantise (the offset is 0 for the identity matrix)
-        auto quantise = [&](float c) -> uint32_t { return BiasedToCode(__fadd_rz((c + p.chromaOffset) + 0.5f, kTwo23)); };
+        // upper clamp: with the H.273 offset a saturated red / blue reaches 2^depth exactly
+        auto quantise = [&](float c) -> uint32_t { return BiasedToCode(fminf(__fadd_rz((c + p.chromaOffset) + 0.5f, kTwo23), p.biasedMax)); };
         if (XS == 0)
         {
 #pragma unroll
@@ -501,9 +502,9 @@ int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHa
             return 0;
         }
         static std::atomic<uint64_t> configuredDevices{ 0 };
-        if (AllowDynamicShared(EncodeGray16LutKernel, kLutEntries * 2, configuredDevices) != cudaSuccess)
+        if (const cudaError_t configured = AllowDynamicShared(EncodeGray16LutKernel, kLutEntries * 2, configuredDevices))
         {
-            return AVIFGPU_ERR_CUDA;
+            return ReportLaunchFailure(static_cast<int>(configured));
         }
         Gray16Params gp{};
         gp.rows = static_cast<const uint8_t*>(p.rows);
@@ -514,9 +515,9 @@ int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHa
         gp.rowCount = p.rowCount;
         gp.lut = p.gray16Lut;
         EncodeGray16LutKernel<<<smCount, kLutThreads, kLutEntries * 2, stream>>>(gp);
-        if (cudaGetLastError() != cudaSuccess)
+        if (const cudaError_t launchError = cudaGetLastError())
         {
-            return AVIFGPU_ERR_CUDA;
+            return ReportLaunchFailure(static_cast<int>(launchError));
         }
         int launched = 1;
         const int covered = gp.chunksPerRow * 8;
@@ -570,7 +571,7 @@ int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHa
         }
         if (e != cudaSuccess)
         {
-            return AVIFGPU_ERR_CUDA;
+            return ReportLaunchFailure(static_cast<int>(e));
         }
         int launched = 1;
         if (width8 < p.width)
@@ -639,7 +640,7 @@ int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHa
         }
         if (e != cudaSuccess)
         {
-            return AVIFGPU_ERR_CUDA;
+            return ReportLaunchFailure(static_cast<int>(e));
         }
         int launched = 1;
         const int colBytes = p.channels * hostBytes;

@@ -585,7 +585,8 @@ int LaunchEncodeGeneric(const EncodeParams& params, int hostDepth, void* streamH
         default: EncodeReferenceLayoutKernel<float><<<grid, kThreads, 0, stream>>>(p); break;
         }
     }
-    return cudaGetLastError() == cudaSuccess ? 1 : AVIFGPU_ERR_CUDA;
+    const cudaError_t launchError = cudaGetLastError();
+    return launchError == cudaSuccess ? 1 : ReportLaunchFailure(static_cast<int>(launchError));
 }
 
 int LaunchDecodeGeneric(const DecodeParams& p, void* streamHandle)
@@ -602,7 +603,8 @@ int LaunchDecodeGeneric(const DecodeParams& p, void* streamHandle)
     case 16: DecodeKernel<uint16_t, uint16_t><<<grid, kThreads, 0, stream>>>(p); break;
     default: DecodeKernel<uint16_t, float><<<grid, kThreads, 0, stream>>>(p); break;
     }
-    return cudaGetLastError() == cudaSuccess ? 1 : AVIFGPU_ERR_CUDA;
+    const cudaError_t launchError = cudaGetLastError();
+    return launchError == cudaSuccess ? 1 : ReportLaunchFailure(static_cast<int>(launchError));
 }
 
 int LaunchTransfer(int function, float param, const float* in, float* out, size_t count, void* streamHandle)
@@ -618,7 +620,8 @@ int LaunchTransfer(int function, float param, const float* in, float* out, size_
         blocks = 148u * 16u;
     }
     TransferKernel<<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(function, param, in, out, count);
-    return cudaGetLastError() == cudaSuccess ? 1 : AVIFGPU_ERR_CUDA;
+    const cudaError_t launchError = cudaGetLastError();
+    return launchError == cudaSuccess ? 1 : ReportLaunchFailure(static_cast<int>(launchError));
 }
 
 namespace
@@ -661,7 +664,8 @@ int LaunchHlgOotf(int inverse, const float luma[3], float displayGamma, float pe
     }
     HlgOotfKernel<<<static_cast<unsigned>(blocks), kThreads, 0, static_cast<cudaStream_t>(streamHandle)>>>(inverse, luma[0], luma[1], luma[2], displayGamma, peak, in,
                                                                                                       out, pixels);
-    return cudaGetLastError() == cudaSuccess ? 1 : AVIFGPU_ERR_CUDA;
+    const cudaError_t launchError = cudaGetLastError();
+    return launchError == cudaSuccess ? 1 : ReportLaunchFailure(static_cast<int>(launchError));
 }
 
 } // namespace avifgpu

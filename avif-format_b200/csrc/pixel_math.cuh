@@ -254,8 +254,9 @@ AVIF_HD uint32_t FloatToCode(float v, float maxValue)
 }
 
 // Forward matrix, this project's definition of the stage the reference leaves to libheif (DESIGN.md "Forward
-// matrix"): the algebraic inverse of YuvDecode.cpp:555-557 on integer
-// codes, full range: Y = (kr R + kg G) + kb B, Cb = (B - Y) * 0.5f/(1-kb), Cr = (R - Y) * 0.5f/(1-kr).
+// matrix"): H.273's full-range equations on integer codes (the algebraic inverse of YuvDecode.cpp:555-557 up to the
+// chroma zero): Y = (kr R + kg G) + kb B, Cb = (B - Y) * 0.5f/(1-kb), Cr = (R - Y) * 0.5f/(1-kr); Ycode = Clip(Round(Y)),
+// Ccode = Clip(Round(C + 2^(depth-1))) with Round(v) = (int)(v + 0.5f).
 struct ForwardMatrix
 {
     float kr, kg, kb;
@@ -302,15 +303,16 @@ AVIF_HD uint32_t TruncateToCode(float v, int maxCode)
 
 AVIF_HD uint32_t QuantiseLuma(float y, int maxCode) { return TruncateToCode(y + 0.5f, maxCode); }
 
-// The same quantisers without the upper clamp, for callers that have checked ForwardMatrixStaysInRange(): the
+// The luma quantiser without the upper clamp, for callers that have checked ForwardMatrixStaysInRange(): the
 // float -> unsigned conversion already sends negatives (and NaN) to 0, and the matrix cannot reach maxCode + 1.
 #if defined(__CUDACC__)
 __device__ __forceinline__ uint32_t QuantiseLumaInRange(float y) { return __float2uint_rz(y + 0.5f); }
-__device__ __forceinline__ uint32_t QuantiseChromaInRange(float c, float chromaOffset) { return __float2uint_rz((c + chromaOffset) + 0.5f); }
 #endif
 
-// True when, for R'G'B' codes in [0, maxCode], Y + 0.5 and C + chromaOffset + 0.5 stay below maxCode + 1 with a
-// margin (0.25) far above the float rounding of the five-operation matrix and the box filter (< 0.01 at 16 bits).
+// True when, for R'G'B' codes in [0, maxCode], Y + 0.5 stays below maxCode + 1 with a margin (0.25) far above the float
+// rounding of the five-operation matrix (< 0.01 at 16 bits), and C + chromaOffset + 0.5 stays below maxCode + 2: with
+// the H.273 offset 2^(depth-1) a saturated red / blue lands exactly on 2^depth = maxCode + 1, which the tuned kernels
+// clip with one packed min; nothing may reach further.
 inline bool ForwardMatrixStaysInRange(const ForwardMatrix& m, float chromaOffset, int maxCode)
 {
     if (m.identity)
@@ -321,11 +323,10 @@ inline bool ForwardMatrixStaysInRange(const ForwardMatrix& m, float chromaOffset
     const double lumaTop = (static_cast<double>(m.kr) + m.kg + m.kb) * max + 0.5;
     const double cbTop = max * (1.0 - m.kb) * m.cbScale + chromaOffset + 0.5;
     const double crTop = max * (1.0 - m.kr) * m.crScale + chromaOffset + 0.5;
-    const double limit = max + 0.75;
-    return m.kr >= 0 && m.kg >= 0 && m.kb >= 0 && m.kb < 1 && m.kr < 1 && lumaTop < limit && cbTop < limit && crTop < limit;
+    return m.kr >= 0 && m.kg >= 0 && m.kb >= 0 && m.kb < 1 && m.kr < 1 && lumaTop < max + 0.75 && cbTop < max + 1.75 && crTop < max + 1.75;
 }
 
-// chromaOffset = max/2 as a float (the decoder's chroma zero), or 0 for the identity matrix.
+// chromaOffset = 2^(depth-1) as a float (H.273 full range), or 0 for the identity matrix.
 AVIF_HD uint32_t QuantiseChroma(float c, float chromaOffset, int maxCode) { return TruncateToCode((c + chromaOffset) + 0.5f, maxCode); }
 
 // ---- decode side: YuvLookupTables.cpp / YuvDecode.cpp -----------------------------------------------------

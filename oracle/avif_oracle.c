@@ -768,7 +768,8 @@ static void store_code(void* row, int index, int bytes_per_sample, uint16_t code
  *     Y  = (kr*R + kg*G) + kb*B
  *     Cb = (B - Y) * cb_scale,  cb_scale = 0.5f / (1 - kb)
  *     Cr = (R - Y) * cr_scale,  cr_scale = 0.5f / (1 - kr)
- *     Ycode = clamp((int)(Y + 0.5f)),  Ccode = clamp((int)((C + max/2) + 0.5f))   (max/2 = the decoder's chroma zero)
+ *     Ycode = clamp((int)(Y + 0.5f)),  Ccode = clamp((int)((C + 2^(depth-1)) + 0.5f))   (H.273 full range:
+ *     Clip(Round(C) + 2^(depth-1)), what libheif's RGB->YCbCr writes; a pure red / blue at max reaches 2^depth and is clipped)
  * Identity matrix (lossless GBR, WriteMetadata.cpp:143-146): Y = G, Cb = B, Cr = R.
  */
 typedef struct forward_matrix
@@ -824,8 +825,8 @@ static uint16_t quantise_chroma(const forward_matrix* m, float c, int depth)
     }
     else
     {
-        /* the decoder's chroma zero sits at max/2 (unormFloatTableUV[i] = i/max - 0.5f, YuvLookupTables.cpp:183) */
-        v = (int)((c + (float)((1 << depth) - 1) * 0.5f) + 0.5f);
+        /* H.273 full range: chroma zero on 2^(depth-1) (the reference decoder's own zero, max/2, is half a code lower) */
+        v = (int)((c + (float)(1 << (depth - 1))) + 0.5f);
     }
     return (uint16_t)((v < 0) ? 0 : ((v > max_code) ? max_code : v));
 }

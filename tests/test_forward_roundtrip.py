@@ -1,7 +1,15 @@
-"""Pins this project's definition of the libheif stage (forward matrix + quantisation) by a
-round trip through the reference's own decoder: RGB codes -> (forward, 4:4:4) -> Y/Cb/Cr codes -> the compiled
-reference's DecodeYUV*Row* must return the RGB codes within +-2 codes (the B channel's gain 2(1-kb) ~ 1.8 amplifies
-the +-1/2-code rounding of Cb).  Also checks the down-filter definition on flat blocks."""
+"""Pins this project's definition of the libheif stage (forward matrix + quantisation) two ways.
+
+1. Against the STANDARD, independently of any code of this repo: H.273's full-range equations evaluated here in float64
+   (E'Y = kr R + kg G + kb B, E'Cb = (B - E'Y) / (2 (1 - kb)), Ycode = Clip(Round(E'Y)), Ccode = Clip(Round(E'C) +
+   2^(depth-1))) must agree with the float32 implementation on every sample up to the one code a float32 rounding can move
+   a value sitting on a .5 boundary; and the H.273 inverse must return the RGB codes within the quantisation bound.
+2. By a round trip through the reference's own decoder (the compiled DecodeYUV*Row*).  That decoder puts the chroma zero
+   at max/2 (YuvLookupTables.cpp:183: i/max - 0.5f), half a code below H.273's 2^(depth-1), so it sees every chroma
+   sample half a code high: |error| <= (0.5 rounding + 0.5 offset) x the channel gain 2(1-kb) ~ 1.9, plus the roundings
+   of Y and of the output -- within 3 codes, and the MEAN error of B and R shows the bias (that is the decoder's doing;
+   any other AVIF decoder uses 2^(depth-1)).
+Also checks the down-filter definition on flat blocks."""
 import numpy as np
 import pytest
 
@@ -38,7 +46,57 @@ MATRICES = [("601-default", None), ("709", cases.NCLX_709()), ("2020", cases.NCL
 def test_round_trip_through_reference_decoder(port, ref, name, nclx, depth):
     err = round_trip_error(lambda d, r: port.encode(d, r), lambda d, p: ref.decode(d, p), nclx, depth, 8 if depth == 8 else 32,
                            np.random.default_rng(depth))
-    assert err <= 2.0, err
+    assert err <= 3.0, err
+
+
+def h273_forward(rgb, kr, kb, depth):
+    """H.273 section 8.3 full range, float64: rgb = (..., 3) integer codes -> integer Y, Cb, Cr codes."""
+    top = (1 << depth) - 1
+    kg = 1.0 - kr - kb
+    r, g, b = (rgb[..., i].astype(np.float64) for i in range(3))
+    y = kr * r + kg * g + kb * b
+    cb = (b - y) / (2 * (1 - kb))
+    cr = (r - y) / (2 * (1 - kr))
+    half = 1 << (depth - 1)
+    q = lambda v: np.clip(np.floor(v + 0.5), 0, top).astype(np.int64)
+    return q(y), q(cb + half), q(cr + half)
+
+
+@pytest.mark.parametrize("name,nclx", MATRICES, ids=[m[0] for m in MATRICES])
+@pytest.mark.parametrize("depth", [8, 10, 12])
+def test_forward_matrix_is_h273(port, name, nclx, depth):
+    rng = np.random.default_rng(depth * 7)
+    w, h = 96, 64
+    top = (1 << depth) - 1
+    codes = rng.integers(0, top + 1, (h, w, 3))
+    codes[0, :8] = [[top, 0, 0], [0, top, 0], [0, 0, top], [top, top, top], [0, 0, 0], [top, top, 0], [0, top, top], [top, 0, top]]
+    if depth == 8:
+        enc = abi.EncodeDesc(w, h, 8, 3, abi.ALPHA_NONE, 8, layout=abi.LAYOUT_PLANAR_YCBCR, chroma=abi.CHROMA_444, nclx=nclx)
+        y, cb, cr, _ = port.encode(enc, codes.reshape(h, w * 3).astype(np.uint8))
+    else:
+        rows = (codes.reshape(h, w * 3).astype(np.float64) / top + 0.25 / top).astype(np.float32)
+        enc = abi.EncodeDesc(w, h, 32, 3, abi.ALPHA_NONE, depth, abi.TRANSFER_CLIP, 80, abi.LAYOUT_PLANAR_YCBCR, abi.CHROMA_444, nclx=nclx)
+        y, cb, cr, _ = port.encode(enc, rows)
+    k = port.yuv_coefficients(nclx)
+    ey, ecb, ecr = h273_forward(codes, float(k[0]), float(k[2]), depth)
+    for got, expected in ((y, ey), (cb, ecb), (cr, ecr)):
+        delta = np.abs(got.astype(np.int64) - expected)
+        assert delta.max() <= 1                 # float32 vs float64 may straddle a .5 boundary ...
+        assert (delta != 0).mean() < 2e-3       # ... on a handful of samples, never systematically
+    # neutral grey sits on 2^(depth-1); saturated red / blue clip at the top code
+    assert cb[0, 3] == cr[0, 3] == 1 << (depth - 1) and cb[0, 4] == 1 << (depth - 1)
+    assert cr[0, 0] == top and cb[0, 2] == top
+    # H.273 inverse (float64) of our codes returns the RGB codes within the quantisation bound
+    kr, kb = float(k[0]), float(k[2])
+    kg = 1 - kr - kb
+    half = 1 << (depth - 1)
+    yf, cbf, crf = y.astype(np.float64), cb.astype(np.float64) - half, cr.astype(np.float64) - half
+    r = yf + 2 * (1 - kr) * crf
+    b = yf + 2 * (1 - kb) * cbf
+    g = (yf - kr * r - kb * b) / kg
+    back = np.stack([r, g, b], axis=-1)
+    inner = codes[1:]  # the constructed first row holds the clipped extremes
+    assert np.abs(back[1:] - inner).max() <= 0.5 + 0.5 * 2 * (1 - min(kr, kb)) + 0.05
 
 
 def test_identity_matrix_round_trip_is_lossless(port, ref):
@@ -75,4 +133,4 @@ def test_down_filter_definition_on_constructed_blocks(port):
 def test_gpu_round_trip_through_reference_decoder(gpu, checker, depth):
     err = round_trip_error(lambda d, r: gpu.encode(d, r), lambda d, p: checker.decode(d, p), cases.NCLX_2020_PQ(), depth,
                            8 if depth == 8 else 32, np.random.default_rng(depth + 10))
-    assert err <= 2.0, err
+    assert err <= 3.0, err
