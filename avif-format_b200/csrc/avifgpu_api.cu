@@ -15,6 +15,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace avifgpu
@@ -85,10 +86,11 @@ namespace
 {
     thread_local std::string g_creationError;
 
-    // Number of row-block slices a host-pointer call is cut into so that the H2D copy of slice i+1, the kernel
-    // of slice i and the D2H copy of slice i-1 overlap (three streams would not help: PCIe is full duplex, one
-    // copy engine per direction).
-    constexpr int kPipelineStreams = 2;
+    // A host-pointer call is cut into row-block slices that rotate through this many pipeline slots (stream + staging
+    // buffers each), so that the H2D copy of slice i+1, the kernel of slice i and the D2H copy of slice i-1 overlap.
+    // Two slots keep both copy engines busy; the third lets the host thread fill / drain a pinned bounce buffer
+    // (pageable caller memory) while the other two are on the wire.
+    constexpr int kPipelineStreams = 3;
 }
 
 struct avifgpu_context
@@ -96,6 +98,29 @@ struct avifgpu_context
     int device = -1;
     cudaStream_t streams[kPipelineStreams] = {};
     cudaEvent_t sliceDone[kPipelineStreams] = {};
+    cudaEvent_t rowsConsumed[kPipelineStreams] = {}; // encode: the slot's H2D of caller rows has finished
+
+    // Work a slot still owes the caller once its stream has drained: copies from a pinned bounce buffer into pageable
+    // caller memory (libheif's planes on the encode side, pageable host rows on the decode side).
+    struct HostCopy
+    {
+        uint8_t* target;
+        int64_t targetStride;
+        const uint8_t* source;
+        int64_t sourceStride;
+        int64_t payload;
+        int rows;
+    };
+    struct SlotState
+    {
+        bool busy = false;
+        int64_t ticket = 0;
+        std::vector<HostCopy> owed;
+    };
+    SlotState slots[kPipelineStreams];
+    int nextSlot = 0;
+    int64_t lastTicket = 0;       // ticket of the most recent host-pointer call
+    int lastRowsSlot = -1;        // slot whose rowsConsumed event covers the last H2D of the previous asynchronous encode call
     std::string lastError;
     int64_t launches = 0;
     int smCount = 0;
@@ -369,6 +394,8 @@ struct avifgpu_context
     }
 };
 
+static int RetireThrough(avifgpu_context* ctx, int64_t ticket);
+
 namespace
 {
     bool IsPinned(const void* p)
@@ -493,7 +520,8 @@ AVIFGPU_EXPORT int avifgpu_create(int device_ordinal, avifgpu_context** out_ctx)
     for (int i = 0; i < kPipelineStreams; ++i)
     {
         if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->sliceDone[i], cudaEventDisableTiming) != cudaSuccess)
+            cudaEventCreateWithFlags(&ctx->sliceDone[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->rowsConsumed[i], cudaEventDisableTiming) != cudaSuccess)
         {
             g_creationError = std::string("stream/event creation failed: ") + cudaGetErrorString(cudaGetLastError());
             avifgpu_destroy(ctx);
@@ -516,6 +544,7 @@ AVIFGPU_EXPORT void avifgpu_destroy(avifgpu_context* ctx)
     {
         if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
         if (ctx->sliceDone[i]) cudaEventDestroy(ctx->sliceDone[i]);
+        if (ctx->rowsConsumed[i]) cudaEventDestroy(ctx->rowsConsumed[i]);
         if (ctx->deviceRows[i].ptr) cudaFree(ctx->deviceRows[i].ptr);
         if (ctx->pinnedRows[i].ptr) cudaFreeHost(ctx->pinnedRows[i].ptr);
         for (int k = 0; k < AVIFGPU_MAX_PLANES; ++k)
@@ -554,7 +583,10 @@ AVIFGPU_EXPORT int avifgpu_synchronize(avifgpu_context* ctx)
         return AVIFGPU_ERR_BAD_PARAM;
     }
     DeviceGuard guard(ctx->device);
-    return ctx->Cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    const int status = ctx->Cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    const int retired = RetireThrough(ctx, ctx->lastTicket); // pays the bounce copies asynchronous calls still owe
+    ctx->lastRowsSlot = -1;
+    return status != AVIFGPU_OK ? status : retired;
 }
 
 AVIFGPU_EXPORT int avifgpu_host_alloc(avifgpu_context* ctx, size_t bytes, void** out_ptr)
@@ -787,9 +819,17 @@ AVIFGPU_EXPORT int avifgpu_decode_rows_device(avifgpu_context* ctx, const avifgp
     return AVIFGPU_OK;
 }
 
-// ---- host-pointer entry points (PCIe inside) ---------------------------------------------------------------------
+} // extern "C"
 
-// Rows per pipeline slice: big enough to amortise launch + copy latency, small enough that two slices overlap.
+// ---- host-pointer entry points (PCIe inside) ---------------------------------------------------------------------
+//
+// A call is cut into row-block slices; slice i uses pipeline slot i mod kPipelineStreams (a stream, device staging,
+// pinned bounce buffers).  Caller memory that is not page-locked is bounced through the slot's pinned buffers on BOTH
+// sides -- a copy to or from pageable memory would make the driver stage it synchronously and serialise the pipeline --
+// and the bounce -> pageable copies a slot still owes are made when the slot is retired (before it is reused, when a
+// call or a ticket is waited for).  Slots retire in issue order, so "everything up to ticket t" is a prefix.
+
+// Rows per pipeline slice: big enough to amortise launch + copy latency, small enough that the slots overlap.
 static int SliceRows(int nrows, int64_t bytesPerRow)
 {
     const int64_t target = 32ll << 20; // ~32 MiB of host rows per slice
@@ -799,8 +839,71 @@ static int SliceRows(int nrows, int64_t bytesPerRow)
     return static_cast<int>(std::min<int64_t>(rows, nrows));
 }
 
-AVIFGPU_EXPORT int avifgpu_encode_rows(avifgpu_context* ctx, const avifgpu_encode_desc* desc, const void* host_rows,
-                                       int64_t row_stride_bytes, int32_t y0, int32_t nrows, const avifgpu_planes* dst)
+static void CopyRows(uint8_t* target, int64_t targetStride, const uint8_t* source, int64_t sourceStride, int64_t payload, int rows)
+{
+    if (targetStride == payload && sourceStride == payload)
+    {
+        std::memcpy(target, source, static_cast<size_t>(payload) * rows);
+        return;
+    }
+    for (int r = 0; r < rows; ++r)
+    {
+        std::memcpy(target + static_cast<int64_t>(r) * targetStride, source + static_cast<int64_t>(r) * sourceStride, static_cast<size_t>(payload));
+    }
+}
+
+// Waits for the slot's stream work and pays what it owes the caller.
+static int RetireSlot(avifgpu_context* ctx, int slot)
+{
+    avifgpu_context::SlotState& state = ctx->slots[slot];
+    if (!state.busy)
+    {
+        return AVIFGPU_OK;
+    }
+    const int status = ctx->Cuda(cudaEventSynchronize(ctx->sliceDone[slot]), "cudaEventSynchronize");
+    if (status == AVIFGPU_OK)
+    {
+        for (const avifgpu_context::HostCopy& c : state.owed)
+        {
+            CopyRows(c.target, c.targetStride, c.source, c.sourceStride, c.payload, c.rows);
+        }
+    }
+    state.owed.clear();
+    state.busy = false;
+    return status;
+}
+
+// Retires, oldest first, every slot issued by a call with ticket <= `ticket`.
+static int RetireThrough(avifgpu_context* ctx, int64_t ticket)
+{
+    int result = AVIFGPU_OK;
+    for (int i = 0; i < kPipelineStreams; ++i)
+    {
+        const int slot = (ctx->nextSlot + i) % kPipelineStreams; // nextSlot is the oldest
+        if (ctx->slots[slot].busy && ctx->slots[slot].ticket <= ticket)
+        {
+            const int status = RetireSlot(ctx, slot);
+            if (result == AVIFGPU_OK) result = status;
+        }
+    }
+    return result;
+}
+
+// A failure in the middle of a call: nothing of this context may still be writing into caller memory on return.
+static int AbandonCall(avifgpu_context* ctx, int status)
+{
+    for (int i = 0; i < kPipelineStreams; ++i)
+    {
+        cudaStreamSynchronize(ctx->streams[i]);
+        ctx->slots[i].owed.clear();
+        ctx->slots[i].busy = false;
+    }
+    cudaGetLastError();
+    return status;
+}
+
+static int EncodeRowsHost(avifgpu_context* ctx, const avifgpu_encode_desc* desc, const void* host_rows, int64_t row_stride_bytes, int32_t y0,
+                          int32_t nrows, const avifgpu_planes* dst, bool wait, int64_t* out_ticket)
 {
     if (ctx == nullptr)
     {
@@ -823,11 +926,18 @@ AVIFGPU_EXPORT int avifgpu_encode_rows(avifgpu_context* ctx, const avifgpu_encod
     {
         return status;
     }
+    const int64_t ticket = ++ctx->lastTicket;
+    if (out_ticket != nullptr)
+    {
+        *out_ticket = ticket;
+    }
+    DeviceGuard guard(ctx->device);
     if (nrows == 0 || desc->width == 0)
     {
-        return AVIFGPU_OK;
+        return wait ? RetireThrough(ctx, ticket) : AVIFGPU_OK;
     }
     PlaneGeometry geometry[AVIFGPU_MAX_PLANES];
+    bool planePinned[AVIFGPU_MAX_PLANES] = {};
     for (int k = 0; k < AVIFGPU_MAX_PLANES; ++k)
     {
         geometry[k] = EncodePlaneGeometry(*desc, k);
@@ -835,9 +945,9 @@ AVIFGPU_EXPORT int avifgpu_encode_rows(avifgpu_context* ctx, const avifgpu_encod
         {
             return ctx->Fail(AVIFGPU_ERR_BAD_PARAM, "missing destination plane");
         }
+        planePinned[k] = geometry[k].present && IsPinned(dst->data[k]);
     }
 
-    DeviceGuard guard(ctx->device);
     base.smCount = ctx->smCount;
     if (CurveTable* table = ctx->CurveTableFor(*desc, static_cast<int64_t>(desc->width) * nrows, false))
     {
@@ -849,34 +959,37 @@ AVIFGPU_EXPORT int avifgpu_encode_rows(avifgpu_context* ctx, const avifgpu_encod
     const bool rowsPinned = IsPinned(host_rows);
     const int sliceRows = SliceRows(nrows, rowPayload);
 
-    int slot = 0;
-    for (int begin = 0; begin < nrows; begin += sliceRows, slot = (slot + 1) % kPipelineStreams)
+    // The rows handed to the PREVIOUS asynchronous call may be overwritten once this call returns: wait for their last H2D.
+    if (ctx->lastRowsSlot >= 0)
+    {
+        if ((status = ctx->Cuda(cudaEventSynchronize(ctx->rowsConsumed[ctx->lastRowsSlot]), "cudaEventSynchronize")) != AVIFGPU_OK) return AbandonCall(ctx, status);
+        ctx->lastRowsSlot = -1;
+    }
+
+    for (int begin = 0; begin < nrows; begin += sliceRows)
     {
         const int rows = std::min(sliceRows, nrows - begin);
+        const int slot = ctx->nextSlot;
         cudaStream_t stream = ctx->streams[slot];
-        // The slot's buffers are free once its previous slice has been copied back.
-        if ((status = ctx->Cuda(cudaEventSynchronize(ctx->sliceDone[slot]), "cudaEventSynchronize")) != AVIFGPU_OK) return status;
+        if ((status = RetireSlot(ctx, slot)) != AVIFGPU_OK) return AbandonCall(ctx, status);
+        ctx->nextSlot = (slot + 1) % kPipelineStreams;
 
-        if ((status = ctx->EnsureDevice(ctx->deviceRows[slot], static_cast<size_t>(deviceRowStride) * rows)) != AVIFGPU_OK) return status;
+        if ((status = ctx->EnsureDevice(ctx->deviceRows[slot], static_cast<size_t>(deviceRowStride) * rows)) != AVIFGPU_OK) return AbandonCall(ctx, status);
         const uint8_t* source = static_cast<const uint8_t*>(host_rows) + static_cast<int64_t>(begin) * row_stride_bytes;
         int64_t sourceStride = row_stride_bytes;
         if (!rowsPinned)
         {
-            // Pageable caller memory: bounce through pinned memory so the DMA is asynchronous and full speed.
-            if ((status = ctx->EnsurePinned(ctx->pinnedRows[slot], static_cast<size_t>(rowPayload) * rows)) != AVIFGPU_OK) return status;
+            if ((status = ctx->EnsurePinned(ctx->pinnedRows[slot], static_cast<size_t>(rowPayload) * rows)) != AVIFGPU_OK) return AbandonCall(ctx, status);
             uint8_t* bounce = static_cast<uint8_t*>(ctx->pinnedRows[slot].ptr);
-            for (int r = 0; r < rows; ++r)
-            {
-                std::memcpy(bounce + static_cast<int64_t>(r) * rowPayload, source + static_cast<int64_t>(r) * row_stride_bytes,
-                            static_cast<size_t>(rowPayload));
-            }
+            CopyRows(bounce, rowPayload, source, row_stride_bytes, rowPayload, rows);
             source = bounce;
             sourceStride = rowPayload;
         }
         if ((status = ctx->Cuda(cudaMemcpy2DAsync(ctx->deviceRows[slot].ptr, static_cast<size_t>(deviceRowStride), source,
                                                   static_cast<size_t>(sourceStride), static_cast<size_t>(rowPayload),
                                                   static_cast<size_t>(rows), cudaMemcpyHostToDevice, stream),
-                                "H2D rows")) != AVIFGPU_OK) return status;
+                                "H2D rows")) != AVIFGPU_OK) return AbandonCall(ctx, status);
+        if ((status = ctx->Cuda(cudaEventRecord(ctx->rowsConsumed[slot], stream), "cudaEventRecord")) != AVIFGPU_OK) return AbandonCall(ctx, status);
 
         EncodeParams p = base;
         p.rows = ctx->deviceRows[slot].ptr;
@@ -895,17 +1008,18 @@ AVIFGPU_EXPORT int avifgpu_encode_rows(avifgpu_context* ctx, const avifgpu_encod
             planePayload[k] = static_cast<int64_t>(g.widthSamples) * g.bytesPerSample;
             planeStride[k] = (planePayload[k] + 255) & ~255ll;
             planeRows[k] = (rows + g.ys) >> g.ys;
-            if ((status = ctx->EnsureDevice(ctx->devicePlanes[slot][k], static_cast<size_t>(planeStride[k]) * planeRows[k])) != AVIFGPU_OK) return status;
+            if ((status = ctx->EnsureDevice(ctx->devicePlanes[slot][k], static_cast<size_t>(planeStride[k]) * planeRows[k])) != AVIFGPU_OK) return AbandonCall(ctx, status);
             p.plane[k] = ctx->devicePlanes[slot][k].ptr;
             p.planeStride[k] = planeStride[k];
         }
         const int launched = LaunchEncode(p, desc->host_depth, stream);
         if (launched < 0)
         {
-            return ctx->LaunchFailed(launched, "encode kernel launch");
+            return AbandonCall(ctx, ctx->LaunchFailed(launched, "encode kernel launch"));
         }
         ctx->launches += launched;
 
+        avifgpu_context::SlotState& state = ctx->slots[slot];
         for (int k = 0; k < AVIFGPU_MAX_PLANES; ++k)
         {
             const PlaneGeometry& g = geometry[k];
@@ -914,22 +1028,40 @@ AVIFGPU_EXPORT int avifgpu_encode_rows(avifgpu_context* ctx, const avifgpu_encod
                 continue;
             }
             uint8_t* target = static_cast<uint8_t*>(dst->data[k]) + static_cast<int64_t>((y0 + begin) >> g.ys) * dst->stride[k];
-            if ((status = ctx->Cuda(cudaMemcpy2DAsync(target, static_cast<size_t>(dst->stride[k]), p.plane[k],
+            int64_t targetStride = dst->stride[k];
+            if (!planePinned[k])
+            {
+                // pageable plane (libheif's): land in pinned memory now, copy across when the slot retires
+                if ((status = ctx->EnsurePinned(ctx->pinnedPlanes[slot][k], static_cast<size_t>(planePayload[k]) * planeRows[k])) != AVIFGPU_OK) return AbandonCall(ctx, status);
+                uint8_t* bounce = static_cast<uint8_t*>(ctx->pinnedPlanes[slot][k].ptr);
+                state.owed.push_back(avifgpu_context::HostCopy{ target, dst->stride[k], bounce, planePayload[k], planePayload[k], planeRows[k] });
+                target = bounce;
+                targetStride = planePayload[k];
+            }
+            if ((status = ctx->Cuda(cudaMemcpy2DAsync(target, static_cast<size_t>(targetStride), p.plane[k],
                                                       static_cast<size_t>(planeStride[k]), static_cast<size_t>(planePayload[k]),
                                                       static_cast<size_t>(planeRows[k]), cudaMemcpyDeviceToHost, stream),
-                                    "D2H plane")) != AVIFGPU_OK) return status;
+                                    "D2H plane")) != AVIFGPU_OK) return AbandonCall(ctx, status);
         }
-        if ((status = ctx->Cuda(cudaEventRecord(ctx->sliceDone[slot], stream), "cudaEventRecord")) != AVIFGPU_OK) return status;
+        if ((status = ctx->Cuda(cudaEventRecord(ctx->sliceDone[slot], stream), "cudaEventRecord")) != AVIFGPU_OK) return AbandonCall(ctx, status);
+        state.busy = true;
+        state.ticket = ticket;
+        if (!wait && rowsPinned)
+        {
+            ctx->lastRowsSlot = slot; // the caller's own memory is on the wire until this event
+        }
     }
-    for (int i = 0; i < kPipelineStreams; ++i)
+    if (wait)
     {
-        if ((status = ctx->Cuda(cudaStreamSynchronize(ctx->streams[i]), "cudaStreamSynchronize")) != AVIFGPU_OK) return status;
+        ctx->lastRowsSlot = -1;
+        status = RetireThrough(ctx, ticket);
+        return status == AVIFGPU_OK ? AVIFGPU_OK : AbandonCall(ctx, status);
     }
     return AVIFGPU_OK;
 }
 
-AVIFGPU_EXPORT int avifgpu_decode_rows(avifgpu_context* ctx, const avifgpu_decode_desc* desc, const avifgpu_planes* src,
-                                       int32_t y0, int32_t nrows, void* host_rows, int64_t row_stride_bytes)
+static int DecodeRowsHost(avifgpu_context* ctx, const avifgpu_decode_desc* desc, const avifgpu_planes* src, int32_t y0, int32_t nrows,
+                          void* host_rows, int64_t row_stride_bytes, bool wait, int64_t* out_ticket)
 {
     if (ctx == nullptr)
     {
@@ -955,11 +1087,18 @@ AVIFGPU_EXPORT int avifgpu_decode_rows(avifgpu_context* ctx, const avifgpu_decod
     {
         return ctx->Fail(AVIFGPU_ERR_BAD_PARAM, "row block outside the image");
     }
+    const int64_t ticket = ++ctx->lastTicket;
+    if (out_ticket != nullptr)
+    {
+        *out_ticket = ticket;
+    }
+    DeviceGuard guard(ctx->device);
     if (nrows == 0 || desc->width == 0)
     {
-        return AVIFGPU_OK;
+        return wait ? RetireThrough(ctx, ticket) : AVIFGPU_OK;
     }
     PlaneGeometry geometry[AVIFGPU_MAX_PLANES];
+    bool planePinned[AVIFGPU_MAX_PLANES] = {};
     for (int k = 0; k < AVIFGPU_MAX_PLANES; ++k)
     {
         geometry[k] = DecodePlaneGeometry(*desc, k);
@@ -967,9 +1106,9 @@ AVIFGPU_EXPORT int avifgpu_decode_rows(avifgpu_context* ctx, const avifgpu_decod
         {
             return ctx->Fail(AVIFGPU_ERR_BAD_PARAM, "missing source plane");
         }
+        planePinned[k] = geometry[k].present && IsPinned(src->data[k]);
     }
 
-    DeviceGuard guard(ctx->device);
     base.verifiedHlgDivisions = (desc->host_depth == 32 && transfer == AVIFGPU_TRANSFER_HLG) ? ctx->VerifiedHlgDivisions() : 0;
     base.verifiedGreenDivision = ctx->VerifiedGreenDivision(base);
     const int64_t rowPayload = static_cast<int64_t>(desc->width) * DecodeHostColBytes(*desc);
@@ -977,43 +1116,13 @@ AVIFGPU_EXPORT int avifgpu_decode_rows(avifgpu_context* ctx, const avifgpu_decod
     const int sliceRows = SliceRows(nrows, rowPayload);
     const bool rowsPinned = IsPinned(host_rows);
 
-    struct Pending
-    {
-        bool active = false;
-        int begin = 0;
-        int rows = 0;
-    } pending[kPipelineStreams];
-
-    auto drain = [&](int slot) -> int
-    {
-        // Copies a finished slice from the pinned bounce buffer to pageable caller rows.
-        if (!pending[slot].active)
-        {
-            return AVIFGPU_OK;
-        }
-        int st = ctx->Cuda(cudaEventSynchronize(ctx->sliceDone[slot]), "cudaEventSynchronize");
-        if (st != AVIFGPU_OK) return st;
-        if (!rowsPinned)
-        {
-            const uint8_t* bounce = static_cast<const uint8_t*>(ctx->pinnedRows[slot].ptr);
-            uint8_t* target = static_cast<uint8_t*>(host_rows) + static_cast<int64_t>(pending[slot].begin) * row_stride_bytes;
-            for (int r = 0; r < pending[slot].rows; ++r)
-            {
-                std::memcpy(target + static_cast<int64_t>(r) * row_stride_bytes, bounce + static_cast<int64_t>(r) * rowPayload,
-                            static_cast<size_t>(rowPayload));
-            }
-        }
-        pending[slot].active = false;
-        return AVIFGPU_OK;
-    };
-
-    int slot = 0;
-    for (int begin = 0; begin < nrows; begin += sliceRows, slot = (slot + 1) % kPipelineStreams)
+    for (int begin = 0; begin < nrows; begin += sliceRows)
     {
         const int rows = std::min(sliceRows, nrows - begin);
+        const int slot = ctx->nextSlot;
         cudaStream_t stream = ctx->streams[slot];
-        if ((status = drain(slot)) != AVIFGPU_OK) return status;
-        if ((status = ctx->Cuda(cudaEventSynchronize(ctx->sliceDone[slot]), "cudaEventSynchronize")) != AVIFGPU_OK) return status;
+        if ((status = RetireSlot(ctx, slot)) != AVIFGPU_OK) return AbandonCall(ctx, status);
+        ctx->nextSlot = (slot + 1) % kPipelineStreams;
 
         const int yFirst = y0 + begin;
         DecodeParams p = base;
@@ -1032,59 +1141,402 @@ AVIFGPU_EXPORT int avifgpu_decode_rows(avifgpu_context* ctx, const avifgpu_decod
             const int planeRows = lastRow - firstRow + 1;
             const int64_t payload = static_cast<int64_t>(g.widthSamples) * g.bytesPerSample;
             const int64_t stride = (payload + 255) & ~255ll;
-            if ((status = ctx->EnsureDevice(ctx->devicePlanes[slot][k], static_cast<size_t>(stride) * planeRows)) != AVIFGPU_OK) return status;
+            if ((status = ctx->EnsureDevice(ctx->devicePlanes[slot][k], static_cast<size_t>(stride) * planeRows)) != AVIFGPU_OK) return AbandonCall(ctx, status);
             const uint8_t* source = static_cast<const uint8_t*>(src->data[k]) + static_cast<int64_t>(firstRow) * src->stride[k];
             int64_t sourceStride = src->stride[k];
-            if (!IsPinned(source))
+            if (!planePinned[k])
             {
-                if ((status = ctx->EnsurePinned(ctx->pinnedPlanes[slot][k], static_cast<size_t>(payload) * planeRows)) != AVIFGPU_OK) return status;
+                if ((status = ctx->EnsurePinned(ctx->pinnedPlanes[slot][k], static_cast<size_t>(payload) * planeRows)) != AVIFGPU_OK) return AbandonCall(ctx, status);
                 uint8_t* bounce = static_cast<uint8_t*>(ctx->pinnedPlanes[slot][k].ptr);
-                for (int r = 0; r < planeRows; ++r)
-                {
-                    std::memcpy(bounce + static_cast<int64_t>(r) * payload, source + static_cast<int64_t>(r) * src->stride[k],
-                                static_cast<size_t>(payload));
-                }
+                CopyRows(bounce, payload, source, src->stride[k], payload, planeRows);
                 source = bounce;
                 sourceStride = payload;
             }
             if ((status = ctx->Cuda(cudaMemcpy2DAsync(ctx->devicePlanes[slot][k].ptr, static_cast<size_t>(stride), source,
                                                       static_cast<size_t>(sourceStride), static_cast<size_t>(payload),
                                                       static_cast<size_t>(planeRows), cudaMemcpyHostToDevice, stream),
-                                    "H2D plane")) != AVIFGPU_OK) return status;
+                                    "H2D plane")) != AVIFGPU_OK) return AbandonCall(ctx, status);
             p.plane[k] = ctx->devicePlanes[slot][k].ptr;
             p.planeStride[k] = stride;
         }
-        if ((status = ctx->EnsureDevice(ctx->deviceRows[slot], static_cast<size_t>(deviceRowStride) * rows)) != AVIFGPU_OK) return status;
+        if ((status = ctx->EnsureDevice(ctx->deviceRows[slot], static_cast<size_t>(deviceRowStride) * rows)) != AVIFGPU_OK) return AbandonCall(ctx, status);
         p.rows = ctx->deviceRows[slot].ptr;
         p.rowStride = deviceRowStride;
         const int launched = LaunchDecode(p, stream);
         if (launched < 0)
         {
-            return ctx->LaunchFailed(launched, "decode kernel launch");
+            return AbandonCall(ctx, ctx->LaunchFailed(launched, "decode kernel launch"));
         }
         ctx->launches += launched;
 
+        avifgpu_context::SlotState& state = ctx->slots[slot];
         uint8_t* target = static_cast<uint8_t*>(host_rows) + static_cast<int64_t>(begin) * row_stride_bytes;
         int64_t targetStride = row_stride_bytes;
         if (!rowsPinned)
         {
-            if ((status = ctx->EnsurePinned(ctx->pinnedRows[slot], static_cast<size_t>(rowPayload) * rows)) != AVIFGPU_OK) return status;
-            target = static_cast<uint8_t*>(ctx->pinnedRows[slot].ptr);
+            if ((status = ctx->EnsurePinned(ctx->pinnedRows[slot], static_cast<size_t>(rowPayload) * rows)) != AVIFGPU_OK) return AbandonCall(ctx, status);
+            uint8_t* bounce = static_cast<uint8_t*>(ctx->pinnedRows[slot].ptr);
+            state.owed.push_back(avifgpu_context::HostCopy{ target, row_stride_bytes, bounce, rowPayload, rowPayload, rows });
+            target = bounce;
             targetStride = rowPayload;
         }
         if ((status = ctx->Cuda(cudaMemcpy2DAsync(target, static_cast<size_t>(targetStride), ctx->deviceRows[slot].ptr,
                                                   static_cast<size_t>(deviceRowStride), static_cast<size_t>(rowPayload),
                                                   static_cast<size_t>(rows), cudaMemcpyDeviceToHost, stream),
-                                "D2H rows")) != AVIFGPU_OK) return status;
-        if ((status = ctx->Cuda(cudaEventRecord(ctx->sliceDone[slot], stream), "cudaEventRecord")) != AVIFGPU_OK) return status;
-        pending[slot].active = true;
-        pending[slot].begin = begin;
-        pending[slot].rows = rows;
+                                "D2H rows")) != AVIFGPU_OK) return AbandonCall(ctx, status);
+        if ((status = ctx->Cuda(cudaEventRecord(ctx->sliceDone[slot], stream), "cudaEventRecord")) != AVIFGPU_OK) return AbandonCall(ctx, status);
+        state.busy = true;
+        state.ticket = ticket;
     }
-    for (int i = 0; i < kPipelineStreams; ++i)
+    if (wait)
     {
-        if ((status = drain(i)) != AVIFGPU_OK) return status;
-        if ((status = ctx->Cuda(cudaStreamSynchronize(ctx->streams[i]), "cudaStreamSynchronize")) != AVIFGPU_OK) return status;
+        status = RetireThrough(ctx, ticket);
+        return status == AVIFGPU_OK ? AVIFGPU_OK : AbandonCall(ctx, status);
+    }
+    return AVIFGPU_OK;
+}
+
+extern "C" {
+
+AVIFGPU_EXPORT int avifgpu_encode_rows(avifgpu_context* ctx, const avifgpu_encode_desc* desc, const void* host_rows,
+                                       int64_t row_stride_bytes, int32_t y0, int32_t nrows, const avifgpu_planes* dst)
+{
+    return EncodeRowsHost(ctx, desc, host_rows, row_stride_bytes, y0, nrows, dst, true, nullptr);
+}
+
+AVIFGPU_EXPORT int avifgpu_decode_rows(avifgpu_context* ctx, const avifgpu_decode_desc* desc, const avifgpu_planes* src,
+                                       int32_t y0, int32_t nrows, void* host_rows, int64_t row_stride_bytes)
+{
+    return DecodeRowsHost(ctx, desc, src, y0, nrows, host_rows, row_stride_bytes, true, nullptr);
+}
+
+AVIFGPU_EXPORT int avifgpu_encode_rows_async(avifgpu_context* ctx, const avifgpu_encode_desc* desc, const void* host_rows,
+                                             int64_t row_stride_bytes, int32_t y0, int32_t nrows, const avifgpu_planes* dst,
+                                             int64_t* out_ticket)
+{
+    return EncodeRowsHost(ctx, desc, host_rows, row_stride_bytes, y0, nrows, dst, false, out_ticket);
+}
+
+AVIFGPU_EXPORT int avifgpu_decode_rows_async(avifgpu_context* ctx, const avifgpu_decode_desc* desc, const avifgpu_planes* src,
+                                             int32_t y0, int32_t nrows, void* host_rows, int64_t row_stride_bytes, int64_t* out_ticket)
+{
+    return DecodeRowsHost(ctx, desc, src, y0, nrows, host_rows, row_stride_bytes, false, out_ticket);
+}
+
+AVIFGPU_EXPORT int avifgpu_wait(avifgpu_context* ctx, int64_t ticket)
+{
+    if (ctx == nullptr)
+    {
+        return AVIFGPU_ERR_BAD_PARAM;
+    }
+    DeviceGuard guard(ctx->device);
+    if (ticket <= 0 || ticket >= ctx->lastTicket)
+    {
+        ticket = ctx->lastTicket;
+        if (ctx->lastRowsSlot >= 0)
+        {
+            ctx->lastRowsSlot = -1; // everything is about to be drained
+        }
+    }
+    const int status = RetireThrough(ctx, ticket);
+    return status == AVIFGPU_OK ? AVIFGPU_OK : AbandonCall(ctx, status);
+}
+
+// ---- several GPUs of one box -----------------------------------------------------------------------------------------
+
+} // extern "C"
+
+struct avifgpu_shard_group
+{
+    std::vector<avifgpu_context*> members;
+    std::vector<int> devices;
+    std::vector<uint8_t> peer; // peer[from * n + to]
+    std::string lastError;
+
+    int Fail(int status, const std::string& message)
+    {
+        lastError = message;
+        return status;
+    }
+
+    // Runs work(r) for every member on its own host thread (each drives its own device and PCIe link); returns the
+    // first failure and keeps its message.
+    template <typename Work>
+    int ForEachMember(Work work)
+    {
+        const int n = static_cast<int>(members.size());
+        std::vector<int> status(n, AVIFGPU_OK);
+        std::vector<std::thread> threads;
+        threads.reserve(n > 0 ? n - 1 : 0);
+        for (int r = 1; r < n; ++r)
+        {
+            threads.emplace_back([&, r] { status[r] = work(r); });
+        }
+        if (n > 0)
+        {
+            status[0] = work(0);
+        }
+        for (std::thread& t : threads)
+        {
+            t.join();
+        }
+        for (int r = 0; r < n; ++r)
+        {
+            if (status[r] != AVIFGPU_OK)
+            {
+                return Fail(status[r], "member " + std::to_string(r) + " (device " + std::to_string(devices[r]) + "): " + members[r]->lastError);
+            }
+        }
+        return AVIFGPU_OK;
+    }
+};
+
+static void RowBlocks(int y0, int nrows, int parts, int32_t* outY0, int32_t* outRows)
+{
+    // inner boundaries at even image rows: a 2x2 chroma site never straddles two blocks (4:2:0), and the same split
+    // serves every other layout
+    int previous = y0;
+    for (int i = 0; i < parts; ++i)
+    {
+        int end = (i == parts - 1) ? y0 + nrows : y0 + static_cast<int>((static_cast<int64_t>(nrows) * (i + 1)) / parts);
+        if (i != parts - 1)
+        {
+            end &= ~1;
+        }
+        end = std::min(std::max(end, previous), y0 + nrows);
+        outY0[i] = previous;
+        outRows[i] = end - previous;
+        previous = end;
+    }
+}
+
+extern "C" {
+
+AVIFGPU_EXPORT int avifgpu_shard_row_blocks(int32_t y0, int32_t nrows, int32_t parts, int32_t* out_y0, int32_t* out_nrows)
+{
+    if (parts <= 0 || nrows < 0 || y0 < 0 || out_y0 == nullptr || out_nrows == nullptr)
+    {
+        return AVIFGPU_ERR_BAD_PARAM;
+    }
+    RowBlocks(y0, nrows, parts, out_y0, out_nrows);
+    return AVIFGPU_OK;
+}
+
+AVIFGPU_EXPORT int avifgpu_shard_group_create(const int32_t* device_ordinals, int32_t count, avifgpu_shard_group** out_group)
+{
+    if (out_group == nullptr)
+    {
+        g_creationError = "out_group is NULL";
+        return AVIFGPU_ERR_BAD_PARAM;
+    }
+    *out_group = nullptr;
+    if (device_ordinals == nullptr || count <= 0 || count > 64)
+    {
+        g_creationError = "a shard group needs 1..64 device ordinals";
+        return AVIFGPU_ERR_BAD_PARAM;
+    }
+    for (int i = 0; i < count; ++i)
+    {
+        for (int j = 0; j < i; ++j)
+        {
+            if (device_ordinals[i] == device_ordinals[j])
+            {
+                g_creationError = "device ordinals of a shard group must be distinct";
+                return AVIFGPU_ERR_BAD_PARAM;
+            }
+        }
+    }
+    avifgpu_shard_group* group = new (std::nothrow) avifgpu_shard_group();
+    if (group == nullptr)
+    {
+        g_creationError = "out of host memory";
+        return AVIFGPU_ERR_OOM;
+    }
+    for (int i = 0; i < count; ++i)
+    {
+        avifgpu_context* ctx = nullptr;
+        const int status = avifgpu_create(device_ordinals[i], &ctx);
+        if (status != AVIFGPU_OK)
+        {
+            avifgpu_shard_group_destroy(group);
+            return status; // g_creationError set by avifgpu_create
+        }
+        group->members.push_back(ctx);
+        group->devices.push_back(device_ordinals[i]);
+    }
+    group->peer.assign(static_cast<size_t>(count) * count, 0);
+    for (int from = 0; from < count; ++from)
+    {
+        DeviceGuard guard(group->devices[from]);
+        for (int to = 0; to < count; ++to)
+        {
+            if (from == to)
+            {
+                group->peer[from * count + to] = 1;
+                continue;
+            }
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, group->devices[from], group->devices[to]) != cudaSuccess || !can)
+            {
+                cudaGetLastError();
+                continue;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(group->devices[to], 0);
+            if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled)
+            {
+                group->peer[from * count + to] = 1;
+            }
+            cudaGetLastError();
+        }
+    }
+    *out_group = group;
+    return AVIFGPU_OK;
+}
+
+AVIFGPU_EXPORT void avifgpu_shard_group_destroy(avifgpu_shard_group* group)
+{
+    if (group == nullptr)
+    {
+        return;
+    }
+    for (avifgpu_context* ctx : group->members)
+    {
+        avifgpu_destroy(ctx);
+    }
+    delete group;
+}
+
+AVIFGPU_EXPORT int32_t avifgpu_shard_group_size(const avifgpu_shard_group* group) { return group ? static_cast<int32_t>(group->members.size()) : 0; }
+
+AVIFGPU_EXPORT avifgpu_context* avifgpu_shard_group_context(avifgpu_shard_group* group, int32_t index)
+{
+    return (group != nullptr && index >= 0 && index < static_cast<int32_t>(group->members.size())) ? group->members[index] : nullptr;
+}
+
+AVIFGPU_EXPORT int avifgpu_shard_group_peer_access(const avifgpu_shard_group* group, int32_t from, int32_t to)
+{
+    const int n = group ? static_cast<int>(group->members.size()) : 0;
+    return (from >= 0 && to >= 0 && from < n && to < n) ? group->peer[from * n + to] : 0;
+}
+
+AVIFGPU_EXPORT const char* avifgpu_shard_group_last_error(const avifgpu_shard_group* group)
+{
+    return group ? group->lastError.c_str() : g_creationError.c_str();
+}
+
+AVIFGPU_EXPORT int avifgpu_shard_group_prepare_encode(avifgpu_shard_group* group, const avifgpu_encode_desc* desc)
+{
+    if (group == nullptr)
+    {
+        return AVIFGPU_ERR_BAD_PARAM;
+    }
+    return group->ForEachMember([&](int r) { return avifgpu_prepare_encode(group->members[r], desc, nullptr); });
+}
+
+AVIFGPU_EXPORT int avifgpu_shard_group_synchronize(avifgpu_shard_group* group)
+{
+    if (group == nullptr)
+    {
+        return AVIFGPU_ERR_BAD_PARAM;
+    }
+    int result = AVIFGPU_OK;
+    for (size_t r = 0; r < group->members.size(); ++r)
+    {
+        const int status = avifgpu_synchronize(group->members[r]);
+        if (status != AVIFGPU_OK && result == AVIFGPU_OK)
+        {
+            result = group->Fail(status, "member " + std::to_string(r) + ": " + group->members[r]->lastError);
+        }
+    }
+    return result;
+}
+
+AVIFGPU_EXPORT int avifgpu_encode_rows_sharded(avifgpu_shard_group* group, const avifgpu_encode_desc* desc, const void* host_rows,
+                                               int64_t row_stride_bytes, int32_t y0, int32_t nrows, const avifgpu_planes* dst)
+{
+    if (group == nullptr)
+    {
+        return AVIFGPU_ERR_BAD_PARAM;
+    }
+    const int n = static_cast<int>(group->members.size());
+    if (nrows < 0 || y0 < 0)
+    {
+        return group->Fail(AVIFGPU_ERR_BAD_PARAM, "row block outside the image");
+    }
+    std::vector<int32_t> blockY0(n), blockRows(n);
+    RowBlocks(y0, nrows, n, blockY0.data(), blockRows.data());
+    return group->ForEachMember([&](int r) -> int
+    {
+        if (blockRows[r] == 0 && !(r == 0 && nrows == 0))
+        {
+            return AVIFGPU_OK;
+        }
+        const uint8_t* rows = host_rows ? static_cast<const uint8_t*>(host_rows) + static_cast<int64_t>(blockY0[r] - y0) * row_stride_bytes : nullptr;
+        return avifgpu_encode_rows(group->members[r], desc, rows, row_stride_bytes, blockY0[r], blockRows[r], dst);
+    });
+}
+
+AVIFGPU_EXPORT int avifgpu_decode_rows_sharded(avifgpu_shard_group* group, const avifgpu_decode_desc* desc, const avifgpu_planes* src,
+                                               int32_t y0, int32_t nrows, void* host_rows, int64_t row_stride_bytes)
+{
+    if (group == nullptr)
+    {
+        return AVIFGPU_ERR_BAD_PARAM;
+    }
+    const int n = static_cast<int>(group->members.size());
+    if (nrows < 0 || y0 < 0)
+    {
+        return group->Fail(AVIFGPU_ERR_BAD_PARAM, "row block outside the image");
+    }
+    std::vector<int32_t> blockY0(n), blockRows(n);
+    RowBlocks(y0, nrows, n, blockY0.data(), blockRows.data());
+    return group->ForEachMember([&](int r) -> int
+    {
+        if (blockRows[r] == 0 && !(r == 0 && nrows == 0))
+        {
+            return AVIFGPU_OK;
+        }
+        uint8_t* rows = host_rows ? static_cast<uint8_t*>(host_rows) + static_cast<int64_t>(blockY0[r] - y0) * row_stride_bytes : nullptr;
+        return avifgpu_decode_rows(group->members[r], desc, src, blockY0[r], blockRows[r], rows, row_stride_bytes);
+    });
+}
+
+AVIFGPU_EXPORT int avifgpu_encode_rows_sharded_device(avifgpu_shard_group* group, const avifgpu_encode_desc* desc,
+                                                      const void* const* device_rows, const int64_t* row_stride_bytes,
+                                                      const avifgpu_planes* owner_planes, int32_t owner)
+{
+    if (group == nullptr)
+    {
+        return AVIFGPU_ERR_BAD_PARAM;
+    }
+    const int n = static_cast<int>(group->members.size());
+    if (desc == nullptr || device_rows == nullptr || row_stride_bytes == nullptr || owner_planes == nullptr || owner < 0 || owner >= n)
+    {
+        return group->Fail(AVIFGPU_ERR_BAD_PARAM, "NULL argument or owner outside the group");
+    }
+    std::vector<int32_t> blockY0(n), blockRows(n);
+    RowBlocks(0, desc->height, n, blockY0.data(), blockRows.data());
+    for (int r = 0; r < n; ++r)
+    {
+        if (blockRows[r] > 0 && !group->peer[r * n + owner])
+        {
+            return group->Fail(AVIFGPU_ERR_UNSUPPORTED, "member " + std::to_string(r) + " has no peer access to the owner's memory");
+        }
+    }
+    // Launches are asynchronous: a plain loop enqueues all of them in microseconds, each on its member's own stream.
+    for (int r = 0; r < n; ++r)
+    {
+        if (blockRows[r] == 0)
+        {
+            continue;
+        }
+        avifgpu_context* ctx = group->members[r];
+        const int status = avifgpu_encode_rows_device(ctx, desc, device_rows[r], row_stride_bytes[r], blockY0[r], blockRows[r], owner_planes,
+                                                      ctx->streams[0]);
+        if (status != AVIFGPU_OK)
+        {
+            return group->Fail(status, "member " + std::to_string(r) + ": " + ctx->lastError);
+        }
     }
     return AVIFGPU_OK;
 }

@@ -72,8 +72,39 @@ def library():
     sig("avifgpu_prepare_encode", C.c_int, [ctx_p, C.POINTER(abi.EncodeDesc), C.POINTER(abi.CurveStats)])
     sig("avifgpu_set_table_autobuild", C.c_int, [ctx_p, C.c_int64])
     sig("avifgpu_hlg_ootf_f32", C.c_int, [ctx_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t])
+    sig("avifgpu_encode_rows_async", C.c_int,
+        [ctx_p, C.POINTER(abi.EncodeDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(abi.Planes), C.POINTER(C.c_int64)])
+    sig("avifgpu_decode_rows_async", C.c_int,
+        [ctx_p, C.POINTER(abi.DecodeDesc), C.POINTER(abi.Planes), C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)])
+    sig("avifgpu_wait", C.c_int, [ctx_p, C.c_int64])
+    group_p = C.c_void_p
+    sig("avifgpu_shard_group_create", C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(group_p)])
+    sig("avifgpu_shard_group_destroy", None, [group_p])
+    sig("avifgpu_shard_group_size", C.c_int32, [group_p])
+    sig("avifgpu_shard_group_context", ctx_p, [group_p, C.c_int32])
+    sig("avifgpu_shard_group_peer_access", C.c_int, [group_p, C.c_int32, C.c_int32])
+    sig("avifgpu_shard_group_last_error", C.c_char_p, [group_p])
+    sig("avifgpu_shard_group_prepare_encode", C.c_int, [group_p, C.POINTER(abi.EncodeDesc)])
+    sig("avifgpu_shard_group_synchronize", C.c_int, [group_p])
+    sig("avifgpu_shard_row_blocks", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)])
+    sig("avifgpu_encode_rows_sharded", C.c_int,
+        [group_p, C.POINTER(abi.EncodeDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(abi.Planes)])
+    sig("avifgpu_decode_rows_sharded", C.c_int,
+        [group_p, C.POINTER(abi.DecodeDesc), C.POINTER(abi.Planes), C.c_int32, C.c_int32, C.c_void_p, C.c_int64])
+    sig("avifgpu_encode_rows_sharded_device", C.c_int,
+        [group_p, C.POINTER(abi.EncodeDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(abi.Planes), C.c_int32])
     _lib = lib
     return lib
+
+
+def shard_row_blocks(y0, nrows, parts):
+    """[(y0, rows)] * parts as avifgpu_shard_row_blocks cuts rows [y0, y0 + nrows) (pure host arithmetic)."""
+    starts = (C.c_int32 * parts)()
+    counts = (C.c_int32 * parts)()
+    status = library().avifgpu_shard_row_blocks(y0, nrows, parts, starts, counts)
+    if status != 0:
+        raise AvifGpuError(status, "avifgpu_shard_row_blocks")
+    return [(int(starts[i]), int(counts[i])) for i in range(parts)]
 
 
 EXPORTED_SYMBOLS = [
@@ -84,6 +115,11 @@ EXPORTED_SYMBOLS = [
     "avifgpu_build_yuv_tables", "avifgpu_encode_rows", "avifgpu_decode_rows", "avifgpu_encode_rows_device",
     "avifgpu_decode_rows_device", "avifgpu_transfer_f32", "avifgpu_prepare_encode", "avifgpu_set_table_autobuild",
     "avifgpu_hlg_ootf_f32",
+    "avifgpu_encode_rows_async", "avifgpu_decode_rows_async", "avifgpu_wait",
+    "avifgpu_shard_group_create", "avifgpu_shard_group_destroy", "avifgpu_shard_group_size", "avifgpu_shard_group_context",
+    "avifgpu_shard_group_peer_access", "avifgpu_shard_group_last_error", "avifgpu_shard_group_prepare_encode",
+    "avifgpu_shard_group_synchronize", "avifgpu_shard_row_blocks", "avifgpu_encode_rows_sharded", "avifgpu_decode_rows_sharded",
+    "avifgpu_encode_rows_sharded_device",
 ]
 
 
@@ -195,6 +231,26 @@ class Context:
                                                  out.strides[0]))
         return out
 
+    def encode_async(self, desc, rows, planes, y0=0, nrows=None):
+        """avifgpu_encode_rows_async into caller-provided planes; returns the ticket."""
+        nrows = desc.height - y0 if nrows is None else nrows
+        p = abi.planes_from_arrays(planes)
+        ticket = C.c_int64()
+        self._check(self.lib.avifgpu_encode_rows_async(self.handle, C.byref(desc), rows.ctypes.data, rows.strides[0], y0, nrows, C.byref(p),
+                                                       C.byref(ticket)))
+        return ticket.value
+
+    def decode_async(self, desc, planes, out, y0=0, nrows=None):
+        nrows = desc.height - y0 if nrows is None else nrows
+        p = abi.planes_from_arrays(planes)
+        ticket = C.c_int64()
+        self._check(self.lib.avifgpu_decode_rows_async(self.handle, C.byref(desc), C.byref(p), y0, nrows, out.ctypes.data, out.strides[0],
+                                                       C.byref(ticket)))
+        return ticket.value
+
+    def wait(self, ticket=0):
+        self._check(self.lib.avifgpu_wait(self.handle, ticket))
+
     def set_table_autobuild(self, pixels):
         """After how many pixels of one configuration the step tables are built automatically (0 = at first use,
         negative = never); see avifgpu_set_table_autobuild."""
@@ -230,6 +286,80 @@ class Context:
         nrows = desc.height - y0 if nrows is None else nrows
         self._check(self.lib.avifgpu_decode_rows_device(self.handle, C.byref(desc), C.byref(planes_struct), y0, nrows,
                                                         rows_ptr, row_stride, stream))
+
+
+class ShardGroup:
+    """avifgpu_shard_group: one context per device of this process, row blocks split between them."""
+
+    def __init__(self, devices):
+        self.lib = library()
+        devices = list(devices)
+        ordinals = (C.c_int32 * len(devices))(*devices)
+        handle = C.c_void_p()
+        status = self.lib.avifgpu_shard_group_create(ordinals, len(devices), C.byref(handle))
+        if status != 0:
+            raise AvifGpuError(status, self.lib.avifgpu_shard_group_last_error(None).decode("utf-8", "replace"))
+        self.handle = handle
+        self.devices = devices
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.avifgpu_shard_group_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, status):
+        if status != 0:
+            raise AvifGpuError(status, self.lib.avifgpu_shard_group_last_error(self.handle).decode("utf-8", "replace"))
+
+    def size(self):
+        return int(self.lib.avifgpu_shard_group_size(self.handle))
+
+    def peer_access(self, source, target):
+        return bool(self.lib.avifgpu_shard_group_peer_access(self.handle, source, target))
+
+    def launch_count(self):
+        return sum(int(self.lib.avifgpu_launch_count(self.lib.avifgpu_shard_group_context(self.handle, i))) for i in range(self.size()))
+
+    def prepare_encode(self, desc):
+        self._check(self.lib.avifgpu_shard_group_prepare_encode(self.handle, C.byref(desc)))
+
+    def synchronize(self):
+        self._check(self.lib.avifgpu_shard_group_synchronize(self.handle))
+
+    def encode(self, desc, rows, y0=0, nrows=None, planes=None):
+        nrows = desc.height - y0 if nrows is None else nrows
+        assert rows.dtype == abi.host_dtype(desc.host_depth) and rows.ndim == 2
+        if planes is None:
+            planes = alloc_planes(abi.encode_plane_shapes(desc), abi.code_dtype(desc.image_bit_depth))
+        p = abi.planes_from_arrays(planes)
+        self._check(self.lib.avifgpu_encode_rows_sharded(self.handle, C.byref(desc), rows.ctypes.data, rows.strides[0], y0, nrows, C.byref(p)))
+        return planes
+
+    def decode(self, desc, planes, y0=0, nrows=None, out=None):
+        nrows = desc.height - y0 if nrows is None else nrows
+        if out is None:
+            out = np.zeros((nrows, desc.width * abi.decode_host_channels(desc)), abi.host_dtype(desc.host_depth))
+        p = abi.planes_from_arrays(planes)
+        self._check(self.lib.avifgpu_decode_rows_sharded(self.handle, C.byref(desc), C.byref(p), y0, nrows, out.ctypes.data, out.strides[0]))
+        return out
+
+    def encode_device(self, desc, row_pointers, row_strides, owner_planes, owner=0):
+        n = self.size()
+        pointers = (C.c_void_p * n)(*[int(v) if v else None for v in row_pointers])
+        strides = (C.c_int64 * n)(*[int(v) for v in row_strides])
+        self._check(self.lib.avifgpu_encode_rows_sharded_device(self.handle, C.byref(desc), pointers, strides, C.byref(owner_planes), owner))
 
 
 _pinned_owners = {}

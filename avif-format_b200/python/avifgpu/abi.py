@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-API_VERSION = 2
+API_VERSION = 3
 
 # avifgpu_status
 OK = 0

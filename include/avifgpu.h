@@ -50,7 +50,7 @@ extern "C" {
 #define AVIFGPU_EXPORT __attribute__((visibility("default")))
 #endif
 
-#define AVIFGPU_API_VERSION 2
+#define AVIFGPU_API_VERSION 3
 
 typedef enum avifgpu_status
 {
@@ -270,6 +270,30 @@ AVIFGPU_EXPORT int avifgpu_decode_rows(avifgpu_context* ctx, const avifgpu_decod
                                        const avifgpu_planes* src, int32_t y0, int32_t nrows,
                                        void* host_rows, int64_t row_stride_bytes);
 
+/* ---- the hot path: asynchronous host-pointer variants ------------------------------------------------------ */
+
+/*
+ * The same conversions, enqueued: the call returns once the work is on the device's queues, so the caller's thread can
+ * produce the next row block (the plug-in: advanceState, i.e. Photoshop filling the next rows, Write.cpp:297-336) while
+ * the GPU converts and copies this one.  Single-threaded contract like the rest of a context: calls on one context come
+ * from one thread at a time.
+ *   encode: on return the rows of THIS call may still be read by the copy engine when host_rows is page-locked memory
+ *           (avifgpu_host_alloc); they may be overwritten once the NEXT call on this context has returned (two row
+ *           buffers make a double-buffered shuttle) or avifgpu_wait() has.  Pageable rows are consumed before return.
+ *           The destination planes are complete after avifgpu_wait(ticket).
+ *   decode: the source planes must stay valid and the host rows are complete after avifgpu_wait(ticket).
+ * out_ticket (may be NULL) identifies the call; tickets increase by one per host-pointer call on a context.
+ */
+AVIFGPU_EXPORT int avifgpu_encode_rows_async(avifgpu_context* ctx, const avifgpu_encode_desc* desc,
+                                             const void* host_rows, int64_t row_stride_bytes,
+                                             int32_t y0, int32_t nrows, const avifgpu_planes* dst, int64_t* out_ticket);
+AVIFGPU_EXPORT int avifgpu_decode_rows_async(avifgpu_context* ctx, const avifgpu_decode_desc* desc,
+                                             const avifgpu_planes* src, int32_t y0, int32_t nrows,
+                                             void* host_rows, int64_t row_stride_bytes, int64_t* out_ticket);
+/* Blocks until every host-pointer call up to and including `ticket` has completed and its results are in the
+ * caller's memory; ticket <= 0 waits for everything issued so far. */
+AVIFGPU_EXPORT int avifgpu_wait(avifgpu_context* ctx, int64_t ticket);
+
 /* ---- the hot path: device-pointer variants (no copies, no synchronisation) --------------------------- */
 
 /* Same contracts, but host_rows / planes are DEVICE pointers valid on the context's device and the work is
@@ -283,6 +307,61 @@ AVIFGPU_EXPORT int avifgpu_decode_rows_device(avifgpu_context* ctx, const avifgp
                                               const avifgpu_planes* device_src, int32_t y0, int32_t nrows,
                                               void* device_rows, int64_t row_stride_bytes,
                                               void* cuda_stream);
+
+/* ---- the hot path across several GPUs of one box ------------------------------------------------ */
+
+/*
+ * An image shards by row block (4:2:0: even boundaries, no halo; tables are replicated), so one process can put every
+ * GPU of the box behind the same seam: the reference's row loops (WriteHeifImage.cpp:808-988 for a 16-bit RGBA save,
+ * ReadHeifImage.cpp:290-400 for a float load, ...) have no cross-row state.  A shard group owns one context per device
+ * and splits every call into `size` contiguous row blocks with avifgpu_shard_row_blocks().
+ *
+ *   host-pointer calls   block r is staged over device r's OWN PCIe link, converted there and copied back into the
+ *                        caller's planes / rows: the PCIe-bound end-to-end rate scales with the number of links.
+ *   device-pointer call  block r's rows already sit in device r's HBM; every device's conversion kernel stores its
+ *                        part of the planes straight into the OWNER device's memory over NVLink / NVSwitch (peer
+ *                        mapping inside the process), so the planar image is assembled when the kernels end -- the
+ *                        "gather of the final planar buffer" is fused into the conversion, no collective pass.
+ */
+typedef struct avifgpu_shard_group avifgpu_shard_group;
+
+/* One context per entry of device_ordinals[0 .. count) (distinct CUDA devices, compute capability 10.x); enables peer
+ * access between them where the hardware offers it. */
+AVIFGPU_EXPORT int avifgpu_shard_group_create(const int32_t* device_ordinals, int32_t count, avifgpu_shard_group** out_group);
+AVIFGPU_EXPORT void avifgpu_shard_group_destroy(avifgpu_shard_group* group);
+AVIFGPU_EXPORT int32_t avifgpu_shard_group_size(const avifgpu_shard_group* group);
+/* The context of member `index` (owned by the group), e.g. for avifgpu_host_alloc or avifgpu_launch_count. */
+AVIFGPU_EXPORT avifgpu_context* avifgpu_shard_group_context(avifgpu_shard_group* group, int32_t index);
+/* 1 when member `from` can address member `to`'s memory (needed by the device-pointer call), else 0. */
+AVIFGPU_EXPORT int avifgpu_shard_group_peer_access(const avifgpu_shard_group* group, int32_t from, int32_t to);
+AVIFGPU_EXPORT const char* avifgpu_shard_group_last_error(const avifgpu_shard_group* group);
+/* avifgpu_prepare_encode on every member (concurrently). */
+AVIFGPU_EXPORT int avifgpu_shard_group_prepare_encode(avifgpu_shard_group* group, const avifgpu_encode_desc* desc);
+/* Blocks until every member's work has finished. */
+AVIFGPU_EXPORT int avifgpu_shard_group_synchronize(avifgpu_shard_group* group);
+
+/* Row blocks of rows [y0, y0 + nrows) for `parts` members: contiguous, in order, every inner boundary even (a 2x2
+ * chroma site never straddles two blocks); trailing blocks may be empty.  Pure host arithmetic. */
+AVIFGPU_EXPORT int avifgpu_shard_row_blocks(int32_t y0, int32_t nrows, int32_t parts, int32_t* out_y0, int32_t* out_nrows);
+
+/* avifgpu_encode_rows / avifgpu_decode_rows with the row block split across the group (same arguments, same result,
+ * bit for bit).  y0 even for 4:2:0. */
+AVIFGPU_EXPORT int avifgpu_encode_rows_sharded(avifgpu_shard_group* group, const avifgpu_encode_desc* desc,
+                                               const void* host_rows, int64_t row_stride_bytes,
+                                               int32_t y0, int32_t nrows, const avifgpu_planes* dst);
+AVIFGPU_EXPORT int avifgpu_decode_rows_sharded(avifgpu_shard_group* group, const avifgpu_decode_desc* desc,
+                                               const avifgpu_planes* src, int32_t y0, int32_t nrows,
+                                               void* host_rows, int64_t row_stride_bytes);
+
+/*
+ * Device-resident frame, rows distributed: device_rows[r] / row_stride_bytes[r] = the first row of member r's block
+ * (avifgpu_shard_row_blocks(0, desc->height, size)) in member r's memory.  owner_planes = whole-image planes in member
+ * `owner`'s memory; every member must have peer access to it.  Enqueues one conversion per member on that member's
+ * own stream and returns; avifgpu_shard_group_synchronize() (or the next sharded call) orders after it.
+ */
+AVIFGPU_EXPORT int avifgpu_encode_rows_sharded_device(avifgpu_shard_group* group, const avifgpu_encode_desc* desc,
+                                                      const void* const* device_rows, const int64_t* row_stride_bytes,
+                                                      const avifgpu_planes* owner_planes, int32_t owner);
 
 /* ---- preparation (optional) --------------------------------------------------------------------------- */
 

@@ -191,6 +191,17 @@ def decode_cases(sizes=None, full=True):
                 name = f"dec_ycc_b{bit_depth}_h{host_depth}_ch{chroma}_a{alpha}_{nclx_name}_{w}x{h}"
                 desc = abi.DecodeDesc(w, h, abi.COLORSPACE_YCBCR, chroma, bit_depth, alpha, host_depth, nclx)
                 yield name, desc, code_planes(rng_for(name), desc, overshoot=True), True
+        # YCbCr 4:4:4 carrying the identity (GBR) matrix -- what a lossless file decodes as when libheif hands the planes over
+        # as YCbCr: the tables treat chroma like luma (YuvLookupTables.cpp:145,177-180), the row decoders have no identity
+        # branch and apply the default coefficients; whatever the reference does with it is the contract
+        for alpha, (bit_depth, host_depth) in itertools.product((abi.ALPHA_NONE, abi.ALPHA_STRAIGHT), ((8, 8), (10, 16), (12, 32))):
+            name = f"dec_ycc_gbr_b{bit_depth}_h{host_depth}_a{alpha}_{w}x{h}"
+            nclx = NCLX_GBR()
+            if host_depth == 32:
+                nclx = NCLX_2020_PQ()
+                nclx.matrix_coefficients = abi.MATRIX_GBR
+            desc = abi.DecodeDesc(w, h, abi.COLORSPACE_YCBCR, abi.CHROMA_444, bit_depth, alpha, host_depth, nclx)
+            yield name, desc, code_planes(rng_for(name), desc, overshoot=False), True
         # float outputs: PQ / HLG (+OOTF on/off) / SMPTE 428
         for chroma, alpha, (nclx_fn, tname), bit_depth in itertools.product(
                 (abi.CHROMA_444, abi.CHROMA_420), (abi.ALPHA_NONE, abi.ALPHA_PREMULTIPLIED),
