@@ -7,15 +7,37 @@
 #include "../../include/avifgpu.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <new>
 #include <string>
+
+#if defined(AVIFGPU_HOST_USE_PLUGIN_HEADERS)
+#include "ColorProfileConversion.h"
+#include "HostMetadata.h"
+#endif
 
 namespace
 {
     avifgpu_context* g_context = nullptr;
-    int32 g_rowsPerBlock = 512;
+    avifgpu_shard_group* g_group = nullptr; // several GPUs (avifgpu_host::UseDevices), else nullptr
+    int32 g_rowsPerBlock = 4096;
+    int64_t g_stagingBudget = 64ll << 20;
+    avifgpu_host::RowTransformFactory g_transformFactory = nullptr;
+    void* g_transformUser = nullptr;
+    avifgpu_host::ShuttleTimes g_times{};
+
+    using Clock = std::chrono::steady_clock;
+    double Seconds(Clock::time_point from) { return std::chrono::duration<double>(Clock::now() - from).count(); }
+
+    // Accumulates the time spent inside the host's callbacks.
+    struct HostTimer
+    {
+        Clock::time_point start = Clock::now();
+        ~HostTimer() { g_times.host += Seconds(start); }
+    };
 
     // avifgpu status -> the exception the reference would have thrown for the same condition.
     void ThrowIfFailed(avifgpu_context* ctx, int status)
@@ -100,10 +122,107 @@ namespace
         void* memory = nullptr;
     };
 
-    int32 BlockRows(int32 height)
+    // Rows per advanceState: bounded by the caller's setting and by the page-locked byte budget (an even count, at
+    // least two rows -- a 4:2:0 block must hold whole row pairs).  With several GPUs a block feeds all of them.
+    int32 BlockRows(int32 height, int64_t rowBytes)
     {
-        int32 rows = std::max<int32>(g_rowsPerBlock & ~1, 2);
-        return std::min(rows, std::max<int32>(height, 1));
+        const int64_t budget = g_stagingBudget * (g_group != nullptr ? avifgpu_shard_group_size(g_group) : 1);
+        int64_t rows = std::max<int64_t>(rowBytes, 1) > 0 ? budget / std::max<int64_t>(rowBytes, 1) : height;
+        rows = std::min<int64_t>(rows, g_rowsPerBlock);
+        rows = std::max<int64_t>(rows & ~1ll, 2);
+        return static_cast<int32>(std::min<int64_t>(rows, std::max<int32>(height, 1)));
+    }
+
+    // Two page-locked row buffers; when the allocation fails the block is halved until it fits (down to two rows).
+    struct StagingPair
+    {
+        std::unique_ptr<PinnedRows> buffer[2];
+        int32 blockRows = 0;
+        StagingPair(avifgpu_context* ctx, int64_t rowBytes, int32 height)
+        {
+            blockRows = BlockRows(height, rowBytes);
+            for (;;)
+            {
+                try
+                {
+                    const size_t bytes = static_cast<size_t>(std::max<int64_t>(rowBytes, 1)) * blockRows;
+                    buffer[0].reset(new PinnedRows(ctx, bytes));
+                    buffer[1].reset(new PinnedRows(ctx, bytes));
+                    return;
+                }
+                catch (const std::bad_alloc&)
+                {
+                    buffer[0].reset();
+                    buffer[1].reset();
+                    if (blockRows <= 2)
+                    {
+                        throw;
+                    }
+                    blockRows = std::max<int32>((blockRows / 2) & ~1, 2);
+                }
+            }
+        }
+    };
+
+    // Nothing issued on the context may outlive the buffers and planes of a call, whichever way the call is left.
+    struct DrainOnExit
+    {
+        avifgpu_context* ctx;
+        ~DrainOnExit() { avifgpu_wait(ctx, 0); }
+    };
+
+    // HostMetadata.cpp:63-69 (the handle-suite availability test is the plug-in's; the compat record has no suites).
+    bool RecordHasColorProfile(const FormatRecordPtr formatRecord)
+    {
+#if defined(AVIFGPU_HOST_USE_PLUGIN_HEADERS)
+        return HasColorProfileMetadata(formatRecord);
+#else
+        return formatRecord->canUseICCProfiles && formatRecord->iCCprofileData != nullptr && formatRecord->iCCprofileSize > 0;
+#endif
+    }
+
+#if defined(AVIFGPU_HOST_USE_PLUGIN_HEADERS)
+    // The plug-in's own converter behind the RowTransform interface.
+    struct PluginRowTransform final : avifgpu_host::RowTransform
+    {
+        ColorProfileConversion converter;
+        PluginRowTransform(FormatRecordPtr record, bool hasAlpha, ColorTransferFunction transfer, bool keep) : converter(record, hasAlpha, transfer, keep) {}
+        PluginRowTransform(FormatRecordPtr record, bool hasAlpha, int hostBits, bool keep) : converter(record, hasAlpha, hostBits, keep) {}
+        void ConvertRow(void* row, uint32_t pixelsPerLine, uint32_t bytesPerLine) override { converter.ConvertRow(row, pixelsPerLine, bytesPerLine); }
+    };
+#endif
+
+    // The per-save colour-profile step of CreateHeifImageRGB*Bit (WriteHeifImage.cpp:651, 830, 1015), or nullptr when the
+    // reference would not convert.  Gray saves never convert (WriteHeifImage.cpp:169-627 construct no converter).
+    std::unique_ptr<avifgpu_host::RowTransform> MakeRowTransform(FormatRecordPtr formatRecord, bool gray, bool hasAlpha, int hostDepth,
+                                                                 const SaveUIOptions& saveOptions)
+    {
+        if (gray || !RecordHasColorProfile(formatRecord))
+        {
+            return nullptr;
+        }
+        // ColorProfileConversion.cpp:107 (32-bit hosts) / :143 (8 and 16-bit hosts)
+        const bool mayRequireConversion = hostDepth == 32 ? (saveOptions.hdrTransferFunction != ColorTransferFunction::Clip || !saveOptions.keepColorProfile)
+                                                          : !saveOptions.keepColorProfile;
+        if (!mayRequireConversion)
+        {
+            return nullptr;
+        }
+        if (g_transformFactory != nullptr)
+        {
+            return std::unique_ptr<avifgpu_host::RowTransform>(
+                g_transformFactory(formatRecord, hasAlpha, hostDepth, saveOptions.hdrTransferFunction, saveOptions.keepColorProfile, g_transformUser));
+        }
+#if defined(AVIFGPU_HOST_USE_PLUGIN_HEADERS)
+        if (hostDepth == 32)
+        {
+            return std::unique_ptr<avifgpu_host::RowTransform>(new PluginRowTransform(formatRecord, hasAlpha, saveOptions.hdrTransferFunction, saveOptions.keepColorProfile));
+        }
+        return std::unique_ptr<avifgpu_host::RowTransform>(new PluginRowTransform(formatRecord, hasAlpha, hostDepth, saveOptions.keepColorProfile));
+#else
+        // A profile that may need converting and nobody to decide or do it: an error, never unconverted pixels tagged sRGB / BT.2020.
+        throw OSErrException(formatBadParameters);
+#endif
     }
 
     // Restores the caller's formatRecord->data / rowBytes when the shuttle leaves (normally or by exception).
@@ -136,9 +255,18 @@ namespace
 
     // ---- encode --------------------------------------------------------------------------------------------------
 
+    // Stamps g_times.total when an entry point is left.
+    struct CallTimer
+    {
+        Clock::time_point start = Clock::now();
+        CallTimer() { g_times = avifgpu_host::ShuttleTimes{}; }
+        ~CallTimer() { g_times.total = Seconds(start); }
+    };
+
     ScopedHeifImage EncodeThroughGpu(FormatRecordPtr formatRecord, AlphaState alphaState, const VPoint& imageSize,
                                      const SaveUIOptions& saveOptions, int hostDepth, bool gray)
     {
+        CallTimer callTimer;
         avifgpu_context* ctx = avifgpu_host::SharedContext();
         const bool hasAlpha = alphaState != AlphaState::None;
         const int bitDepth = HeifBitDepth(saveOptions.imageBitDepth);
@@ -235,23 +363,60 @@ namespace
         {
             throw std::bad_alloc(); // Write.cpp:286-295
         }
-        const int32 blockRows = BlockRows(imageSize.v);
-        PinnedRows staging(ctx, static_cast<size_t>(std::max<int64_t>(rowBytes, 1)) * blockRows);
+        std::unique_ptr<avifgpu_host::RowTransform> transform = MakeRowTransform(formatRecord, gray, hasAlpha, hostDepth, saveOptions);
+        StagingPair staging(ctx, rowBytes, imageSize.v);
+        const int32 blockRows = staging.blockRows;
+        g_times.rowsPerBlock = blockRows;
         RecordDataGuard guard(formatRecord);
-        formatRecord->data = staging.get();
+        DrainOnExit drain{ ctx };
         formatRecord->rowBytes = static_cast<int32>(rowBytes);
 
-        for (int32 top = 0; top < imageSize.v; top += blockRows)
+        int32 block = 0;
+        for (int32 top = 0; top < imageSize.v; top += blockRows, ++block)
         {
-            if (formatRecord->abortProc())
-            {
-                throw OSErrException(userCanceledErr); // WriteHeifImage.cpp:208-211, once per block here
-            }
+            void* rows = staging.buffer[block & 1]->get();
             const int32 bottom = std::min(top + blockRows, imageSize.v);
-            SetRectOf(formatRecord, top, 0, bottom, imageSize.h);
-            OSErrException::ThrowIfError(formatRecord->advanceState()); // the host fills rows [top, bottom)
-            ThrowIfFailed(ctx, avifgpu_encode_rows(ctx, &desc, staging.get(), rowBytes, top, bottom - top, &planes));
+            {
+                HostTimer timer;
+                if (formatRecord->abortProc())
+                {
+                    throw OSErrException(userCanceledErr); // WriteHeifImage.cpp:208-211, once per block here
+                }
+                SetRectOf(formatRecord, top, 0, bottom, imageSize.h);
+                formatRecord->data = rows;
+                OSErrException::ThrowIfError(formatRecord->advanceState()); // the host fills rows [top, bottom)
+            }
+            if (transform)
+            {
+                const Clock::time_point start = Clock::now();
+                for (int32 y = 0; y < bottom - top; ++y)
+                {
+                    // WriteHeifImage.cpp:1028-1031: converter.ConvertRow(formatRecord->data, imageSize.h, formatRecord->rowBytes)
+                    transform->ConvertRow(static_cast<uint8_t*>(rows) + static_cast<int64_t>(y) * rowBytes, static_cast<uint32_t>(imageSize.h),
+                                          static_cast<uint32_t>(rowBytes));
+                }
+                g_times.transform += Seconds(start);
+            }
+            if (g_group != nullptr)
+            {
+                // every GPU of the group takes a part of the block over its own PCIe link
+                const int status = avifgpu_encode_rows_sharded(g_group, &desc, rows, rowBytes, top, bottom - top, &planes);
+                if (status != AVIFGPU_OK)
+                {
+                    if (status == AVIFGPU_ERR_BAD_PARAM) throw OSErrException(formatBadParameters);
+                    if (status == AVIFGPU_ERR_OOM) throw std::bad_alloc();
+                    throw std::runtime_error(avifgpu_shard_group_last_error(g_group));
+                }
+            }
+            else
+            {
+                // returns once the block is queued: the host fills the other buffer while this one is on the wire;
+                // the buffer handed over in the previous iteration is free again when this call returns
+                ThrowIfFailed(ctx, avifgpu_encode_rows_async(ctx, &desc, rows, rowBytes, top, bottom - top, &planes, nullptr));
+            }
         }
+        g_times.blocks = block;
+        ThrowIfFailed(ctx, avifgpu_wait(ctx, 0)); // the planes are complete
         return image;
     }
 
@@ -260,6 +425,7 @@ namespace
     void DecodeThroughGpu(const heif_image* image, AlphaState alphaState, const heif_color_profile_nclx* nclxProfile,
                           const LoadUIOptions* loadOptions, FormatRecordPtr formatRecord, int hostDepth, bool gray)
     {
+        CallTimer callTimer;
         avifgpu_context* ctx = avifgpu_host::SharedContext();
         const VPoint imageSize = GetImageSizeOf(formatRecord);
         const bool hasAlpha = alphaState != AlphaState::None;
@@ -377,19 +543,57 @@ namespace
             }
         }
 
-        const int32 blockRows = BlockRows(imageSize.v);
-        PinnedRows staging(ctx, static_cast<size_t>(std::max<int64_t>(rowBytes, 1)) * blockRows);
+        StagingPair staging(ctx, rowBytes, imageSize.v);
+        const int32 blockRows = staging.blockRows;
+        g_times.rowsPerBlock = blockRows;
         RecordDataGuard guard(formatRecord);
-        formatRecord->data = staging.get();
+        DrainOnExit drain{ ctx };
         formatRecord->rowBytes = static_cast<int32>(rowBytes);
 
-        for (int32 top = 0; top < imageSize.v; top += blockRows)
+        // Block k+1 converts and travels while the host takes block k.
+        auto issue = [&](int32 top, int32 index, int64_t* ticket)
         {
             const int32 bottom = std::min(top + blockRows, imageSize.v);
-            ThrowIfFailed(ctx, avifgpu_decode_rows(ctx, &desc, &planes, top, bottom - top, staging.get(), rowBytes));
+            void* rows = staging.buffer[index & 1]->get();
+            if (g_group != nullptr)
+            {
+                const int status = avifgpu_decode_rows_sharded(g_group, &desc, &planes, top, bottom - top, rows, rowBytes);
+                if (status != AVIFGPU_OK)
+                {
+                    if (status == AVIFGPU_ERR_BAD_PARAM) throw OSErrException(formatBadParameters);
+                    if (status == AVIFGPU_ERR_OOM) throw std::bad_alloc();
+                    throw std::runtime_error(avifgpu_shard_group_last_error(g_group));
+                }
+                *ticket = 0;
+                return;
+            }
+            ThrowIfFailed(ctx, avifgpu_decode_rows_async(ctx, &desc, &planes, top, bottom - top, rows, rowBytes, ticket));
+        };
+        int64_t ticket = 0;
+        if (imageSize.v > 0)
+        {
+            issue(0, 0, &ticket);
+        }
+        int32 block = 0;
+        for (int32 top = 0; top < imageSize.v; top += blockRows, ++block)
+        {
+            const int32 bottom = std::min(top + blockRows, imageSize.v);
+            int64_t nextTicket = 0;
+            if (bottom < imageSize.v)
+            {
+                issue(bottom, block + 1, &nextTicket);
+            }
+            if (g_group == nullptr)
+            {
+                ThrowIfFailed(ctx, avifgpu_wait(ctx, ticket));
+            }
+            ticket = nextTicket;
+            HostTimer timer;
+            formatRecord->data = staging.buffer[block & 1]->get();
             SetRectOf(formatRecord, top, 0, bottom, imageSize.h);
             OSErrException::ThrowIfError(formatRecord->advanceState()); // the host consumes rows [top, bottom)
         }
+        g_times.blocks = block;
     }
 }
 
@@ -413,6 +617,12 @@ avifgpu_context* SharedContext()
 
 void ReleaseSharedContext()
 {
+    if (g_group != nullptr)
+    {
+        avifgpu_shard_group_destroy(g_group);
+        g_group = nullptr;
+        g_context = nullptr; // owned by the group
+    }
     if (g_context != nullptr)
     {
         avifgpu_destroy(g_context);
@@ -421,6 +631,32 @@ void ReleaseSharedContext()
 }
 
 void SetRowsPerBlock(int32 rows) { g_rowsPerBlock = std::max<int32>(rows, 2); }
+
+void SetStagingBudgetBytes(int64_t bytes) { g_stagingBudget = std::max<int64_t>(bytes, 1); }
+
+void UseDevices(const int32_t* deviceOrdinals, int32_t count)
+{
+    ReleaseSharedContext();
+    if (deviceOrdinals == nullptr || count <= 1)
+    {
+        return; // the next call creates the single shared context
+    }
+    avifgpu_shard_group* group = nullptr;
+    if (avifgpu_shard_group_create(deviceOrdinals, count, &group) != AVIFGPU_OK)
+    {
+        throw OSErrException(errPlugInHostInsufficient);
+    }
+    g_group = group;
+    g_context = avifgpu_shard_group_context(group, 0); // staging memory and the geometry helpers go through member 0
+}
+
+void SetRowTransformFactory(RowTransformFactory factory, void* user)
+{
+    g_transformFactory = factory;
+    g_transformUser = user;
+}
+
+ShuttleTimes LastShuttleTimes() { return g_times; }
 
 } // namespace avifgpu_host
 

@@ -68,6 +68,11 @@ struct FormatRecord
     Boolean (*abortProc)(void);
     void (*progressProc)(int32 done, int32 total);
     BufferProcs* bufferProcs;
+    // document colour profile (HostMetadata.cpp:63-69 HasColorProfileMetadata reads exactly these; the handle suite the
+    // real test also asks for is not modelled here)
+    Boolean canUseICCProfiles;
+    void* iCCprofileData; // a Handle in the SDK
+    int32 iCCprofileSize;
 };
 typedef FormatRecord* FormatRecordPtr;
 

@@ -1,0 +1,211 @@
+// shuttle_bench.cpp -- times the plug-in's row shuttle (GpuRowShuttle.cpp: CreateHeifImageRGBThirtyTwoBit /
+// CreateHeifImageRGBSixteenBit exactly as Write.cpp:303-336 calls them) end to end on this box: a mock Photoshop host
+// serves row blocks through FormatRecord::advanceState into the shuttle's pinned buffers, the planes belong to a
+// heap-backed heif_image (pageable memory with padded strides, like libheif's), the GPU path is whatever the shuttle
+// uses.  bench.py runs it for its `e2e_shuttle` figure.
+//
+//   shuttle_bench <c2|c4> <width> <height> <steps> <copy|resident> [device ...]
+//
+//   copy      advanceState memcpy's the requested rows out of a pageable source frame (what any real host at least does)
+//   resident  advanceState leaves the staging buffers as they are after their first fill: the host's own cost removed,
+//             what remains is the shuttle + the library (the figure to hold against bench.py's e2e)
+// Prints one JSON object.
+#include "../GpuRowShuttle.h"
+#include "../../../include/avifgpu.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+// ---- a heap-backed heif_image (only what the shuttle calls) -----------------------------------------------------------
+struct heif_image
+{
+    int width, height;
+    heif_colorspace colorspace;
+    heif_chroma chroma;
+    struct Plane { int width, height, depth, stride; uint8_t* memory; };
+    std::map<int, Plane> planes;
+};
+
+extern "C" {
+heif_error heif_image_create(int width, int height, heif_colorspace colorspace, heif_chroma chroma, heif_image** out)
+{
+    *out = new heif_image{ width, height, colorspace, chroma, {} };
+    return heif_error{ heif_error_Ok, heif_suberror_Unspecified, "Success" };
+}
+heif_error heif_image_add_plane(heif_image* image, heif_channel channel, int width, int height, int depth)
+{
+    heif_image::Plane p{ width, height, depth, 0, nullptr };
+    p.stride = ((width * (depth > 8 ? 2 : 1) + 15) / 16 + 1) * 16; // padded rows, like libheif's
+    p.memory = static_cast<uint8_t*>(std::malloc(static_cast<size_t>(p.stride) * (height > 0 ? height : 1)));
+    image->planes[channel] = p;
+    return heif_error{ p.memory ? heif_error_Ok : heif_error_Memory_allocation_error, heif_suberror_Unspecified, "" };
+}
+uint8_t* heif_image_get_plane(heif_image* image, heif_channel channel, int* stride)
+{
+    auto it = image->planes.find(channel);
+    if (it == image->planes.end()) return nullptr;
+    if (stride) *stride = it->second.stride;
+    return it->second.memory;
+}
+const uint8_t* heif_image_get_plane_readonly(const heif_image* image, heif_channel channel, int* stride)
+{
+    return heif_image_get_plane(const_cast<heif_image*>(image), channel, stride);
+}
+int heif_image_get_bits_per_pixel_range(const heif_image* image, heif_channel channel)
+{
+    auto it = image->planes.find(channel);
+    return it == image->planes.end() ? -1 : it->second.depth;
+}
+heif_chroma heif_image_get_chroma_format(const heif_image* image) { return image->chroma; }
+heif_colorspace heif_image_get_colorspace(const heif_image* image) { return image->colorspace; }
+void heif_image_release(const heif_image* image)
+{
+    for (auto& kv : image->planes) std::free(kv.second.memory);
+    delete image;
+}
+}
+
+namespace
+{
+    struct Host
+    {
+        FormatRecord record{};
+        BufferProcs procs{};
+        const uint8_t* source = nullptr;
+        int64_t stride = 0;
+        bool copy = true;
+        std::vector<void*> filled; // resident mode: buffers already holding rows
+    };
+    Host* g_host = nullptr;
+
+    OSErr Advance()
+    {
+        Host& h = *g_host;
+        FormatRecord& r = h.record;
+        const int top = r.theRect32.top, bottom = r.theRect32.bottom;
+        if (!h.copy)
+        {
+            for (void* p : h.filled)
+                if (p == r.data) return noErr;
+            h.filled.push_back(r.data);
+        }
+        for (int y = top; y < bottom; ++y)
+        {
+            std::memcpy(static_cast<uint8_t*>(r.data) + static_cast<int64_t>(y - top) * r.rowBytes, h.source + static_cast<int64_t>(y) * h.stride,
+                        static_cast<size_t>(h.stride));
+        }
+        return noErr;
+    }
+    Boolean Abort() { return 0; }
+    void Progress(int32, int32) {}
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 6)
+    {
+        std::fprintf(stderr, "usage: shuttle_bench <c2|c4> <width> <height> <steps> <copy|resident> [device ...]\n");
+        return 2;
+    }
+    const std::string workload = argv[1];
+    const int w = std::atoi(argv[2]), h = std::atoi(argv[3]), steps = std::atoi(argv[4]);
+    const bool copy = std::string(argv[5]) == "copy";
+    std::vector<int32_t> devices;
+    for (int i = 6; i < argc; ++i) devices.push_back(std::atoi(argv[i]));
+    const bool c2 = workload == "c2";
+    const int channels = c2 ? 3 : 4;
+    const int depth = c2 ? 32 : 16;
+    const int64_t stride = static_cast<int64_t>(w) * channels * (depth / 8);
+
+    // synthetic frame: finite, in range, different everywhere (a 64-bit LCG), pageable memory like a host's tiles
+    std::vector<uint8_t> frame(static_cast<size_t>(stride) * h);
+    uint64_t state = 0x9e3779b97f4a7c15ull;
+    if (c2)
+    {
+        float* v = reinterpret_cast<float*>(frame.data());
+        for (size_t i = 0; i < frame.size() / 4; ++i)
+        {
+            state = state * 6364136223846793005ull + 1442695040888963407ull;
+            v[i] = static_cast<float>(state >> 40) * (1.0f / 16777216.0f);
+        }
+    }
+    else
+    {
+        uint16_t* v = reinterpret_cast<uint16_t*>(frame.data());
+        for (size_t i = 0; i < frame.size() / 2; ++i)
+        {
+            state = state * 6364136223846793005ull + 1442695040888963407ull;
+            v[i] = static_cast<uint16_t>((state >> 33) % 32769u);
+        }
+    }
+
+    try
+    {
+        if (devices.size() > 1)
+        {
+            avifgpu_host::UseDevices(devices.data(), static_cast<int32_t>(devices.size()));
+        }
+        SaveUIOptions options{};
+        options.chromaSubsampling = c2 ? ChromaSubsampling::Yuv420 : ChromaSubsampling::Yuv422;
+        options.imageBitDepth = c2 ? ImageBitDepth::Twelve : ImageBitDepth::Ten;
+        options.hdrTransferFunction = c2 ? ColorTransferFunction::PQ : ColorTransferFunction::Clip;
+        options.pq.nominalPeakBrightness = 80;
+        options.keepColorProfile = true;
+        const AlphaState alpha = c2 ? AlphaState::None : AlphaState::Straight;
+
+        double best = 1e30, total = 0.0, hostSeconds = 0.0;
+        avifgpu_host::ShuttleTimes times{};
+        for (int step = -1; step < steps; ++step) // step -1 = warm-up (allocations, table state)
+        {
+            Host host;
+            host.record.planes = static_cast<int16>(channels);
+            host.record.depth = static_cast<int16>(depth);
+            host.record.imageSize32.h = w;
+            host.record.imageSize32.v = h;
+            host.record.HostSupports32BitCoordinates = 1;
+            host.record.PluginUsing32BitCoordinates = 1;
+            host.record.advanceState = Advance;
+            host.record.abortProc = Abort;
+            host.record.progressProc = Progress;
+            host.record.bufferProcs = &host.procs;
+            host.source = frame.data();
+            host.stride = stride;
+            host.copy = copy;
+            g_host = &host;
+            const auto start = std::chrono::steady_clock::now();
+            ScopedHeifImage image = c2 ? CreateHeifImageRGBThirtyTwoBit(&host.record, alpha, VPoint{ h, w }, options)
+                                       : CreateHeifImageRGBSixteenBit(&host.record, alpha, VPoint{ h, w }, options);
+            const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+            if (step >= 0)
+            {
+                total += seconds;
+                best = seconds < best ? seconds : best;
+                times = avifgpu_host::LastShuttleTimes();
+                hostSeconds += times.host;
+            }
+        }
+        const double pixels = static_cast<double>(w) * h;
+        std::printf("{\"workload\": \"%s\", \"width\": %d, \"height\": %d, \"steps\": %d, \"host\": \"%s\", \"gpus\": %d, "
+                    "\"seconds_per_image\": %.6f, \"best_seconds\": %.6f, \"host_seconds_per_image\": %.6f, \"gpx_s\": %.4f, \"best_gpx_s\": %.4f, "
+                    "\"blocks\": %d, \"rows_per_block\": %d, \"planes\": \"pageable (malloc), padded strides\"}\n",
+                    workload.c_str(), w, h, steps, copy ? "copy" : "resident", devices.size() > 1 ? static_cast<int>(devices.size()) : 1,
+                    total / steps, best, hostSeconds / steps, pixels * steps / total / 1e9, pixels / best / 1e9, times.blocks, times.rowsPerBlock);
+    }
+    catch (const OSErrException& e)
+    {
+        std::printf("{\"error\": \"OSErr %d\"}\n", static_cast<int>(e.GetErrorCode()));
+        return 1;
+    }
+    catch (const std::exception& e)
+    {
+        std::printf("{\"error\": \"%s\"}\n", e.what());
+        return 1;
+    }
+    avifgpu_host::ReleaseSharedContext();
+    return 0;
+}

@@ -177,6 +177,125 @@ namespace
                "decode 10-bit HLG 4:2:0 -> RGB32f bit-identical to the oracle; formatRecord->data/rowBytes restored");
     }
 
+    // A stand-in for the plug-in's lcms2 transform: something observable and exactly reproducible (halve every colour
+    // sample; powers of two are exact in float32).
+    struct HalvingTransform final : avifgpu_host::RowTransform
+    {
+        int channels;
+        int rowsConverted = 0;
+        explicit HalvingTransform(int c) : channels(c) {}
+        void ConvertRow(void* row, uint32_t pixelsPerLine, uint32_t) override
+        {
+            float* v = static_cast<float*>(row);
+            for (uint32_t x = 0; x < pixelsPerLine; ++x)
+                for (int c = 0; c < 3; ++c) v[x * channels + c] *= 0.5f;
+            ++rowsConverted;
+        }
+    };
+    HalvingTransform* g_lastTransform = nullptr;
+    int g_factoryCalls = 0;
+    avifgpu_host::RowTransform* HalvingFactory(FormatRecordPtr, bool hasAlpha, int hostBits, ColorTransferFunction, bool, void*)
+    {
+        ++g_factoryCalls;
+        g_lastTransform = hostBits == 32 ? new HalvingTransform(hasAlpha ? 4 : 3) : nullptr; // nullptr = "profile already matches"
+        return g_lastTransform;
+    }
+
+    // The ICC seam (WriteHeifImage.cpp:1015-1036, ColorProfileConversion.cpp:107-120, HostMetadata.cpp:63-69).
+    void TestColorProfileStep()
+    {
+        const int w = 40, h = 22;
+        std::mt19937 rng(4321);
+        std::uniform_real_distribution<float> dist(0.0f, 1.2f);
+        std::vector<float> rows(static_cast<size_t>(w) * h * 3);
+        for (float& v : rows) v = dist(rng);
+        static const unsigned char fakeProfile[16] = { 1 };
+
+        auto save = [&](bool withProfile, bool keepProfile, ColorTransferFunction transfer, MockHost& host) -> ScopedHeifImage
+        {
+            InitHost(host, w, h, 3, 32);
+            host.source = reinterpret_cast<const uint8_t*>(rows.data());
+            host.stride = host.payload = static_cast<int64_t>(w) * 12;
+            if (withProfile)
+            {
+                host.record.canUseICCProfiles = 1;
+                host.record.iCCprofileData = const_cast<unsigned char*>(fakeProfile);
+                host.record.iCCprofileSize = sizeof(fakeProfile);
+            }
+            SaveUIOptions options{};
+            options.chromaSubsampling = ChromaSubsampling::Yuv444;
+            options.imageBitDepth = ImageBitDepth::Twelve;
+            options.hdrTransferFunction = transfer;
+            options.pq.nominalPeakBrightness = 80;
+            options.keepColorProfile = keepProfile;
+            avifgpu_host::SetRowsPerBlock(8);
+            return CreateHeifImageRGBThirtyTwoBit(&host.record, AlphaState::None, VPoint{ h, w }, options);
+        };
+
+        // 1. a profile that may need converting, and nobody to do it: an error -- never unconverted pixels
+        avifgpu_host::SetRowTransformFactory(nullptr, nullptr);
+        {
+            MockHost host;
+            bool refused = false;
+            try { save(true, false, ColorTransferFunction::PQ, host); }
+            catch (const OSErrException& e) { refused = e.GetErrorCode() == formatBadParameters; }
+            Expect(refused && host.advanceCalls == 0, "document profile + PQ save without a row transform -> OSErrException(formatBadParameters) before any row is read");
+        }
+        // 2. the reference's "no conversion" cases need no transform: no profile; keepColorProfile with the clip transfer
+        {
+            MockHost host;
+            bool ok = true;
+            try { save(false, false, ColorTransferFunction::PQ, host); save(true, true, ColorTransferFunction::Clip, host); }
+            catch (...) { ok = false; }
+            Expect(ok, "no document profile, or keepColorProfile with the clip transfer: no transform asked for (ColorProfileConversion.cpp:107)");
+        }
+        // 3. with a factory the transform runs over every staged row before the conversion
+        avifgpu_host::SetRowTransformFactory(HalvingFactory, nullptr);
+        {
+            MockHost host;
+            g_factoryCalls = 0;
+            ScopedHeifImage image = save(true, true, ColorTransferFunction::PQ, host); // PQ: may require conversion even when keeping the profile
+            std::vector<float> halved(rows);
+            for (float& v : halved) v *= 0.5f;
+            avifgpu_encode_desc d{};
+            d.struct_size = sizeof(d);
+            d.width = w; d.height = h; d.host_depth = 32; d.host_channels = 3; d.image_bit_depth = 12; d.transfer = AVIFGPU_TRANSFER_PQ;
+            d.pq_peak_nits = 80; d.layout = AVIFGPU_LAYOUT_PLANAR_YCBCR; d.chroma = AVIFGPU_CHROMA_444;
+            d.nclx.present = 1; d.nclx.color_primaries = 9; d.nclx.transfer_characteristics = 16; d.nclx.matrix_coefficients = 9; d.nclx.full_range_flag = 1;
+            std::vector<uint16_t> y(static_cast<size_t>(w) * h), cb(y.size()), cr(y.size());
+            avifgpu_planes planes{};
+            planes.data[0] = y.data(); planes.data[1] = cb.data(); planes.data[2] = cr.data();
+            planes.stride[0] = planes.stride[1] = planes.stride[2] = w * 2;
+            const int status = avif_oracle_encode_image(&d, halved.data(), static_cast<int64_t>(w) * 12, &planes);
+            const bool same = status == 0 && PlaneEquals(image.get(), heif_channel_Y, y, w, h) && PlaneEquals(image.get(), heif_channel_Cb, cb, w, h) &&
+                              PlaneEquals(image.get(), heif_channel_Cr, cr, w, h);
+            Expect(same && g_factoryCalls == 1, "row transform applied to every staged row, once, before the conversion (planes == oracle of the transformed rows)");
+        }
+        avifgpu_host::SetRowTransformFactory(nullptr, nullptr);
+    }
+
+    // Staging is bounded in bytes, not rows (a 300 000-pixel RGBA32f row is 4.8 MB).
+    void TestStagingBudget()
+    {
+        const int w = 4096, h = 64;
+        std::vector<uint8_t> rows(static_cast<size_t>(w) * h * 4, 9);
+        MockHost host;
+        InitHost(host, w, h, 4, 8);
+        host.source = rows.data();
+        host.stride = host.payload = static_cast<int64_t>(w) * 4;
+        SaveUIOptions options{};
+        options.chromaSubsampling = ChromaSubsampling::Yuv420;
+        options.imageBitDepth = ImageBitDepth::Eight;
+        options.hdrTransferFunction = ColorTransferFunction::Clip;
+        avifgpu_host::SetRowsPerBlock(4096);
+        avifgpu_host::SetStagingBudgetBytes(5 * 16384); // five rows' worth -> blocks of four rows
+        CreateHeifImageRGBEightBit(&host.record, AlphaState::Straight, VPoint{ h, w }, options);
+        const avifgpu_host::ShuttleTimes times = avifgpu_host::LastShuttleTimes();
+        Expect(host.maxRowsSeen == 4 && times.rowsPerBlock == 4 && times.blocks == 16 && times.total > 0.0,
+               "staging budget in bytes bounds the block (4 rows of 16 KiB under an 80 KiB budget), 16 blocks for 64 rows");
+        avifgpu_host::SetStagingBudgetBytes(64ll << 20);
+    }
+
     void TestErrors()
     {
         // user cancel between blocks -> OSErrException(userCanceledErr), as WriteHeifImage.cpp:208-211
@@ -230,6 +349,8 @@ int main()
         TestEncodeRgb32(64, 16, ChromaSubsampling::Yuv422, true);
         TestEncodeRgb32(33, 9, ChromaSubsampling::Yuv444, false);
         TestDecodeHlg(75, 33);
+        TestColorProfileStep();
+        TestStagingBudget();
         TestErrors();
     }
     catch (const std::exception& e)
