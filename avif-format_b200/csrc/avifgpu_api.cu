@@ -26,9 +26,11 @@ int LaunchEncodeFast(const EncodeParams& params, int hostDepth, void* stream);  
 int LaunchEncodeFastInteger(const EncodeParams& params, int hostDepth, void* stream); // 0 = not applicable
 cudaError_t BuildGray16Lut(uint16_t* deviceLut, int smpte428, uint32_t maxCode, void* stream);
 long long VerifyHlgDivisions(void* stream);
+long long VerifyFastPremultiply(uint32_t maxCode, void* stream);
 long long VerifyGreenDivision(const DecodeParams& params, void* stream);
 int LaunchDecodeFast(const DecodeParams& params, void* stream);                  // 0 = not applicable
 int LaunchDecodeFastInteger(const DecodeParams& params, void* stream);           // 0 = not applicable
+int LaunchDecodeFastTable(const DecodeParams& params, void* stream);             // 0 = not applicable
 int LaunchHlgOotf(int inverse, const float luma[3], float displayGamma, float peak, const float* in, float* out, size_t pixels, void* stream);
 
 namespace
@@ -72,6 +74,11 @@ int LaunchDecode(const DecodeParams& params, void* stream)
         return fast;
     }
     fast = LaunchDecodeFastInteger(params, stream);
+    if (fast != 0)
+    {
+        return fast;
+    }
+    fast = LaunchDecodeFastTable(params, stream);
     if (fast != 0)
     {
         return fast;
@@ -152,6 +159,23 @@ struct avifgpu_context
         uint16_t* device = nullptr;
     };
     std::vector<Gray16Lut> gray16Luts;
+    int premultiplyState[3] = { -1, -1, -1 }; // image depth 8 / 10 / 12: -1 not checked yet, 0 keep the reference sequence, 1 fast form verified
+    // The tuned integer encode kernel premultiplies with a 6-instruction form, but only after it has been compared with
+    // PremultiplyColor's own sequence for every (colour, alpha) code pair of the depth, on this device.
+    int VerifiedPremultiply(const avifgpu_encode_desc& d)
+    {
+        if (d.alpha_state != AVIFGPU_ALPHA_PREMULTIPLIED || d.host_depth == 32 || d.host_channels != 4 || d.layout != AVIFGPU_LAYOUT_PLANAR_YCBCR)
+        {
+            return 0;
+        }
+        const int slot = d.image_bit_depth == 8 ? 0 : d.image_bit_depth == 10 ? 1 : 2;
+        if (premultiplyState[slot] < 0)
+        {
+            premultiplyState[slot] = VerifyFastPremultiply((1u << d.image_bit_depth) - 1u, streams[0]) == 0 ? 1 : 0;
+            launches += 1;
+        }
+        return premultiplyState[slot];
+    }
     int hlgDivisionState = -1; // -1 not checked yet, 0 keep IEEE divisions, 1 fast divisions verified exact
 
     // HLG decode replaces two constant divisions by a 3-instruction form, but only after comparing it with the
@@ -746,6 +770,7 @@ AVIFGPU_EXPORT int avifgpu_encode_rows_device(avifgpu_context* ctx, const avifgp
         p.curveTable = table->valid ? &table->view : nullptr;
     }
     p.gray16Lut = ctx->Gray16LutFor(*desc);
+    p.verifiedPremultiply = ctx->VerifiedPremultiply(*desc);
     const int launched = LaunchEncode(p, desc->host_depth, cuda_stream);
     if (launched < 0)
     {
@@ -954,6 +979,7 @@ static int EncodeRowsHost(avifgpu_context* ctx, const avifgpu_encode_desc* desc,
         base.curveTable = table->valid ? &table->view : nullptr;
     }
     base.gray16Lut = ctx->Gray16LutFor(*desc);
+    base.verifiedPremultiply = ctx->VerifiedPremultiply(*desc);
     const int64_t rowPayload = static_cast<int64_t>(desc->width) * EncodeHostColBytes(*desc);
     const int64_t deviceRowStride = (rowPayload + 255) & ~255ll;
     const bool rowsPinned = IsPinned(host_rows);

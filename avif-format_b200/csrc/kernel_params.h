@@ -77,6 +77,7 @@ struct EncodeParams
     const CurveTableView* curveTable; // verified exact step table for `transfer`, or nullptr
     const uint16_t* gray16Lut;        // 65536-entry code table for Gray16 hosts (device memory), or nullptr
     int32_t smCount;
+    int32_t verifiedPremultiply;      // 1 once the context has verified FastPremultiplyBiased for this image depth on this device
 };
 
 struct DecodeParams

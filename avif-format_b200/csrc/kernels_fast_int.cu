@@ -147,7 +147,46 @@ struct Rgb16Params
     float chromaOffset;
     int32_t topLeft;
     uint32_t maxCode;
+    float maxReciprocal; // RN(1 / maxCode), for the verified premultiply
 };
+
+// PremultiplyColor(uint16_t, uint16_t, maxValue) (PremultipliedAlpha.cpp:62-70) behind the callers' guard
+// (WriteHeifImage.cpp:947-965: alpha == max keeps the colour, alpha == 0 clears it) in six full-rate instructions:
+//     product (exact: both codes < 2^12)  ->  / max by reciprocal + one residual step  ->  + 0.5, truncate.
+// The division by reciprocal is not the IEEE division and trunc(x + 0.5) is not roundf(x) for every float x, but over the
+// (max + 1)^2 code pairs of a bit depth it either always agrees with the reference's own sequence or it does not:
+// VerifyFastPremultiplyKernel enumerates them all, and the tuned kernel is used only for depths that passed.  No special
+// cases are needed: alpha == 0 gives a zero product, alpha == max gives product / max == colour exactly.
+__device__ __forceinline__ float FastPremultiplyBiased(float colour, float alpha, float maxCodeFloat, float maxReciprocal)
+{
+    const float product = __fmul_rn(colour, alpha);
+    const float quotient = DivideByConstant(product, maxCodeFloat, maxReciprocal);
+    return __fadd_rz(__fadd_rn(quotient, 0.5f), kTwo23); // 2^23 + code
+}
+
+__global__ void VerifyFastPremultiplyKernel(uint32_t maxCode, unsigned long long* __restrict__ counter)
+{
+    const float maxCodeFloat = static_cast<float>(maxCode);
+    const float reciprocal = 1.0f / maxCodeFloat;
+    const unsigned long long pairs = static_cast<unsigned long long>(maxCode + 1u) * (maxCode + 1u);
+    unsigned long long bad = 0;
+    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < pairs;
+         i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+    {
+        const uint32_t colour = static_cast<uint32_t>(i % (maxCode + 1u));
+        const uint32_t alpha = static_cast<uint32_t>(i / (maxCode + 1u));
+        const uint32_t expected = PremultiplyCodeGuarded(colour, alpha, maxCode);
+        const uint32_t fast = __float_as_uint(FastPremultiplyBiased(static_cast<float>(colour), static_cast<float>(alpha), maxCodeFloat, reciprocal)) & 0x7fffffu;
+        if (fast != expected)
+        {
+            ++bad;
+        }
+    }
+    if (bad)
+    {
+        atomicAdd(counter, bad);
+    }
+}
 
 // Host sample -> 2^23 + code, as a float.
 //   16-bit host (0..32768, or beyond: the formula is defined to continue)  WriteHeifImage.cpp:140-166:
@@ -201,7 +240,9 @@ __device__ __forceinline__ void StoreFour(uint8_t* address, const uint32_t (&c)[
 }
 
 // HostT: uint8_t / uint16_t host samples; PlaneT: uint8_t (8-bit image) / uint16_t (10 / 12-bit image) plane samples.
-template <typename HostT, typename PlaneT, int CHANNELS, int XS, int YS>
+// PREMULTIPLY (CHANNELS == 4 only): the colour codes are multiplied by the alpha code in the image's depth before the matrix
+// (WriteHeifImage.cpp:700-718, 760-778, 877-895, 947-965), through FastPremultiplyBiased.
+template <typename HostT, typename PlaneT, int CHANNELS, int XS, int YS, int PREMULTIPLY>
 __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rgb16Params p)
 {
     constexpr int kRows = 1 + YS;
@@ -270,7 +311,14 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
                     return (words[r][k >> 2] >> (8 * (k & 3))) & 0xffu;
                 };
                 float rf, gf, bf;
-                if (sizeof(HostT) == 1 && sizeof(PlaneT) == 1)
+                if (PREMULTIPLY)
+                {
+                    const float af = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 3), p, hostLut) - kTwo23;
+                    rf = FastPremultiplyBiased(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 0), p, hostLut) - kTwo23, af, p.maxCodeFloat, p.maxReciprocal) - kTwo23;
+                    gf = FastPremultiplyBiased(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 1), p, hostLut) - kTwo23, af, p.maxCodeFloat, p.maxReciprocal) - kTwo23;
+                    bf = FastPremultiplyBiased(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 2), p, hostLut) - kTwo23, af, p.maxCodeFloat, p.maxReciprocal) - kTwo23;
+                }
+                else if (sizeof(HostT) == 1 && sizeof(PlaneT) == 1)
                 {
                     // 8-bit host into an 8-bit image: the sample is the code.  Byte -> float is one conversion instruction
                     // (it takes the byte lane as an operand modifier); at 4.5 bytes per pixel this kernel is bound by
@@ -454,7 +502,7 @@ bool Aligned(const void* p, int64_t stride, int alignment)
     return (reinterpret_cast<uintptr_t>(p) % alignment) == 0 && (stride % alignment) == 0;
 }
 
-template <typename HostT, typename PlaneT, int CHANNELS>
+template <typename HostT, typename PlaneT, int CHANNELS, int PREMULTIPLY>
 cudaError_t LaunchRgbInt(const Rgb16Params& rp, int xs, int ys, int smCount, cudaStream_t stream)
 {
     const long long groups = static_cast<long long>(rp.groupsPerRow) * ((rp.rowCount + ys) >> ys);
@@ -463,21 +511,41 @@ cudaError_t LaunchRgbInt(const Rgb16Params& rp, int xs, int ys, int smCount, cud
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const unsigned grid = static_cast<unsigned>(blocks);
-    if (xs == 1 && ys == 1) EncodeRgbIntPlanarKernel<HostT, PlaneT, CHANNELS, 1, 1><<<grid, kRgbThreads, 0, stream>>>(rp);
-    else if (xs == 1) EncodeRgbIntPlanarKernel<HostT, PlaneT, CHANNELS, 1, 0><<<grid, kRgbThreads, 0, stream>>>(rp);
-    else EncodeRgbIntPlanarKernel<HostT, PlaneT, CHANNELS, 0, 0><<<grid, kRgbThreads, 0, stream>>>(rp);
+    if (xs == 1 && ys == 1) EncodeRgbIntPlanarKernel<HostT, PlaneT, CHANNELS, 1, 1, PREMULTIPLY><<<grid, kRgbThreads, 0, stream>>>(rp);
+    else if (xs == 1) EncodeRgbIntPlanarKernel<HostT, PlaneT, CHANNELS, 1, 0, PREMULTIPLY><<<grid, kRgbThreads, 0, stream>>>(rp);
+    else EncodeRgbIntPlanarKernel<HostT, PlaneT, CHANNELS, 0, 0, PREMULTIPLY><<<grid, kRgbThreads, 0, stream>>>(rp);
     return cudaGetLastError();
 }
 
 template <typename HostT, typename PlaneT>
-cudaError_t LaunchRgbIntChannels(const Rgb16Params& rp, int channels, int xs, int ys, int smCount, cudaStream_t stream)
+cudaError_t LaunchRgbIntChannels(const Rgb16Params& rp, int channels, bool premultiply, int xs, int ys, int smCount, cudaStream_t stream)
 {
-    return channels == 4 ? LaunchRgbInt<HostT, PlaneT, 4>(rp, xs, ys, smCount, stream) : LaunchRgbInt<HostT, PlaneT, 3>(rp, xs, ys, smCount, stream);
+    if (channels == 4 && premultiply) return LaunchRgbInt<HostT, PlaneT, 4, 1>(rp, xs, ys, smCount, stream);
+    return channels == 4 ? LaunchRgbInt<HostT, PlaneT, 4, 0>(rp, xs, ys, smCount, stream) : LaunchRgbInt<HostT, PlaneT, 3, 0>(rp, xs, ys, smCount, stream);
 }
 
 } // namespace
 
 int LaunchEncodeGeneric(const EncodeParams& params, int hostDepth, void* stream);
+
+// Runs the exhaustive comparison behind FastPremultiplyBiased for one bit depth; returns the number of disagreements
+// (0 = verified) or -1 on a CUDA error.  Synchronous.
+long long VerifyFastPremultiply(uint32_t maxCode, void* streamHandle)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
+    unsigned long long* counter = nullptr;
+    if (cudaMalloc(&counter, sizeof(unsigned long long)) != cudaSuccess)
+    {
+        return -1;
+    }
+    cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
+    VerifyFastPremultiplyKernel<<<148 * 8, 256, 0, stream>>>(maxCode, counter);
+    unsigned long long bad = 0;
+    const bool ok = cudaMemcpyAsync(&bad, counter, sizeof(bad), cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+                    cudaStreamSynchronize(stream) == cudaSuccess;
+    cudaFree(counter);
+    return ok ? static_cast<long long>(bad) : -1;
+}
 
 cudaError_t BuildGray16Lut(uint16_t* deviceLut, int smpte428, uint32_t maxCode, void* streamHandle)
 {
@@ -560,6 +628,7 @@ int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHa
         rp.maxCodeFloat = p.maxCodeFloat;
         rp.biasedMax = 8388608.0f + p.maxCodeFloat;
         rp.maxCode = p.maxCode;
+        rp.maxReciprocal = 1.0f / p.maxCodeFloat;
         cudaError_t e;
         if (hostBytes == 2)
         {
@@ -590,7 +659,7 @@ int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHa
 
     // The biased-truncation trick needs non-negative intermediates: true for every matrix with kr, kg, kb >= 0
     // (all of H.273's); anything else takes the generic kernel.
-    if (p.planar && (p.channels == 3 || p.channels == 4) && !p.premultiply && p.imageDepth <= 12 &&
+    if (p.planar && (p.channels == 3 || p.channels == 4) && (!p.premultiply || (p.channels == 4 && p.verifiedPremultiply)) && p.imageDepth <= 12 &&
         (p.matrix.identity || (p.matrix.kr >= 0.0f && p.matrix.kg >= 0.0f && p.matrix.kb >= 0.0f && p.matrix.kr < 1.0f && p.matrix.kb < 1.0f)) &&
         ForwardMatrixStaysInRange(p.matrix, p.chromaOffset, static_cast<int>(p.maxCode)))
     {
@@ -627,16 +696,17 @@ int LaunchEncodeFastInteger(const EncodeParams& p, int hostDepth, void* streamHa
         rp.chromaOffset = p.chromaOffset;
         rp.topLeft = p.topLeft;
         rp.maxCode = p.maxCode;
+        rp.maxReciprocal = 1.0f / p.maxCodeFloat;
         cudaError_t e;
         if (hostBytes == 2)
         {
-            e = planeBytes == 2 ? LaunchRgbIntChannels<uint16_t, uint16_t>(rp, p.channels, p.xs, p.ys, smCount, stream)
-                                : LaunchRgbIntChannels<uint16_t, uint8_t>(rp, p.channels, p.xs, p.ys, smCount, stream);
+            e = planeBytes == 2 ? LaunchRgbIntChannels<uint16_t, uint16_t>(rp, p.channels, p.premultiply != 0, p.xs, p.ys, smCount, stream)
+                                : LaunchRgbIntChannels<uint16_t, uint8_t>(rp, p.channels, p.premultiply != 0, p.xs, p.ys, smCount, stream);
         }
         else
         {
-            e = planeBytes == 2 ? LaunchRgbIntChannels<uint8_t, uint16_t>(rp, p.channels, p.xs, p.ys, smCount, stream)
-                                : LaunchRgbIntChannels<uint8_t, uint8_t>(rp, p.channels, p.xs, p.ys, smCount, stream);
+            e = planeBytes == 2 ? LaunchRgbIntChannels<uint8_t, uint16_t>(rp, p.channels, p.premultiply != 0, p.xs, p.ys, smCount, stream)
+                                : LaunchRgbIntChannels<uint8_t, uint8_t>(rp, p.channels, p.premultiply != 0, p.xs, p.ys, smCount, stream);
         }
         if (e != cudaSuccess)
         {
