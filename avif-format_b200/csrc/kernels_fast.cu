@@ -143,6 +143,49 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
     const bool rgba = p.channels == 4 && p.hasAlpha;
+    if (hostDepth == 32 && !p.planar && p.channels == 3 && !p.hasAlpha && p.imageDepth > 8 && !p.hlgInverseOotf &&
+        (p.transfer == AVIFGPU_TRANSFER_PQ || p.transfer == AVIFGPU_TRANSFER_SMPTE428) && p.curveTable != nullptr && p.curveTable->buckets != nullptr)
+    {
+        // The reference's own layout: interleaved RGB codes (WriteHeifImage.cpp:1098-1130), same kernel without the matrix.
+        const int width4 = p.width & ~3;
+        if (width4 < 4 || p.rowCount < 1 || !Aligned(p.rows, p.rowStride, 16) || !Aligned(p.plane[0], p.planeStride[0], 8))
+        {
+            return 0;
+        }
+        FastEncodeParams fp{};
+        fp.rows = static_cast<const uint8_t*>(p.rows);
+        fp.rowStride = p.rowStride;
+        fp.planeY = static_cast<uint8_t*>(p.plane[0]);
+        fp.strideY = p.planeStride[0];
+        fp.width = width4;
+        fp.rowCount = p.rowCount;
+        fp.pqMultiplier = p.pqMultiplier;
+        fp.maxCodeFloat = p.maxCodeFloat;
+        fp.maxCode = static_cast<int32_t>(p.maxCode);
+        fp.table = *p.curveTable;
+        if (!FlatEncodeApplies(fp))
+        {
+            return 0;
+        }
+        const int curve = p.transfer == AVIFGPU_TRANSFER_PQ ? kCurveLinearToPQ : kCurveLinearToSMPTE428;
+        const cudaError_t e = LaunchFastEncodeFlatInterleaved(fp, curve, p.smCount > 0 ? p.smCount : 148, stream);
+        if (e != cudaSuccess)
+        {
+            return ReportLaunchFailure(static_cast<int>(e));
+        }
+        int launched = 1;
+        if (width4 < p.width)
+        {
+            EncodeParams strip = p;
+            strip.rows = static_cast<const uint8_t*>(p.rows) + static_cast<int64_t>(width4) * 12;
+            strip.width = p.width - width4;
+            strip.plane[0] = static_cast<uint8_t*>(p.plane[0]) + static_cast<int64_t>(width4) * 6;
+            const int n = LaunchEncodeGeneric(strip, hostDepth, streamHandle);
+            if (n < 0) return n;
+            launched += n;
+        }
+        return launched;
+    }
     if (hostDepth != 32 || !p.planar || (p.channels != 3 && !rgba) || (p.channels == 3 && p.hasAlpha) || p.imageDepth <= 8)
     {
         return 0;

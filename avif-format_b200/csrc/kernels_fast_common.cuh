@@ -194,6 +194,7 @@ cudaError_t LaunchFastEncodeRgba(const fastenc::FastEncodeParams& fp, int curve,
 // kernels_fast_flat.cu
 bool FlatEncodeApplies(const fastenc::FastEncodeParams& fp);
 cudaError_t LaunchFastEncodeFlat(const fastenc::FastEncodeParams& fp, int curve, int xs, int ys, int smCount, cudaStream_t stream);
+cudaError_t LaunchFastEncodeFlatInterleaved(const fastenc::FastEncodeParams& fp, int curve, int smCount, cudaStream_t stream);
 
 } // namespace avifgpu
 

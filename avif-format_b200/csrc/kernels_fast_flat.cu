@@ -95,7 +95,9 @@ __device__ __forceinline__ void BarrierWait(uint32_t barrier, uint32_t parity)
 
 // TWO_LEVEL = 0: the flat table + band bitmap.  TWO_LEVEL = 1: the per-binade two-level table (curves whose steps are too
 // dense for one bucket size, e.g. 12-bit SMPTE 428); its rare in-band samples take the exact evaluation in place.
-template <int CURVE, int XS, int YS, int TWO_LEVEL>
+// INTERLEAVED = 1: the reference's own output layout (heif_channel_interleaved RGB, WriteHeifImage.cpp:1098-1130) -- the
+// codes are stored as they are, 3 x uint16 per pixel into plane Y's buffer, no matrix (XS = YS = 0 then).
+template <int CURVE, int XS, int YS, int TWO_LEVEL, int INTERLEAVED>
 __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const FastEncodeParams p, const FlatSchedule schedule)
 {
     extern __shared__ __align__(128) uint8_t sharedBytes[];
@@ -204,7 +206,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
         const uint32_t tileBytes = columnBytes(column);
         const bool laneActive = column * kTilePixels + lane * 4 < p.width;
         int64_t sourceOffset = sourceOffsetOf(rowBegin, column);
-        uint8_t* yPointer = p.planeY + static_cast<int64_t>(rowBegin) * 2 * p.strideY + static_cast<int64_t>(column) * (2 * kTilePixels) + lane * 8;
+        uint8_t* yPointer = p.planeY + static_cast<int64_t>(rowBegin) * 2 * p.strideY +
+                            (INTERLEAVED ? static_cast<int64_t>(column) * (6 * kTilePixels) + lane * 24 : static_cast<int64_t>(column) * (2 * kTilePixels) + lane * 8);
         uint8_t* cbPointer = p.planeCb + static_cast<int64_t>(rowBegin) * kChromaRowsPerTile * p.strideCb + static_cast<int64_t>(column) * kChromaTileBytes + lane * (XS ? 4 : 8);
         uint8_t* crPointer = p.planeCr + static_cast<int64_t>(rowBegin) * kChromaRowsPerTile * p.strideCr + static_cast<int64_t>(column) * kChromaTileBytes + lane * (XS ? 4 : 8);
 
@@ -323,7 +326,29 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
 
         if (laneActive)
         {
-            StoreTile<XS, YS>(p, codeF, yPointer, cbPointer, crPointer, secondRow);
+            if (INTERLEAVED)
+            {
+                // 4 pixels x 3 codes per row = 24 bytes: three 64-bit stores
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                {
+                    if (r == 1 && !secondRow) break;
+                    uint32_t words[6];
+#pragma unroll
+                    for (int w = 0; w < 6; ++w)
+                    {
+                        words[w] = __float2uint_rz(codeF[12 * r + 2 * w]) | (__float2uint_rz(codeF[12 * r + 2 * w + 1]) << 16);
+                    }
+                    uint2* target = reinterpret_cast<uint2*>(yPointer + r * p.strideY);
+                    __stcs(target, make_uint2(words[0], words[1]));
+                    __stcs(target + 1, make_uint2(words[2], words[3]));
+                    __stcs(target + 2, make_uint2(words[4], words[5]));
+                }
+            }
+            else
+            {
+                StoreTile<XS, YS>(p, codeF, yPointer, cbPointer, crPointer, secondRow);
+            }
         }
         yPointer += 2 * p.strideY;
         cbPointer += kChromaRowsPerTile * p.strideCb;
@@ -337,13 +362,13 @@ inline size_t TableSharedBytes(const FastEncodeParams& fp, bool twoLevel)
     return twoLevel ? 2048 + static_cast<size_t>(fp.table.bucketCount) * sizeof(uint32_t) : static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
 }
 
-template <int CURVE, int XS, int YS, int TWO_LEVEL>
+template <int CURVE, int XS, int YS, int TWO_LEVEL, int INTERLEAVED = 0>
 cudaError_t LaunchFlatKernel(const FastEncodeParams& fp, int smCount, cudaStream_t stream)
 {
     const size_t shared = static_cast<size_t>(FlatFixedBytes()) + TableSharedBytes(fp, TWO_LEVEL != 0);
     static std::atomic<uint64_t> configuredDevices{ 0 }; // per instantiation
     {
-        const cudaError_t e = AllowDynamicShared(EncodeRgbF32FlatKernel<CURVE, XS, YS, TWO_LEVEL>, kSharedLimit, configuredDevices);
+        const cudaError_t e = AllowDynamicShared(EncodeRgbF32FlatKernel<CURVE, XS, YS, TWO_LEVEL, INTERLEAVED>, kSharedLimit, configuredDevices);
         if (e != cudaSuccess)
         {
             return e;
@@ -371,7 +396,7 @@ cudaError_t LaunchFlatKernel(const FastEncodeParams& fp, int smCount, cudaStream
     schedule.longSegments = schedule.tileRows % schedule.segments;
     schedule.lastColumnBytes = (fp.width - (schedule.tilesX - 1) * kTilePixels) * 12;
     schedule.unpairedTileRow = (fp.rowCount & 1) ? fp.rowCount / 2 : -1;
-    EncodeRgbF32FlatKernel<CURVE, XS, YS, TWO_LEVEL><<<static_cast<unsigned>(blocks), kFlatThreads, shared, stream>>>(fp, schedule);
+    EncodeRgbF32FlatKernel<CURVE, XS, YS, TWO_LEVEL, INTERLEAVED><<<static_cast<unsigned>(blocks), kFlatThreads, shared, stream>>>(fp, schedule);
     return cudaGetLastError();
 }
 
@@ -402,6 +427,18 @@ static bool TwoLevelTableFits(const FastEncodeParams& fp)
 bool FlatEncodeApplies(const FastEncodeParams& fp)
 {
     return FlatTableFits(fp) || TwoLevelTableFits(fp);
+}
+
+// The reference's interleaved RGB layout through the same kernel (fp.planeY / strideY = the interleaved buffer).
+cudaError_t LaunchFastEncodeFlatInterleaved(const FastEncodeParams& fp, int curve, int smCount, cudaStream_t stream)
+{
+    if (FlatTableFits(fp))
+    {
+        if (curve == kCurveLinearToPQ) return LaunchFlatKernel<kCurveLinearToPQ, 0, 0, 0, 1>(fp, smCount, stream);
+        return LaunchFlatKernel<kCurveLinearToSMPTE428, 0, 0, 0, 1>(fp, smCount, stream);
+    }
+    if (curve == kCurveLinearToPQ) return LaunchFlatKernel<kCurveLinearToPQ, 0, 0, 1, 1>(fp, smCount, stream);
+    return LaunchFlatKernel<kCurveLinearToSMPTE428, 0, 0, 1, 1>(fp, smCount, stream);
 }
 
 cudaError_t LaunchFastEncodeFlat(const FastEncodeParams& fp, int curve, int xs, int ys, int smCount, cudaStream_t stream)

@@ -57,6 +57,38 @@ def gather_encode_planes(dist, torch, desc, blocks, local_planes, group=None):
     return out
 
 
+def gather_planes_to_owner(dist, torch, desc, blocks, local_planes, owner_planes, rank, owner=0, group=None):
+    """The collective of SURVEY.md 8(e) as it should be: every rank sends each plane block ONCE, to the owner only, and
+    the owner receives it straight into its rows of the final plane (plane rows are contiguous, so a row block is a
+    contiguous slice: no re-stitch copy).  All sends and receives of a call form one group
+    (torch.distributed.batch_isend_irecv = ncclGroupStart / ncclGroupEnd on NCCL; works on gloo too).
+
+    local_planes   this rank's block planes, exactly the shape of the block presented as an image
+                   (abi.encode_plane_shapes(block_desc(desc, rows)))
+    owner_planes   whole-image planes on the owner (ignored elsewhere; may be None)"""
+    ys = [0, 1 if desc.chroma == abi.CHROMA_420 and desc.layout == abi.LAYOUT_PLANAR_YCBCR else 0,
+          1 if desc.chroma == abi.CHROMA_420 and desc.layout == abi.LAYOUT_PLANAR_YCBCR else 0, 0]
+    ops = []
+    for k, plane in enumerate(local_planes):
+        if plane is None:
+            continue
+        if rank == owner:
+            for r, (y0, n) in enumerate(blocks):
+                rows = (n + ys[k]) >> ys[k]
+                if rows == 0:
+                    continue
+                target = owner_planes[k][(y0 >> ys[k]):(y0 >> ys[k]) + rows]
+                if r == owner:
+                    target.copy_(plane)
+                else:
+                    ops.append(dist.P2POp(dist.irecv, target.view(torch.uint8), r, group))
+        elif plane.numel() > 0:
+            ops.append(dist.P2POp(dist.isend, plane.contiguous().view(torch.uint8), owner, group))
+    if ops:
+        for work in dist.batch_isend_irecv(ops):
+            work.wait()
+
+
 class PeerPlanes:
     """Whole-image planes that live on the OWNER rank's GPU and are mapped into every other rank's address space
     through CUDA IPC (one process per GPU).  A rank hands `planes()` to avifgpu_encode_rows_device together with

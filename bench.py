@@ -664,32 +664,13 @@ def run_tile_block(torch, dist, gpu, avifgpu, device, rank, world, steps, worklo
     block_desc = wl.enc.copy(height=n)
     local = [None if s is None else torch.empty(s, dtype=dt, device=device) for s in abi.encode_plane_shapes(block_desc)]
     full = [None if s is None else torch.empty(s, dtype=dt, device=device) for s in shapes] if rank == 0 else None
-    plane_ys = [0, 1 if wl.enc.chroma == abi.CHROMA_420 else 0, 1 if wl.enc.chroma == abi.CHROMA_420 else 0, 0]
 
     def convert_local():
         if n > 0:
             gpu.encode_device(block_desc, block.data_ptr(), block.stride(0) * block.element_size(), avifgpu.planes_from_tensors(local), stream=stream)
 
     def gather_to_owner():
-        ops = []
-        for k, plane in enumerate(local):
-            if plane is None:
-                continue
-            if rank == 0:
-                for r, (by0, bn) in enumerate(blocks):
-                    rows = (bn + plane_ys[k]) >> plane_ys[k]
-                    if rows == 0:
-                        continue
-                    target = full[k][(by0 >> plane_ys[k]):(by0 >> plane_ys[k]) + rows]
-                    if r == 0:
-                        target.copy_(plane)
-                    else:
-                        ops.append(dist.P2POp(dist.irecv, target.view(torch.uint8), r))
-            elif plane.numel() > 0:
-                ops.append(dist.P2POp(dist.isend, plane.view(torch.uint8), 0))
-        if ops:
-            for work in dist.batch_isend_irecv(ops):  # one ncclGroupStart/End around every send and receive of the step
-                work.wait()
+        sharding.gather_planes_to_owner(dist, torch, wl.enc, blocks, local, full, rank, owner=0)
 
     def time_loop(body):
         for _ in range(2):

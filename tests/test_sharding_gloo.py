@@ -29,6 +29,17 @@ def test_row_blocks_are_even_and_cover():
                 y += n
 
 
+def test_c_abi_row_blocks_match_the_python_partition():
+    """avifgpu_shard_row_blocks (what the in-process shard group cuts by) == sharding.row_blocks (what the ranks cut by)."""
+    import avifgpu
+    for height in (0, 1, 2, 3, 7, 8, 23, 4320, 16384, 4319):
+        for parts in (1, 2, 3, 4, 8):
+            assert avifgpu.shard_row_blocks(0, height, parts) == sharding.row_blocks(height, parts)
+    # a block of an image (the shuttle's case): boundaries stay on even IMAGE rows
+    blocks = avifgpu.shard_row_blocks(512, 1000, 3)
+    assert blocks[0][0] == 512 and sum(n for _, n in blocks) == 1000 and all(y0 % 2 == 0 for y0, _ in blocks)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -64,6 +75,17 @@ def _worker(rank, world, port, results):
             for e, f in zip(expected, full):
                 if e is not None:
                     ok = ok and np.array_equal(f.numpy().view(np.uint16), e)
+            # gather to the owner only, received in place (what bench.py's tile block times as the NCCL baseline)
+            exact = [None if s is None else torch.zeros(s, dtype=torch.int16) for s in abi.encode_plane_shapes(sharding.block_desc(desc, n))]
+            for t, l in zip(exact, local):
+                if t is not None:
+                    t.copy_(l[:t.shape[0], :t.shape[1]])
+            owner_planes = [None if e is None else torch.full(e.shape, -1, dtype=torch.int16) for e in expected] if rank == 0 else None
+            sharding.gather_planes_to_owner(dist, torch, desc, blocks, exact, owner_planes, rank, owner=0)
+            if rank == 0:
+                for e, f in zip(expected, owner_planes):
+                    if e is not None:
+                        ok = ok and np.array_equal(f.numpy().view(np.uint16), e)
         results[rank] = ok
     finally:
         dist.destroy_process_group()
