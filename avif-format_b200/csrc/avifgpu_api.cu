@@ -864,7 +864,7 @@ static int SliceRows(int nrows, int64_t bytesPerRow)
     return static_cast<int>(std::min<int64_t>(rows, nrows));
 }
 
-static void CopyRows(uint8_t* target, int64_t targetStride, const uint8_t* source, int64_t sourceStride, int64_t payload, int rows)
+static void CopyRowsSerial(uint8_t* target, int64_t targetStride, const uint8_t* source, int64_t sourceStride, int64_t payload, int rows)
 {
     if (targetStride == payload && sourceStride == payload)
     {
@@ -874,6 +874,44 @@ static void CopyRows(uint8_t* target, int64_t targetStride, const uint8_t* sourc
     for (int r = 0; r < rows; ++r)
     {
         std::memcpy(target + static_cast<int64_t>(r) * targetStride, source + static_cast<int64_t>(r) * sourceStride, static_cast<size_t>(payload));
+    }
+}
+
+// Bounce copies between pageable caller memory and the pinned slot buffers.  One core moves ~10 GB/s, a fifth of what
+// the PCIe link next to it carries, so anything beyond a few megabytes is split across a handful of threads (created per
+// copy: tens of microseconds against milliseconds of copying).
+static void CopyRows(uint8_t* target, int64_t targetStride, const uint8_t* source, int64_t sourceStride, int64_t payload, int rows)
+{
+    const int64_t bytes = payload * rows;
+    int workers = static_cast<int>(std::min<int64_t>(bytes / (4ll << 20), 8));
+    const unsigned cores = std::thread::hardware_concurrency();
+    if (cores > 0)
+    {
+        workers = std::min<int>(workers, static_cast<int>(cores));
+    }
+    if (workers < 2 || rows < workers)
+    {
+        CopyRowsSerial(target, targetStride, source, sourceStride, payload, rows);
+        return;
+    }
+    std::vector<std::thread> threads;
+    threads.reserve(workers - 1);
+    const int share = (rows + workers - 1) / workers;
+    for (int w = 1; w < workers; ++w)
+    {
+        const int begin = w * share;
+        const int count = std::min(share, rows - begin);
+        if (count <= 0)
+        {
+            break;
+        }
+        threads.emplace_back(CopyRowsSerial, target + static_cast<int64_t>(begin) * targetStride, targetStride,
+                             source + static_cast<int64_t>(begin) * sourceStride, sourceStride, payload, count);
+    }
+    CopyRowsSerial(target, targetStride, source, sourceStride, payload, std::min(share, rows));
+    for (std::thread& t : threads)
+    {
+        t.join();
     }
 }
 

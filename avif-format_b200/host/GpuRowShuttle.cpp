@@ -133,27 +133,50 @@ namespace
         return static_cast<int32>(std::min<int64_t>(rows, std::max<int32>(height, 1)));
     }
 
-    // Two page-locked row buffers; when the allocation fails the block is halved until it fits (down to two rows).
-    struct StagingPair
+    // Two page-locked row buffers, kept between calls (page-locking 128 MiB costs tens of milliseconds -- more than
+    // converting an 8K frame -- so the shuttle pays it once per process, not once per image; ReleaseSharedContext frees
+    // them).  When the allocation fails the block is halved until it fits (down to two rows).
+    struct StagingCache
     {
         std::unique_ptr<PinnedRows> buffer[2];
+        size_t bytes = 0;
+        avifgpu_context* owner = nullptr;
+        void Release()
+        {
+            buffer[0].reset();
+            buffer[1].reset();
+            bytes = 0;
+            owner = nullptr;
+        }
+    };
+    StagingCache g_staging;
+
+    struct StagingPair
+    {
+        PinnedRows* buffer[2] = { nullptr, nullptr };
         int32 blockRows = 0;
         StagingPair(avifgpu_context* ctx, int64_t rowBytes, int32 height)
         {
             blockRows = BlockRows(height, rowBytes);
             for (;;)
             {
+                const size_t bytes = static_cast<size_t>(std::max<int64_t>(rowBytes, 1)) * blockRows;
+                if (g_staging.owner == ctx && g_staging.bytes >= bytes)
+                {
+                    break; // the buffers of an earlier call are large enough
+                }
                 try
                 {
-                    const size_t bytes = static_cast<size_t>(std::max<int64_t>(rowBytes, 1)) * blockRows;
-                    buffer[0].reset(new PinnedRows(ctx, bytes));
-                    buffer[1].reset(new PinnedRows(ctx, bytes));
-                    return;
+                    g_staging.Release();
+                    g_staging.buffer[0].reset(new PinnedRows(ctx, bytes));
+                    g_staging.buffer[1].reset(new PinnedRows(ctx, bytes));
+                    g_staging.bytes = bytes;
+                    g_staging.owner = ctx;
+                    break;
                 }
                 catch (const std::bad_alloc&)
                 {
-                    buffer[0].reset();
-                    buffer[1].reset();
+                    g_staging.Release();
                     if (blockRows <= 2)
                     {
                         throw;
@@ -161,6 +184,8 @@ namespace
                     blockRows = std::max<int32>((blockRows / 2) & ~1, 2);
                 }
             }
+            buffer[0] = g_staging.buffer[0].get();
+            buffer[1] = g_staging.buffer[1].get();
         }
     };
 
@@ -617,6 +642,7 @@ avifgpu_context* SharedContext()
 
 void ReleaseSharedContext()
 {
+    g_staging.Release(); // before the context that owns the page-locked memory goes away
     if (g_group != nullptr)
     {
         avifgpu_shard_group_destroy(g_group);

@@ -4,11 +4,15 @@
 // heap-backed heif_image (pageable memory with padded strides, like libheif's), the GPU path is whatever the shuttle
 // uses.  bench.py runs it for its `e2e_shuttle` figure.
 //
-//   shuttle_bench <c2|c4> <width> <height> <steps> <copy|resident> [device ...]
+//   shuttle_bench <c2|c4> <width> <height> <steps> <copy|resident> <fresh|warm> [device ...]
 //
 //   copy      advanceState memcpy's the requested rows out of a pageable source frame (what any real host at least does)
 //   resident  advanceState leaves the staging buffers as they are after their first fill: the host's own cost removed,
 //             what remains is the shuttle + the library (the figure to hold against bench.py's e2e)
+//   fresh     every image's planes are new malloc'd memory, as libheif allocates them: the first write to each page
+//             faults it in (the kernel zeroes 100 MB per 8K frame) -- a cost of the allocation, paid by whoever writes
+//             the planes first, CPU loop or GPU shuttle alike
+//   warm      the planes come from an arena whose pages have been touched before (an allocator that recycles memory)
 // Prints one JSON object.
 #include "../GpuRowShuttle.h"
 #include "../../../include/avifgpu.h"
@@ -22,6 +26,14 @@
 #include <vector>
 
 // ---- a heap-backed heif_image (only what the shuttle calls) -----------------------------------------------------------
+namespace
+{
+    // "warm" planes: a bump arena over memory that has been written once.
+    uint8_t* g_arena = nullptr;
+    size_t g_arenaBytes = 0, g_arenaUsed = 0;
+    bool g_warm = false;
+}
+
 struct heif_image
 {
     int width, height;
@@ -41,7 +53,16 @@ heif_error heif_image_add_plane(heif_image* image, heif_channel channel, int wid
 {
     heif_image::Plane p{ width, height, depth, 0, nullptr };
     p.stride = ((width * (depth > 8 ? 2 : 1) + 15) / 16 + 1) * 16; // padded rows, like libheif's
-    p.memory = static_cast<uint8_t*>(std::malloc(static_cast<size_t>(p.stride) * (height > 0 ? height : 1)));
+    const size_t bytes = static_cast<size_t>(p.stride) * (height > 0 ? height : 1);
+    if (g_warm && g_arenaUsed + bytes + 64 <= g_arenaBytes)
+    {
+        p.memory = g_arena + g_arenaUsed;
+        g_arenaUsed += (bytes + 63) & ~static_cast<size_t>(63);
+    }
+    else
+    {
+        p.memory = static_cast<uint8_t*>(std::malloc(bytes));
+    }
     image->planes[channel] = p;
     return heif_error{ p.memory ? heif_error_Ok : heif_error_Memory_allocation_error, heif_suberror_Unspecified, "" };
 }
@@ -65,7 +86,11 @@ heif_chroma heif_image_get_chroma_format(const heif_image* image) { return image
 heif_colorspace heif_image_get_colorspace(const heif_image* image) { return image->colorspace; }
 void heif_image_release(const heif_image* image)
 {
-    for (auto& kv : image->planes) std::free(kv.second.memory);
+    for (auto& kv : image->planes)
+    {
+        if (!(kv.second.memory >= g_arena && kv.second.memory < g_arena + g_arenaBytes)) std::free(kv.second.memory);
+    }
+    g_arenaUsed = 0; // one image at a time
     delete image;
 }
 }
@@ -107,20 +132,28 @@ namespace
 
 int main(int argc, char** argv)
 {
-    if (argc < 6)
+    if (argc < 7)
     {
-        std::fprintf(stderr, "usage: shuttle_bench <c2|c4> <width> <height> <steps> <copy|resident> [device ...]\n");
+        std::fprintf(stderr, "usage: shuttle_bench <c2|c4> <width> <height> <steps> <copy|resident> <fresh|warm> [device ...]\n");
         return 2;
     }
     const std::string workload = argv[1];
     const int w = std::atoi(argv[2]), h = std::atoi(argv[3]), steps = std::atoi(argv[4]);
     const bool copy = std::string(argv[5]) == "copy";
+    g_warm = std::string(argv[6]) == "warm";
     std::vector<int32_t> devices;
-    for (int i = 6; i < argc; ++i) devices.push_back(std::atoi(argv[i]));
+    for (int i = 7; i < argc; ++i) devices.push_back(std::atoi(argv[i]));
     const bool c2 = workload == "c2";
     const int channels = c2 ? 3 : 4;
     const int depth = c2 ? 32 : 16;
     const int64_t stride = static_cast<int64_t>(w) * channels * (depth / 8);
+
+    if (g_warm)
+    {
+        g_arenaBytes = static_cast<size_t>(w) * h * 8 + (64u << 20); // every plane of any layout, with padding
+        g_arena = static_cast<uint8_t*>(std::malloc(g_arenaBytes));
+        std::memset(g_arena, 1, g_arenaBytes);
+    }
 
     // synthetic frame: finite, in range, different everywhere (a 64-bit LCG), pageable memory like a host's tiles
     std::vector<uint8_t> frame(static_cast<size_t>(stride) * h);
@@ -192,9 +225,10 @@ int main(int argc, char** argv)
         const double pixels = static_cast<double>(w) * h;
         std::printf("{\"workload\": \"%s\", \"width\": %d, \"height\": %d, \"steps\": %d, \"host\": \"%s\", \"gpus\": %d, "
                     "\"seconds_per_image\": %.6f, \"best_seconds\": %.6f, \"host_seconds_per_image\": %.6f, \"gpx_s\": %.4f, \"best_gpx_s\": %.4f, "
-                    "\"blocks\": %d, \"rows_per_block\": %d, \"planes\": \"pageable (malloc), padded strides\"}\n",
+                    "\"blocks\": %d, \"rows_per_block\": %d, \"planes\": \"pageable (malloc), padded strides, %s\"}\n",
                     workload.c_str(), w, h, steps, copy ? "copy" : "resident", devices.size() > 1 ? static_cast<int>(devices.size()) : 1,
-                    total / steps, best, hostSeconds / steps, pixels * steps / total / 1e9, pixels / best / 1e9, times.blocks, times.rowsPerBlock);
+                    total / steps, best, hostSeconds / steps, pixels * steps / total / 1e9, pixels / best / 1e9, times.blocks, times.rowsPerBlock,
+                    g_warm ? "pages already touched (recycling allocator)" : "fresh pages per image (first-touch faults inside the timed call)");
     }
     catch (const OSErrException& e)
     {

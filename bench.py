@@ -471,9 +471,10 @@ def run_shuttle_bench(wl_key, w, h, steps, devices):
     try:
         subprocess.run(cmd, check=True, capture_output=True, timeout=300)
         out = {}
-        for host in ("resident", "copy"):
-            done = subprocess.run([exe, wl_key, str(w), str(h), str(steps), host] + [str(d) for d in devices], capture_output=True, text=True, timeout=600)
-            out[host] = json.loads(done.stdout.strip().splitlines()[-1])
+        for host, pages in (("resident", "warm"), ("resident", "fresh"), ("copy", "fresh")):
+            done = subprocess.run([exe, wl_key, str(w), str(h), str(steps), host, pages] + [str(d) for d in devices], capture_output=True, text=True,
+                                  timeout=600)
+            out[f"host_{host}_planes_{pages}"] = json.loads(done.stdout.strip().splitlines()[-1])
         return out
     except Exception as error:  # the figure is an extra; the line must still print
         return {"unavailable": f"{type(error).__name__}: {error}"}
@@ -588,12 +589,12 @@ def run_b200(args, workload, rank, world, local_rank):
 
     shuttle = None
     if rank == 0 and not args.no_shuttle and wl.key in ("c2", "c4"):
-        shuttle = {"one_gpu": run_shuttle_bench(wl.key, wl.w, wl.rows_total, 3, [local_rank])}
+        shuttle = {"one_gpu": run_shuttle_bench(wl.key, wl.w, wl.rows_total, 5, [local_rank])}
     if dist is not None:
         dist.barrier()
     if rank == 0 and world > 1 and not args.no_shuttle and wl.key in ("c2", "c4"):
         # every GPU of the job behind ONE plug-in call (avifgpu_shard_group); the other ranks idle at the barrier below
-        shuttle[f"{world}_gpus_one_process"] = run_shuttle_bench(wl.key, wl.w, wl.rows_total, 3, list(range(world)))
+        shuttle[f"{world}_gpus_one_process"] = run_shuttle_bench(wl.key, wl.w, wl.rows_total, 5, list(range(world)))
     if dist is not None:
         dist.barrier()
 
