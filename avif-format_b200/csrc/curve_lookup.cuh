@@ -82,6 +82,56 @@ __device__ __forceinline__ float LookupCurveFlat(uint32_t bits, const uint2* __r
     return LookupCurveFlat(bits, flat, shift, negativeLow, span, inBand, entry);
 }
 
+// Compact look-up (curve_tables.h "Compact entries").  topShift = 32 - flatShift, bandShift = topShift + 5.
+// Thirteen instructions and one 32-bit shared-memory load; the code comes out as a float like LookupCurveFlat's.
+__device__ __forceinline__ float LookupCurveCompact(uint32_t bits, const uint32_t* __restrict__ compact, uint32_t shift, int32_t negativeLow, int32_t span,
+                                                    uint32_t topShift, uint32_t bandShift, uint32_t codeMask, bool& inBand, uint32_t& entryOut)
+{
+    const int32_t index = __viaddmin_s32_relu(static_cast<int32_t>(bits) >> shift, negativeLow, span);
+    const uint32_t entry = compact[index];
+    entryOut = entry;
+    const uint32_t t = entry + (bits << topShift);
+    // 2^23 + (field << 6) is exact in binary32; (x - 2^23) / 64 in one fma
+    float code = __fmaf_rn(__uint_as_float((entry & codeMask) | 0x4b000000u), 1.0f / 64.0f, -131072.0f);
+    if (t < entry) // carry: bits >= first_k of a step bucket
+    {
+        code += 1.0f;
+    }
+    inBand = (t >> bandShift) < (entry & ((1u << kCompactLenBits) - 1u));
+    return code;
+}
+
+// The exact code of a sample LookupCurveCompact flagged, `fastCode` being what it returned for it.
+__device__ __forceinline__ uint32_t ResolveCompactInBand(uint32_t bits, uint32_t entry, uint32_t fastCode, uint32_t topShift, uint32_t codeMask,
+                                                         const uint32_t* __restrict__ firstBits, const uint32_t* __restrict__ bandBits, uint32_t strideLog2)
+{
+    const uint32_t k = ((entry & codeMask) >> kCompactLenBits) + ((entry >> topShift) != 0 ? 1u : 0u); // the step whose band this is
+    const uint32_t distance = bits - firstBits[k];
+    if (k == 0 || distance >= (1u << strideLog2))
+    {
+        return fastCode; // flagged by the superset test only (below first_k, wrapped): the table's answer stands
+    }
+    const uint32_t index = (k << strideLog2) + distance;
+    const uint32_t word = __ldg(bandBits + (index >> 5));
+    return ((word >> (index & 31u)) & 1u) ? k : k - 1u;
+}
+
+// Complete compact look-up for one finite sample (verifier).
+__device__ __forceinline__ uint32_t LookupCurveCodeCompactResolved(uint32_t bits, const CurveTableView& table, bool& inBand)
+{
+    const uint32_t topShift = 32u - table.flatShift;
+    uint32_t entry;
+    const float code = LookupCurveCompact(bits, table.compact, table.flatShift, -static_cast<int32_t>(table.flatLow),
+                                          static_cast<int32_t>(table.flatHigh - table.flatLow), topShift, topShift + kCompactLenUnitLog2, table.compactCodeMask,
+                                          inBand, entry);
+    uint32_t result = static_cast<uint32_t>(code);
+    if (inBand)
+    {
+        result = ResolveCompactInBand(bits, entry, result, topShift, table.compactCodeMask, table.firstBits, table.bandBits, table.bandStrideLog2);
+    }
+    return result;
+}
+
 // Position of an in-band sample's bit in CurveTableView::bandBits (entry = the sample's flat entry).
 __device__ __forceinline__ uint32_t BandBitIndex(uint32_t bits, const uint2 entry, uint32_t strideLog2)
 {

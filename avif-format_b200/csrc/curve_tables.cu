@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kSweepThreads) VerifyKernel(float pqMultiplier
     unsigned long long mismatches = 0;
     unsigned long long inBandCount = 0;
     unsigned long long flatInBand = 0;
+    unsigned long long compactInBand = 0;
     // +inf and the positive NaNs are part of the check (bits up to 0x7fffffff): they must come out as code 0.
     const uint64_t total = 0x80000000ull;
     for (uint64_t u = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; u < total;
@@ -89,6 +90,18 @@ __global__ void __launch_bounds__(kSweepThreads) VerifyKernel(float pqMultiplier
                 {
                     ++flatInBand;
                 }
+                if (table.compact != nullptr)
+                {
+                    bool inBandCompact;
+                    if (LookupCurveCodeCompactResolved(bits, table, inBandCompact) != ExactCurveCode<CURVE>(__uint_as_float(bits), pqMultiplier, maxCodeFloat, t))
+                    {
+                        ++mismatches;
+                    }
+                    if (inBandCompact)
+                    {
+                        ++compactInBand;
+                    }
+                }
             }
         }
         if (inBand)
@@ -105,12 +118,14 @@ __global__ void __launch_bounds__(kSweepThreads) VerifyKernel(float pqMultiplier
         mismatches += __shfl_down_sync(0xffffffffu, mismatches, offset);
         inBandCount += __shfl_down_sync(0xffffffffu, inBandCount, offset);
         flatInBand += __shfl_down_sync(0xffffffffu, flatInBand, offset);
+        compactInBand += __shfl_down_sync(0xffffffffu, compactInBand, offset);
     }
     if ((threadIdx.x & 31) == 0)
     {
         if (mismatches) atomicAdd(&counters[0], mismatches);
         if (inBandCount) atomicAdd(&counters[1], inBandCount);
         if (flatInBand) atomicAdd(&counters[2], flatInBand);
+        if (compactInBand) atomicAdd(&counters[3], compactInBand);
     }
 }
 
@@ -131,13 +146,17 @@ __global__ void __launch_bounds__(kSweepThreads) FillBandBitsKernel(float pqMult
     {
         const uint3 band = bands[w / wordsPerBand];
         const uint32_t offset = static_cast<uint32_t>(w % wordsPerBand) * 32u + lane;
+        // Every offset of the stride is answered, not only the band proper: the compact table's in-band test rounds a band
+        // up to 32 floats, and past the band the exact code is k (or more) anyway.  +inf / NaN never get here (callers
+        // route them to the exact evaluation), but the bitmap must not claim anything about them: left 0.
         bool atOrAbove = false;
-        if (offset < band.y)
+        const uint64_t input = static_cast<uint64_t>(band.x) + offset;
+        if (input <= 0x7f7fffffull)
         {
-            atOrAbove = ExactCurveCode<CURVE>(__uint_as_float(band.x + offset), pqMultiplier, maxCodeFloat, t) >= band.z;
+            atOrAbove = ExactCurveCode<CURVE>(__uint_as_float(static_cast<uint32_t>(input)), pqMultiplier, maxCodeFloat, t) >= band.z;
         }
         const uint32_t word = __ballot_sync(0xffffffffu, atOrAbove);
-        if (lane == 0 && offset < band.y)
+        if (lane == 0)
         {
             bandBits[((static_cast<uint64_t>(band.z) << strideLog2) >> 5) + (w % wordsPerBand)] = word;
         }
@@ -176,6 +195,10 @@ void FreeCurveTable(CurveTable* table)
     if (table->deviceBuckets) cudaFree(table->deviceBuckets);
     if (table->deviceFlat) cudaFree(table->deviceFlat);
     if (table->deviceBandBits) cudaFree(table->deviceBandBits);
+    if (table->deviceCompact) cudaFree(table->deviceCompact);
+    if (table->deviceFirstBits) cudaFree(table->deviceFirstBits);
+    table->deviceCompact = nullptr;
+    table->deviceFirstBits = nullptr;
     table->deviceOctaves = nullptr;
     table->deviceBuckets = nullptr;
     table->deviceFlat = nullptr;
@@ -390,6 +413,7 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
 
     // ---- flat variant ----------------------------------------------------------------------------------------
     std::vector<uint2> flat;
+    std::vector<uint32_t> compact;
     std::vector<uint3> flatBands; // {first, width, k} of every step with a fuzzy band
     uint32_t flatShift = 0, flatLow = 0, flatHigh = 0, bandStrideLog2 = 5;
     if (!steps.empty())
@@ -453,11 +477,63 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
                     }
                 }
                 usable = usable && ((static_cast<uint64_t>(codeCount) << bandStrideLog2) / 8u) <= kBandBitmapMaxBytes;
+                // ---- compact variant (curve_tables.h "Compact entries") over the same buckets
+                if (usable && static_cast<uint32_t>(shift) + static_cast<uint32_t>(depth) + kCompactLenBits <= 32u)
+                {
+                    const uint32_t topShift = 32u - static_cast<uint32_t>(shift);
+                    const uint32_t lenMax = (1u << kCompactLenBits) - 1u;
+                    bool fits = true;
+                    compact.resize(count);
+                    size_t at = 0;
+                    for (uint64_t b = 0; b < count && fits; ++b)
+                    {
+                        const uint64_t bLo = (static_cast<uint64_t>(flatLow) + b) << shift;
+                        const uint64_t bHi = bLo + (1ull << shift);
+                        while (at < steps.size() && steps[at].end < bLo)
+                        {
+                            ++at;
+                        }
+                        uint32_t top = 0, field, inBandFloats = 0;
+                        if (at < steps.size() && steps[at].first < bHi)
+                        {
+                            const Step& step = steps[at];
+                            const bool banded = step.end > step.first;
+                            if (step.first > bLo)
+                            {
+                                // the step starts inside this bucket: code = (k - 1) + carry
+                                top = static_cast<uint32_t>((1ull << shift) - (step.first - bLo));
+                                field = step.k - 1u;
+                                inBandFloats = banded ? static_cast<uint32_t>(std::min<uint64_t>(step.end, bHi - 1) - step.first + 1u) : 0u;
+                            }
+                            else
+                            {
+                                // the step sits exactly on the bucket start, or this is the tail of a band that began in the
+                                // previous bucket: every float here is at or above first_k
+                                field = step.k;
+                                inBandFloats = banded ? static_cast<uint32_t>(std::min<uint64_t>(step.end, bHi - 1) - bLo + 1u) : 0u;
+                            }
+                        }
+                        else
+                        {
+                            field = static_cast<uint32_t>(at); // no step: code = steps below
+                        }
+                        const uint32_t lenq = (inBandFloats + (1u << kCompactLenUnitLog2) - 1u) >> kCompactLenUnitLog2;
+                        fits = lenq <= lenMax && field <= maxCode;
+                        compact[b] = (top << topShift) | (field << kCompactLenBits) | lenq;
+                    }
+                    // the band bitmap answers bits - first_k < 2^stride for every banded step: the rounded-up test must stay inside it
+                    fits = fits && (1u << bandStrideLog2) >= (1u << kCompactLenUnitLog2);
+                    if (!fits)
+                    {
+                        compact.clear();
+                    }
+                }
             }
         }
         if (!usable)
         {
             flat.clear();
+            compact.clear();
         }
     }
 
@@ -475,6 +551,9 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     table->view.flatCount = 0;
     table->view.bandBits = nullptr;
     table->view.bandStrideLog2 = 0;
+    table->view.compact = nullptr;
+    table->view.firstBits = nullptr;
+    table->view.compactCodeMask = 0;
     if (!flat.empty())
     {
         if (!Check(cudaMalloc(&table->deviceFlat, (flat.size() + 1) * sizeof(uint2)), "cudaMalloc", &table->error) ||
@@ -526,11 +605,33 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
         table->view.bandBits = static_cast<const uint32_t*>(table->deviceBandBits);
         table->view.bandStrideLog2 = bandStrideLog2;
         table->stats.bandBitmapBytes = bitmapBytes;
+        if (!compact.empty())
+        {
+            std::vector<uint32_t> firstBits(codeCount + 1, 0u);
+            for (const Step& step : steps)
+            {
+                firstBits[step.k] = step.first;
+            }
+            if (!Check(cudaMalloc(&table->deviceCompact, (compact.size() + 4) * sizeof(uint32_t)), "cudaMalloc", &table->error) ||
+                !Check(cudaMalloc(&table->deviceFirstBits, firstBits.size() * sizeof(uint32_t)), "cudaMalloc", &table->error) ||
+                !Check(cudaMemsetAsync(table->deviceCompact, 0, (compact.size() + 4) * sizeof(uint32_t), stream), "memset", &table->error) ||
+                !Check(cudaMemcpyAsync(table->deviceCompact, compact.data(), compact.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "H2D", &table->error) ||
+                !Check(cudaMemcpyAsync(table->deviceFirstBits, firstBits.data(), firstBits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "H2D", &table->error) ||
+                !Check(cudaStreamSynchronize(stream), "compact table upload", &table->error))
+            {
+                FreeCurveTable(table);
+                return false;
+            }
+            table->view.compact = static_cast<const uint32_t*>(table->deviceCompact);
+            table->view.firstBits = static_cast<const uint32_t*>(table->deviceFirstBits);
+            table->view.compactCodeMask = maxCode << kCompactLenBits;
+            table->stats.compactBuckets = static_cast<int32_t>(compact.size());
+        }
     }
     unsigned long long* dCounters = nullptr;
     ok = Check(cudaMemcpyAsync(table->deviceOctaves, octaves.data(), octaves.size() * sizeof(uint2), cudaMemcpyHostToDevice, stream), "H2D", &table->error) &&
          Check(cudaMemcpyAsync(table->deviceBuckets, buckets.data(), buckets.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "H2D", &table->error) &&
-         Check(cudaMalloc(&dCounters, 3 * sizeof(unsigned long long)), "cudaMalloc", &table->error);
+         Check(cudaMalloc(&dCounters, 4 * sizeof(unsigned long long)), "cudaMalloc", &table->error);
     if (!ok)
     {
         FreeCurveTable(table);
@@ -538,7 +639,7 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     }
 
     // ---- pass 2: verify every input ---------------------------------------------------------------------------
-    cudaMemsetAsync(dCounters, 0, 3 * sizeof(unsigned long long), stream);
+    cudaMemsetAsync(dCounters, 0, 4 * sizeof(unsigned long long), stream);
     if (curve == kCurveLinearToPQ)
     {
         VerifyKernel<kCurveLinearToPQ><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, table->view, dCounters);
@@ -551,7 +652,7 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     {
         VerifyKernel<kCurveLinearToHLG><<<grid, kSweepThreads, 0, stream>>>(pqMultiplier, maxCodeFloat, table->view, dCounters);
     }
-    unsigned long long counters[3] = { 0, 0, 0 };
+    unsigned long long counters[4] = { 0, 0, 0, 0 };
     ok = Check(cudaMemcpyAsync(counters, dCounters, sizeof(counters), cudaMemcpyDeviceToHost, stream), "D2H", &table->error) &&
          Check(cudaStreamSynchronize(stream), "curve verify", &table->error);
     cudaFree(dCounters);
@@ -563,6 +664,7 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     table->stats.verifyMismatches = counters[0];
     table->stats.inBandInputs = counters[1];
     table->stats.flatInBandInputs = counters[2];
+    table->stats.compactInBandInputs = counters[3];
     table->stats.flatBuckets = table->view.flatCount;
     table->stats.buildMilliseconds = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (counters[0] != 0)

@@ -78,7 +78,28 @@ struct CurveTableView
     uint32_t flatHigh;        // bucket number of flat[flatCount - 1]
     const uint32_t* bandBits; // (maxCode + 1) << bandStrideLog2 bits: the exact answer for every in-band float
     uint32_t bandStrideLog2;  // bits reserved per step (power of two >= the widest band)
+    // Compact variant of the flat table (same buckets: flatShift / flatLow / flatHigh), one 32-bit word per bucket, or
+    // nullptr.  See "Compact entries" below.
+    const uint32_t* compact;
+    const uint32_t* firstBits; // first_k for k = 0 .. maxCode + 1 (0 for codes that no input reaches)
+    uint32_t compactCodeMask;  // ((1 << depth) - 1) << 6
 };
+
+// Compact entries.  A random 64-bit gather from shared memory costs ~5.2 data-pipe wavefronts (two half-warp phases of
+// 16 random bank pairs), a 32-bit one ~3.5, and the config-2 kernel is bound by exactly that pipe -- so the flat table
+// is also kept in a one-word form, S = flatShift, D = depth (needs S + D + 6 <= 32):
+//     bits 31 .. 32-S   step bucket: 2^S - off, off = first_k - bucketStart in (0, 2^S);  otherwise 0
+//     bits D+5 .. 6     step bucket: k - 1;  otherwise the code of every float of the bucket (before band corrections)
+//     bits 5 .. 0       lenq: the in-band floats of the bucket are those less than 32 * lenq above the band start
+//                       (band start = first_k for a step bucket, the bucket start for the tail of a band that began in
+//                       the previous bucket or for a step sitting exactly on the bucket start)
+// With t = entry + (bits << (32 - S)): the carry out of bit 31 says bits >= first_k, so code = field + carry, and the top
+// S bits of t are the distance from the band start, so in band <=> (t >> (37 - S)) < lenq.  The test is a superset:
+// a sample below first_k whose wrapped distance happens to be small is flagged too, and lenq rounds the band up to 32
+// floats; the band bitmap (indexed by k and bits - first_k, filled over its whole stride) gives the exact code for every
+// flagged sample, and ResolveCompactInBand leaves the unflagged-worthy ones as they are.
+constexpr uint32_t kCompactLenBits = 6;
+constexpr uint32_t kCompactLenUnitLog2 = 5;
 
 struct CurveTableStats
 {
@@ -88,6 +109,8 @@ struct CurveTableStats
     uint64_t flatInBandInputs = 0; // flat variant: inputs resolved through the band bitmap (exact per-step widths)
     uint64_t bandBitmapBytes = 0;  // size of the flat variant's band bitmap
     int32_t flatBuckets = 0;       // 0 when the flat variant does not apply
+    uint64_t compactInBandInputs = 0; // compact variant: inputs flagged in band (a superset of flatInBandInputs)
+    int32_t compactBuckets = 0;    // 0 when the compact variant does not apply
     uint64_t verifyMismatches = 0; // must be 0
     int32_t steps = 0;             // thresholds found
     int32_t bands = 0;             // thresholds with a non-empty fuzzy band
@@ -107,6 +130,8 @@ struct CurveTable
     void* deviceBuckets = nullptr;
     void* deviceFlat = nullptr;
     void* deviceBandBits = nullptr;
+    void* deviceCompact = nullptr;
+    void* deviceFirstBits = nullptr;
 };
 
 // Builds (sweeps, assembles, uploads, verifies) the table on the current device.  Synchronous; uses `stream`.

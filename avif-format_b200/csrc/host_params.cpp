@@ -354,6 +354,11 @@ void FillEncodeParams(const avifgpu_encode_desc& d, EncodeParams* p)
         p->hlgDisplayGamma = d.hlg_display_gamma;
         p->hlgPeak = static_cast<float>(d.hlg_peak_nits);
     }
+    p->rowMatrixEnabled = (d.row_matrix_enabled && d.host_depth == 32 && d.host_channels >= 3) ? 1 : 0;
+    for (int i = 0; i < 9; ++i)
+    {
+        p->rowMatrix[i] = d.row_matrix[i];
+    }
     p->planar = d.layout == AVIFGPU_LAYOUT_PLANAR_YCBCR;
     if (p->planar)
     {

@@ -69,6 +69,8 @@ struct EncodeParams
     float hlgLuma[3];
     float hlgDisplayGamma;
     float hlgPeak;
+    int32_t rowMatrixEnabled; // avifgpu_encode_desc.row_matrix: the colour-profile 3x3 ahead of everything else (float colour hosts)
+    float rowMatrix[9];
     // Float hosts with a transfer curve: the flat step table + band bitmap in global memory (a by-value copy of
     // *curveTable made by the generic launcher), or useCurveView = 0 -> every sample takes the exact powf.
     CurveTableView curveView;

@@ -12,6 +12,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 
 namespace avifgpu
 {
@@ -143,6 +144,10 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
     const bool rgba = p.channels == 4 && p.hasAlpha;
+    if (p.rowMatrixEnabled)
+    {
+        return 0; // the colour-profile matrix is a prologue of the generic kernels only (they still use the step tables)
+    }
     if (hostDepth == 32 && !p.planar && p.channels == 3 && !p.hasAlpha && p.imageDepth > 8 && !p.hlgInverseOotf &&
         (p.transfer == AVIFGPU_TRANSFER_PQ || p.transfer == AVIFGPU_TRANSFER_SMPTE428) && p.curveTable != nullptr && p.curveTable->buckets != nullptr)
     {
@@ -240,6 +245,8 @@ int LaunchEncodeFast(const EncodeParams& p, int hostDepth, void* streamHandle)
     if (curve != kCurveClip)
     {
         fp.table = *p.curveTable;
+        static const bool wide = []() { const char* v = std::getenv("AVIFGPU_WIDE_TABLE_ENTRIES"); return v != nullptr && v[0] == '1'; }();
+        fp.preferWideEntries = wide ? 1 : 0;
     }
     if (rgba)
     {

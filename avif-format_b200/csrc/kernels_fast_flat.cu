@@ -93,8 +93,11 @@ __device__ __forceinline__ void BarrierWait(uint32_t barrier, uint32_t parity)
         : "memory");
 }
 
-// TWO_LEVEL = 0: the flat table + band bitmap.  TWO_LEVEL = 1: the per-binade two-level table (curves whose steps are too
-// dense for one bucket size, e.g. 12-bit SMPTE 428); its rare in-band samples take the exact evaluation in place.
+// TWO_LEVEL = 0: the flat table (64-bit entries) + band bitmap.  TWO_LEVEL = 1: the per-binade two-level table (curves whose
+// steps are too dense for one bucket size, e.g. 12-bit SMPTE 428); its rare in-band samples take the exact evaluation in
+// place.  TWO_LEVEL = 2: the flat table in its compact one-word form (curve_tables.h "Compact entries") + the first_k
+// array + band bitmap: a 32-bit gather costs ~3.5 shared-memory wavefronts where the 64-bit one costs ~5.2, and that pipe
+// is what bounds this kernel.
 // INTERLEAVED = 1: the reference's own output layout (heif_channel_interleaved RGB, WriteHeifImage.cpp:1098-1130) -- the
 // codes are stored as they are, 3 x uint16 per pixel into plane Y's buffer, no matrix (XS = YS = 0 then).
 template <int CURVE, int XS, int YS, int TWO_LEVEL, int INTERLEAVED>
@@ -105,6 +108,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     uint64_t* barriers = reinterpret_cast<uint64_t*>(sharedBytes + kSharedLibm);
     uint8_t* stageAll = sharedBytes + kSharedLibm + kSharedBarriers;
     uint2* flatEntries = reinterpret_cast<uint2*>(sharedBytes + FlatFixedBytes());
+    uint32_t* compactEntries = reinterpret_cast<uint32_t*>(sharedBytes + FlatFixedBytes());                                  // TWO_LEVEL == 2 ...
+    uint32_t* firstBits = compactEntries + ((p.table.flatCount + 3) & ~3);                                                   // ... then first_k per code
     uint2* octaves = reinterpret_cast<uint2*>(sharedBytes + FlatFixedBytes());            // TWO_LEVEL: 256 entries ...
     uint32_t* bucketWords = reinterpret_cast<uint32_t*>(sharedBytes + FlatFixedBytes() + 2048); // ... then the bucket words
 
@@ -162,7 +167,22 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     }
 
     const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
-    if (TWO_LEVEL)
+    if (TWO_LEVEL == 2)
+    {
+        const uint4* source = reinterpret_cast<const uint4*>(p.table.compact);
+        uint4* target = reinterpret_cast<uint4*>(compactEntries);
+        const int quads = (p.table.flatCount + 3) / 4;
+#pragma unroll 8
+        for (int i = threadIdx.x; i < quads; i += blockDim.x)
+        {
+            target[i] = __ldg(source + i);
+        }
+        for (int i = threadIdx.x; i <= p.maxCode + 1; i += blockDim.x)
+        {
+            firstBits[i] = p.table.firstBits[i];
+        }
+    }
+    else if (TWO_LEVEL)
     {
         for (int i = threadIdx.x; i < 256; i += blockDim.x)
         {
@@ -192,6 +212,9 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     const int32_t span = static_cast<int32_t>(p.table.flatHigh - p.table.flatLow);
     const uint32_t bandStrideLog2 = p.table.bandStrideLog2;
     const uint32_t* __restrict__ bandBits = p.table.bandBits;
+    const uint32_t compactTopShift = 32u - flatShift;
+    const uint32_t compactBandShift = compactTopShift + kCompactLenUnitLog2;
+    const uint32_t compactCodeMask = p.table.compactCodeMask;
     uint32_t parity = 0;
 
 #pragma unroll 1
@@ -234,7 +257,12 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
             {
                 const int j = 4 * q + e;
                 bool inBand;
-                if (TWO_LEVEL)
+                if (TWO_LEVEL == 2)
+                {
+                    uint32_t entry;
+                    codeF[j] = LookupCurveCompact(bits[e], compactEntries, flatShift, negativeLow, span, compactTopShift, compactBandShift, compactCodeMask, inBand, entry);
+                }
+                else if (TWO_LEVEL)
                 {
                     codeF[j] = CodeToFloat(LookupCurveCode(bits[e], octaves, bucketWords, inBand)); // reports +inf / NaN in band itself
                 }
@@ -244,7 +272,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
                 }
                 asm("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p or.b32 %0, %0, %2; }" : "+r"(bandMask) : "r"(static_cast<uint32_t>(inBand)), "r"(1u << j));
             }
-            if (!TWO_LEVEL)
+            if (TWO_LEVEL != 1)
             {
                 largest = max(largest, __vimax3_s32(static_cast<int32_t>(w.x), static_cast<int32_t>(w.y), static_cast<int32_t>(w.z)));
                 largest = max(largest, static_cast<int32_t>(w.w));
@@ -254,7 +282,44 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
         // ---- in-band samples: one bit of the band bitmap each, two loads in flight per lane ---------------------------
         auto stagedBits = [&](int j) { return myStage[j + (j >= 12 ? kRowSegmentWords - 12 : 0)]; };
         uint32_t lowerMask = 0; // samples whose exact code is one below the table's
-        if (!TWO_LEVEL)
+        if (TWO_LEVEL == 2)
+        {
+            // flagged samples: which step, how far above its first_k, one bit of the band bitmap -- two at a time
+            uint32_t pending = bandMask;
+            while (pending != 0)
+            {
+                uint32_t word[2] = { 0xffffffffu, 0xffffffffu }, index[2] = { 0u, 0u }, sampleBit[2] = { 0u, 0u };
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                {
+                    if (pending != 0)
+                    {
+                        const int j = __ffs(static_cast<int>(pending)) - 1;
+                        pending &= pending - 1;
+                        const uint32_t bits = stagedBits(j);
+                        const int32_t bucket = __viaddmin_s32_relu(static_cast<int32_t>(bits) >> flatShift, negativeLow, span);
+                        const uint32_t entry = compactEntries[bucket];
+                        const uint32_t k = ((entry & compactCodeMask) >> kCompactLenBits) + ((entry >> compactTopShift) != 0 ? 1u : 0u);
+                        const uint32_t distance = bits - firstBits[k];
+                        if (k != 0 && distance < (1u << bandStrideLog2)) // else flagged by the superset test only: the table's code stands
+                        {
+                            index[u] = (k << bandStrideLog2) + distance;
+                            word[u] = __ldg(bandBits + (index[u] >> 5));
+                            sampleBit[u] = 1u << j;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                {
+                    if (((word[u] >> (index[u] & 31u)) & 1u) == 0)
+                    {
+                        lowerMask |= sampleBit[u];
+                    }
+                }
+            }
+        }
+        else if (!TWO_LEVEL)
         {
             uint32_t pending = bandMask;
             while (pending != 0)
@@ -288,12 +353,12 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
         }
 
         // ---- +inf / NaN (never in real frames): the exact evaluation, lane by lane ------------------------------------
-        if (__any_sync(0xffffffffu, TWO_LEVEL ? bandMask != 0 : largest > 0x7f7fffff))
+        if (__any_sync(0xffffffffu, TWO_LEVEL == 1 ? bandMask != 0 : largest > 0x7f7fffff))
         {
             for (int j = 0; j < kValuesPerLane; ++j)
             {
                 const uint32_t bits = stagedBits(j);
-                if (TWO_LEVEL ? ((bandMask >> j) & 1u) != 0 : static_cast<int32_t>(bits) > 0x7f7fffff)
+                if (TWO_LEVEL == 1 ? ((bandMask >> j) & 1u) != 0 : static_cast<int32_t>(bits) > 0x7f7fffff)
                 {
                     const float exact = CodeToFloat(ExactCurveCode<CURVE>(__uint_as_float(bits), p.pqMultiplier, p.maxCodeFloat, t));
 #pragma unroll
@@ -357,15 +422,18 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     }
 }
 
-inline size_t TableSharedBytes(const FastEncodeParams& fp, bool twoLevel)
+// tableKind: 0 flat (64-bit entries), 1 two-level, 2 compact (32-bit entries + first_k per code)
+inline size_t TableSharedBytes(const FastEncodeParams& fp, int tableKind)
 {
-    return twoLevel ? 2048 + static_cast<size_t>(fp.table.bucketCount) * sizeof(uint32_t) : static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
+    if (tableKind == 1) return 2048 + static_cast<size_t>(fp.table.bucketCount) * sizeof(uint32_t);
+    if (tableKind == 2) return (static_cast<size_t>((fp.table.flatCount + 3) & ~3) + static_cast<size_t>(fp.maxCode) + 2) * sizeof(uint32_t);
+    return static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
 }
 
 template <int CURVE, int XS, int YS, int TWO_LEVEL, int INTERLEAVED = 0>
 cudaError_t LaunchFlatKernel(const FastEncodeParams& fp, int smCount, cudaStream_t stream)
 {
-    const size_t shared = static_cast<size_t>(FlatFixedBytes()) + TableSharedBytes(fp, TWO_LEVEL != 0);
+    const size_t shared = static_cast<size_t>(FlatFixedBytes()) + TableSharedBytes(fp, TWO_LEVEL);
     static std::atomic<uint64_t> configuredDevices{ 0 }; // per instantiation
     {
         const cudaError_t e = AllowDynamicShared(EncodeRgbF32FlatKernel<CURVE, XS, YS, TWO_LEVEL, INTERLEAVED>, kSharedLimit, configuredDevices);
@@ -413,25 +481,36 @@ cudaError_t DispatchFlatChroma(const FastEncodeParams& fp, int xs, int ys, int s
 static bool FlatTableFits(const FastEncodeParams& fp)
 {
     return fp.table.flat != nullptr && fp.table.bandBits != nullptr &&
-           static_cast<size_t>(FlatFixedBytes()) + TableSharedBytes(fp, false) <= static_cast<size_t>(kSharedLimit);
+           static_cast<size_t>(FlatFixedBytes()) + TableSharedBytes(fp, 0) <= static_cast<size_t>(kSharedLimit);
+}
+
+static bool CompactTableFits(const FastEncodeParams& fp)
+{
+    return fp.table.compact != nullptr && fp.table.firstBits != nullptr && fp.table.bandBits != nullptr &&
+           static_cast<size_t>(FlatFixedBytes()) + TableSharedBytes(fp, 2) <= static_cast<size_t>(kSharedLimit);
 }
 
 static bool TwoLevelTableFits(const FastEncodeParams& fp)
 {
     return fp.table.buckets != nullptr && fp.table.octaves != nullptr &&
-           static_cast<size_t>(FlatFixedBytes()) + TableSharedBytes(fp, true) <= static_cast<size_t>(kSharedLimit);
+           static_cast<size_t>(FlatFixedBytes()) + TableSharedBytes(fp, 1) <= static_cast<size_t>(kSharedLimit);
 }
 
 // True when the copy-engine kernel can serve this table: the flat form with its bitmap, else the two-level form, in
 // shared memory next to the staging buffers.
 bool FlatEncodeApplies(const FastEncodeParams& fp)
 {
-    return FlatTableFits(fp) || TwoLevelTableFits(fp);
+    return CompactTableFits(fp) || FlatTableFits(fp) || TwoLevelTableFits(fp);
 }
 
 // The reference's interleaved RGB layout through the same kernel (fp.planeY / strideY = the interleaved buffer).
 cudaError_t LaunchFastEncodeFlatInterleaved(const FastEncodeParams& fp, int curve, int smCount, cudaStream_t stream)
 {
+    if (CompactTableFits(fp))
+    {
+        if (curve == kCurveLinearToPQ) return LaunchFlatKernel<kCurveLinearToPQ, 0, 0, 2, 1>(fp, smCount, stream);
+        return LaunchFlatKernel<kCurveLinearToSMPTE428, 0, 0, 2, 1>(fp, smCount, stream);
+    }
     if (FlatTableFits(fp))
     {
         if (curve == kCurveLinearToPQ) return LaunchFlatKernel<kCurveLinearToPQ, 0, 0, 0, 1>(fp, smCount, stream);
@@ -443,6 +522,11 @@ cudaError_t LaunchFastEncodeFlatInterleaved(const FastEncodeParams& fp, int curv
 
 cudaError_t LaunchFastEncodeFlat(const FastEncodeParams& fp, int curve, int xs, int ys, int smCount, cudaStream_t stream)
 {
+    if (CompactTableFits(fp) && !fp.preferWideEntries)
+    {
+        if (curve == kCurveLinearToPQ) return DispatchFlatChroma<kCurveLinearToPQ, 2>(fp, xs, ys, smCount, stream);
+        return DispatchFlatChroma<kCurveLinearToSMPTE428, 2>(fp, xs, ys, smCount, stream);
+    }
     if (FlatTableFits(fp))
     {
         if (curve == kCurveLinearToPQ) return DispatchFlatChroma<kCurveLinearToPQ, 0>(fp, xs, ys, smCount, stream);

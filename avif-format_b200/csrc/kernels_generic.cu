@@ -59,6 +59,14 @@ __device__ __forceinline__ void HostPixelToCodes(const EncodeParams& p, const Ho
         {
             color[i] = (i < colors) ? px[i] : 0.0f;
         }
+        if (p.rowMatrixEnabled && colors == 3)
+        {
+            // the colour-profile step (ColorProfileConversion::ConvertRow before the per-pixel loop, WriteHeifImage.cpp:1028-1031)
+            const float r = color[0], g = color[1], b = color[2];
+            color[0] = ((p.rowMatrix[0] * r) + (p.rowMatrix[1] * g)) + (p.rowMatrix[2] * b);
+            color[1] = ((p.rowMatrix[3] * r) + (p.rowMatrix[4] * g)) + (p.rowMatrix[5] * b);
+            color[2] = ((p.rowMatrix[6] * r) + (p.rowMatrix[7] * g)) + (p.rowMatrix[8] * b);
+        }
         if (p.hasAlpha)
         {
             alpha = ClampF(px[colors], 0.0f, 1.0f);

@@ -28,6 +28,7 @@ namespace
     avifgpu_host::RowTransformFactory g_transformFactory = nullptr;
     void* g_transformUser = nullptr;
     avifgpu_host::ShuttleTimes g_times{};
+    bool g_gpuRowMatrix = true;
 
     using Clock = std::chrono::steady_clock;
     double Seconds(Clock::time_point from) { return std::chrono::duration<double>(Clock::now() - from).count(); }
@@ -219,8 +220,10 @@ namespace
 
     // The per-save colour-profile step of CreateHeifImageRGB*Bit (WriteHeifImage.cpp:651, 830, 1015), or nullptr when the
     // reference would not convert.  Gray saves never convert (WriteHeifImage.cpp:169-627 construct no converter).
+    // `desc` receives the GPU form of the step when the profile allows it (a 3x3 matrix ahead of the conversion,
+    // avifgpu_encode_desc.row_matrix) -- then no host-side transform is returned.
     std::unique_ptr<avifgpu_host::RowTransform> MakeRowTransform(FormatRecordPtr formatRecord, bool gray, bool hasAlpha, int hostDepth,
-                                                                 const SaveUIOptions& saveOptions)
+                                                                 const SaveUIOptions& saveOptions, avifgpu_encode_desc* desc)
     {
         if (gray || !RecordHasColorProfile(formatRecord))
         {
@@ -233,6 +236,28 @@ namespace
         {
             return nullptr;
         }
+#if !defined(AVIFGPU_HOST_USE_PLUGIN_HEADERS)
+        // HDR save of a linear-light document in a matrix profile: the whole lcms2 transform is one 3x3 matrix, which the
+        // GPU applies ahead of the conversion.  (In the plug-in tree iCCprofileData is a Handle and the
+        // plug-in's own lcms2 converter below is the default; the compat record holds the profile bytes directly.)
+        if (g_gpuRowMatrix && hostDepth == 32 && saveOptions.hdrTransferFunction != ColorTransferFunction::Clip)
+        {
+            float matrix[9];
+            int32_t alreadyRec2020 = 0;
+            if (avifgpu_icc_to_rec2020_linear_matrix(formatRecord->iCCprofileData, static_cast<size_t>(formatRecord->iCCprofileSize), matrix,
+                                                     &alreadyRec2020) == AVIFGPU_OK)
+            {
+                if (!alreadyRec2020) // ColorProfileConversion.cpp:128-131: a Rec.2020 document is not converted
+                {
+                    desc->row_matrix_enabled = 1;
+                    std::memcpy(desc->row_matrix, matrix, sizeof(matrix));
+                }
+                return nullptr;
+            }
+        }
+#else
+        (void)desc;
+#endif
         if (g_transformFactory != nullptr)
         {
             return std::unique_ptr<avifgpu_host::RowTransform>(
@@ -388,7 +413,7 @@ namespace
         {
             throw std::bad_alloc(); // Write.cpp:286-295
         }
-        std::unique_ptr<avifgpu_host::RowTransform> transform = MakeRowTransform(formatRecord, gray, hasAlpha, hostDepth, saveOptions);
+        std::unique_ptr<avifgpu_host::RowTransform> transform = MakeRowTransform(formatRecord, gray, hasAlpha, hostDepth, saveOptions, &desc);
         StagingPair staging(ctx, rowBytes, imageSize.v);
         const int32 blockRows = staging.blockRows;
         g_times.rowsPerBlock = blockRows;
@@ -681,6 +706,8 @@ void SetRowTransformFactory(RowTransformFactory factory, void* user)
     g_transformFactory = factory;
     g_transformUser = user;
 }
+
+void SetGpuRowMatrixEnabled(bool enabled) { g_gpuRowMatrix = enabled; }
 
 ShuttleTimes LastShuttleTimes() { return g_times; }
 

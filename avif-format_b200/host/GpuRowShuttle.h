@@ -66,6 +66,12 @@ using RowTransformFactory = RowTransform* (*)(FormatRecordPtr formatRecord, bool
                                              ColorTransferFunction transferFunction, bool keepEmbeddedColorProfile, void* user);
 void SetRowTransformFactory(RowTransformFactory factory, void* user);
 
+// HDR saves (32-bit documents, PQ / SMPTE 428) of a document whose profile is a matrix / TRC RGB profile with linear tone
+// curves: the conversion to linear Rec.2020 is a 3x3 matrix, applied on the GPU ahead of the conversion
+// (avifgpu_icc_to_rec2020_linear_matrix, avifgpu_encode_desc.row_matrix) instead of a host-side row transform.  On by
+// default where the FormatRecord holds the profile bytes; any other profile falls through to the RowTransformFactory.
+void SetGpuRowMatrixEnabled(bool enabled);
+
 // Where the time of the last CreateHeifImage* / ReadHeifImage* call went (seconds).
 struct ShuttleTimes
 {

@@ -93,8 +93,20 @@ def library():
         [group_p, C.POINTER(abi.DecodeDesc), C.POINTER(abi.Planes), C.c_int32, C.c_int32, C.c_void_p, C.c_int64])
     sig("avifgpu_encode_rows_sharded_device", C.c_int,
         [group_p, C.POINTER(abi.EncodeDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(abi.Planes), C.c_int32])
+    sig("avifgpu_icc_to_rec2020_linear_matrix", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int32)])
     _lib = lib
     return lib
+
+
+def icc_to_rec2020_linear_matrix(profile_bytes):
+    """(3x3 float32 matrix, is_rec2020) for a matrix / TRC RGB profile with linear tone curves; raises for anything else."""
+    out = np.zeros(9, np.float32)
+    same = C.c_int32(0)
+    buf = (C.c_uint8 * len(profile_bytes)).from_buffer_copy(profile_bytes)
+    status = library().avifgpu_icc_to_rec2020_linear_matrix(buf, len(profile_bytes), out.ctypes.data, C.byref(same))
+    if status != 0:
+        raise AvifGpuError(status, "avifgpu_icc_to_rec2020_linear_matrix")
+    return out.reshape(3, 3), bool(same.value)
 
 
 def shard_row_blocks(y0, nrows, parts):
@@ -119,7 +131,7 @@ EXPORTED_SYMBOLS = [
     "avifgpu_shard_group_create", "avifgpu_shard_group_destroy", "avifgpu_shard_group_size", "avifgpu_shard_group_context",
     "avifgpu_shard_group_peer_access", "avifgpu_shard_group_last_error", "avifgpu_shard_group_prepare_encode",
     "avifgpu_shard_group_synchronize", "avifgpu_shard_row_blocks", "avifgpu_encode_rows_sharded", "avifgpu_decode_rows_sharded",
-    "avifgpu_encode_rows_sharded_device",
+    "avifgpu_encode_rows_sharded_device", "avifgpu_icc_to_rec2020_linear_matrix",
 ]
 
 

@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-API_VERSION = 3
+API_VERSION = 4
 
 # avifgpu_status
 OK = 0
@@ -86,6 +86,8 @@ class EncodeDesc(C.Structure):
         ("hlg_extension", C.c_int32),
         ("hlg_display_gamma", C.c_float),
         ("hlg_peak_nits", C.c_int32),
+        ("row_matrix_enabled", C.c_int32),
+        ("row_matrix", C.c_float * 9),
     ]
 
     def __init__(self, width, height, host_depth, host_channels, alpha_state=ALPHA_NONE, image_bit_depth=8,

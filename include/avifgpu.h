@@ -50,7 +50,7 @@ extern "C" {
 #define AVIFGPU_EXPORT __attribute__((visibility("default")))
 #endif
 
-#define AVIFGPU_API_VERSION 3
+#define AVIFGPU_API_VERSION 4
 
 typedef enum avifgpu_status
 {
@@ -174,6 +174,14 @@ typedef struct avifgpu_encode_desc
     int32_t hlg_extension;       /* avifgpu_hlg_extension */
     float hlg_display_gamma;     /* for AVIFGPU_HLG_INVERSE_OOTF_THEN_OETF (LoadUIOptions.hlg.displayGamma's counterpart) */
     int32_t hlg_peak_nits;       /* nominal peak brightness of the display-referred input */
+    /* Colour-profile step on the GPU, colour float hosts only.  The reference converts every host row
+     * with lcms2 before anything else (ColorProfileConversion::ConvertRow at WriteHeifImage.cpp:1028-1031); for a
+     * linear-light document in a matrix profile that conversion is one 3x3 matrix, applied here per pixel in binary32,
+     * alpha untouched (cmsFLAGS_COPY_ALPHA), before the clamp / premultiply / transfer curve:
+     *     r' = (m[0] r + m[1] g) + m[2] b,  g' = (m[3] r + m[4] g) + m[5] b,  b' = (m[6] r + m[7] g) + m[8] b
+     * avifgpu_icc_to_rec2020_linear_matrix() derives it from an ICC profile.  Parity unpinned (lcms2 is not in the tree). */
+    int32_t row_matrix_enabled;
+    float row_matrix[9];
 } avifgpu_encode_desc;
 
 /* Parameter block of the decode direction = heif_image properties + nclx + LoadUIOptions
@@ -246,6 +254,13 @@ AVIFGPU_EXPORT int avifgpu_get_hlg_luma_coefficients(int32_t color_primaries, fl
 /* YUVLookupTables ctor, YuvLookupTables.cpp:115-192.  Each non-NULL table receives 1 << bit_depth floats. */
 AVIFGPU_EXPORT int avifgpu_build_yuv_tables(const avifgpu_nclx* nclx, int32_t bit_depth, int32_t monochrome,
                                             float* out_table_y, float* out_table_uv, float* out_table_alpha);
+
+/* ICC profile -> the matrix of avifgpu_encode_desc.row_matrix for an HDR save (document RGB, linear light -> linear
+ * Rec.2020, what ColorProfileConversion::InitializeForRec2020Conversion sets up, ColorProfileConversion.cpp:240-266).
+ * AVIFGPU_OK: out_matrix9 filled; *out_is_rec2020 = 1 when the profile already is Rec.2020 (the reference then converts
+ * nothing, ColorProfileConversion.cpp:128-131).  AVIFGPU_ERR_UNSUPPORTED: not a matrix / TRC RGB profile with identity
+ * tone curves (LUT profiles, gamma-encoded profiles: those stay with the host's lcms2).  Pure host arithmetic. */
+AVIFGPU_EXPORT int avifgpu_icc_to_rec2020_linear_matrix(const void* icc_profile, size_t size, float* out_matrix9, int32_t* out_is_rec2020);
 
 /* ---- the hot path: host-pointer variants (PCIe inside) ---------------------------------------------- */
 

@@ -656,6 +656,17 @@ static int host_pixel_to_codes(const avifgpu_encode_desc* d, const void* pixel, 
         float color[3];
         float alpha = 0.0f;
         for (i = 0; i < colors; ++i) color[i] = src[i];
+        if (d->row_matrix_enabled && colors == 3)
+        {
+            /* The colour-profile step: ConvertRow runs over the raw host row before the per-pixel loop
+             * (WriteHeifImage.cpp:1028-1031); alpha is copied (cmsFLAGS_COPY_ALPHA).  This project's definition of the
+             * matrix case, see include/avifgpu.h (parity unpinned: lcms2 is not in the reference tree). */
+            const float r = color[0], g = color[1], b = color[2];
+            const float* m = d->row_matrix;
+            color[0] = ((m[0] * r) + (m[1] * g)) + (m[2] * b);
+            color[1] = ((m[3] * r) + (m[4] * g)) + (m[5] * b);
+            color[2] = ((m[6] * r) + (m[7] * g)) + (m[8] * b);
+        }
         if (has_alpha)
         {
             alpha = clamp_f(src[colors], 0.0f, 1.0f);

@@ -135,6 +135,14 @@ def encode_cases(sizes=None, full=True):
                 desc = abi.EncodeDesc(w, h, 32, channels, alpha, depth, abi.TRANSFER_HLG, 80, layout, abi.CHROMA_420, abi.DOWN_FILTER_BOX,
                                       abi.GRAY16_LUT, NCLX_2020_HLG(), hlg_extension=extension, hlg_display_gamma=1.2, hlg_peak_nits=1000)
                 yield name, desc, float_host_rows(rng, h, w, channels), False
+        # -- colour-profile matrix ahead of the float pipeline (lcms2 is not in the tree: restatement only)
+        for channels, alpha, layout, transfer in ((3, abi.ALPHA_NONE, abi.LAYOUT_PLANAR_YCBCR, abi.TRANSFER_PQ), (4, abi.ALPHA_PREMULTIPLIED, abi.LAYOUT_PLANAR_YCBCR, abi.TRANSFER_PQ),
+                                                  (4, abi.ALPHA_STRAIGHT, abi.LAYOUT_REFERENCE, abi.TRANSFER_SMPTE428), (3, abi.ALPHA_NONE, abi.LAYOUT_REFERENCE, abi.TRANSFER_CLIP)):
+            name = f"enc_rowmatrix_c{channels}_a{alpha}_l{layout}_t{transfer}_{w}x{h}"
+            desc = abi.EncodeDesc(w, h, 32, channels, alpha, 12, transfer, 1000, layout, abi.CHROMA_420, abi.DOWN_FILTER_BOX, abi.GRAY16_LUT, NCLX_2020_PQ())
+            desc.row_matrix_enabled = 1
+            desc.row_matrix = type(desc.row_matrix)(*ROW_MATRIX_709_TO_2020)
+            yield name, desc, float_host_rows(rng_for(name), h, w, channels), False
         # -- gray16 -> SMPTE 428 (BASELINE config 5, this project's composition)
         for channels in (1, 2):
             alpha = abi.ALPHA_NONE if channels == 1 else abi.ALPHA_STRAIGHT
@@ -147,6 +155,10 @@ def encode_cases(sizes=None, full=True):
         yield name, abi.EncodeDesc(w, h, 32, 3, abi.ALPHA_NONE, 12, abi.TRANSFER_PQ, 80), float_host_rows(rng_for(name), h, w, 3, True), False
         name = f"enc_beyond_h16_{w}x{h}"
         yield name, abi.EncodeDesc(w, h, 16, 4, abi.ALPHA_PREMULTIPLIED, 10), int_host_rows(rng_for(name), h, w, 4, 16, True), False
+
+
+# linear Rec.709 -> linear Rec.2020 (ITU-R BT.2087-0), the matrix a linear sRGB-primaries document needs for an HDR save
+ROW_MATRIX_709_TO_2020 = (0.6274039, 0.3292830, 0.0433131, 0.0690973, 0.9195404, 0.0113623, 0.0163914, 0.0880133, 0.8955953)
 
 
 # ---- decode inputs ---------------------------------------------------------------------------------------------

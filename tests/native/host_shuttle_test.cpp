@@ -201,6 +201,40 @@ namespace
         return g_lastTransform;
     }
 
+    // A minimal ICC profile: RGB / XYZ, linear Rec.709 primaries (D65) adapted to D50 (the sRGB profile's colorants), identity
+    // tone curves -- the profile Photoshop attaches to a 32-bit document in the "sRGB (linear)" working space.
+    std::vector<unsigned char> MakeLinearRec709Profile()
+    {
+        const double colorants[3][3] = { { 0.43607, 0.22249, 0.01392 }, { 0.38515, 0.71687, 0.09708 }, { 0.14307, 0.06061, 0.71410 } }; // r, g, b columns as (X, Y, Z)
+        std::vector<unsigned char> p(128, 0);
+        auto put32 = [&](size_t at, uint32_t v) { p[at] = v >> 24; p[at + 1] = (v >> 16) & 0xff; p[at + 2] = (v >> 8) & 0xff; p[at + 3] = v & 0xff; };
+        auto append32 = [&](uint32_t v) { p.push_back(v >> 24); p.push_back((v >> 16) & 0xff); p.push_back((v >> 8) & 0xff); p.push_back(v & 0xff); };
+        std::memcpy(&p[12], "mntr", 4); std::memcpy(&p[16], "RGB ", 4); std::memcpy(&p[20], "XYZ ", 4); std::memcpy(&p[36], "acsp", 4);
+        const char* names[6] = { "rXYZ", "gXYZ", "bXYZ", "rTRC", "gTRC", "bTRC" };
+        append32(6);
+        const uint32_t dataStart = 128 + 4 + 6 * 12;
+        for (int i = 0; i < 6; ++i)
+        {
+            for (int c = 0; c < 4; ++c) p.push_back(static_cast<unsigned char>(names[i][c]));
+            append32(i < 3 ? dataStart + 20 * i : dataStart + 60 + 12 * (i - 3));
+            append32(i < 3 ? 20 : 12);
+        }
+        for (int i = 0; i < 3; ++i)
+        {
+            for (int c = 0; c < 4; ++c) p.push_back(static_cast<unsigned char>("XYZ "[c]));
+            append32(0);
+            for (int k = 0; k < 3; ++k) append32(static_cast<uint32_t>(static_cast<int32_t>(colorants[i][k] * 65536.0 + 0.5)));
+        }
+        for (int i = 0; i < 3; ++i)
+        {
+            for (int c = 0; c < 4; ++c) p.push_back(static_cast<unsigned char>("curv"[c]));
+            append32(0);
+            append32(0); // no entries: the identity curve
+        }
+        put32(0, static_cast<uint32_t>(p.size()));
+        return p;
+    }
+
     // The ICC seam (WriteHeifImage.cpp:1015-1036, ColorProfileConversion.cpp:107-120, HostMetadata.cpp:63-69).
     void TestColorProfileStep()
     {
@@ -272,6 +306,42 @@ namespace
             Expect(same && g_factoryCalls == 1, "row transform applied to every staged row, once, before the conversion (planes == oracle of the transformed rows)");
         }
         avifgpu_host::SetRowTransformFactory(nullptr, nullptr);
+        // 4. a linear-light document in a matrix profile (linear Rec.709 primaries): no host transform needed at all -- the
+        //    shuttle derives the 3x3 from the profile and the GPU applies it ahead of the conversion
+        {
+            const std::vector<unsigned char> profile = MakeLinearRec709Profile();
+            MockHost host;
+            InitHost(host, w, h, 3, 32);
+            host.source = reinterpret_cast<const uint8_t*>(rows.data());
+            host.stride = host.payload = static_cast<int64_t>(w) * 12;
+            host.record.canUseICCProfiles = 1;
+            host.record.iCCprofileData = const_cast<unsigned char*>(profile.data());
+            host.record.iCCprofileSize = static_cast<int32>(profile.size());
+            SaveUIOptions options{};
+            options.chromaSubsampling = ChromaSubsampling::Yuv444;
+            options.imageBitDepth = ImageBitDepth::Twelve;
+            options.hdrTransferFunction = ColorTransferFunction::PQ;
+            options.pq.nominalPeakBrightness = 80;
+            avifgpu_host::SetRowsPerBlock(8);
+            ScopedHeifImage image = CreateHeifImageRGBThirtyTwoBit(&host.record, AlphaState::None, VPoint{ h, w }, options);
+            avifgpu_encode_desc d{};
+            d.struct_size = sizeof(d);
+            d.width = w; d.height = h; d.host_depth = 32; d.host_channels = 3; d.image_bit_depth = 12; d.transfer = AVIFGPU_TRANSFER_PQ;
+            d.pq_peak_nits = 80; d.layout = AVIFGPU_LAYOUT_PLANAR_YCBCR; d.chroma = AVIFGPU_CHROMA_444;
+            d.nclx.present = 1; d.nclx.color_primaries = 9; d.nclx.transfer_characteristics = 16; d.nclx.matrix_coefficients = 9; d.nclx.full_range_flag = 1;
+            int32_t same = 1;
+            const int parsed = avifgpu_icc_to_rec2020_linear_matrix(profile.data(), profile.size(), d.row_matrix, &same);
+            d.row_matrix_enabled = 1;
+            std::vector<uint16_t> y(static_cast<size_t>(w) * h), cb(y.size()), cr(y.size());
+            avifgpu_planes planes{};
+            planes.data[0] = y.data(); planes.data[1] = cb.data(); planes.data[2] = cr.data();
+            planes.stride[0] = planes.stride[1] = planes.stride[2] = w * 2;
+            const int status = avif_oracle_encode_image(&d, rows.data(), static_cast<int64_t>(w) * 12, &planes);
+            const bool matrixLooksRight = d.row_matrix[0] > 0.62f && d.row_matrix[0] < 0.635f && d.row_matrix[4] > 0.91f; // BT.2087: 0.6274 / 0.9195
+            Expect(parsed == 0 && same == 0 && matrixLooksRight && status == 0 && PlaneEquals(image.get(), heif_channel_Y, y, w, h) &&
+                       PlaneEquals(image.get(), heif_channel_Cb, cb, w, h) && PlaneEquals(image.get(), heif_channel_Cr, cr, w, h),
+                   "matrix profile (linear Rec.709) on an HDR save: 3x3 derived from the ICC bytes, applied on the GPU, planes == oracle with that matrix");
+        }
     }
 
     // Staging is bounded in bytes, not rows (a 300 000-pixel RGBA32f row is 4.8 MB).

@@ -24,6 +24,8 @@ def make_desc(kind, fields):
     fields.pop("struct_size")
     desc = abi.EncodeDesc(1, 1, 8, 1) if kind == "encode" else abi.DecodeDesc(1, 1)
     for key, value in fields.items():
+        if isinstance(value, list):
+            value = type(getattr(desc, key))(*value)  # ctypes array fields are stored as lists
         setattr(desc, key, value)
     desc.nclx = nclx
     return desc
