@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -878,41 +879,125 @@ static void CopyRowsSerial(uint8_t* target, int64_t targetStride, const uint8_t*
 }
 
 // Bounce copies between pageable caller memory and the pinned slot buffers.  One core moves ~10 GB/s, a fifth of what
-// the PCIe link next to it carries, so anything beyond a few megabytes is split across a handful of threads (created per
-// copy: tens of microseconds against milliseconds of copying).
+// the PCIe link next to it carries, and an 8K frame owes 100 MB of plane copies: a small pool of parked threads (created
+// at the first bounce, process-wide, joined at exit) splits every copy above a megabyte by rows.
+namespace
+{
+    class CopyPool
+    {
+    public:
+        static CopyPool& Instance()
+        {
+            static CopyPool pool;
+            return pool;
+        }
+
+        void Copy(uint8_t* target, int64_t targetStride, const uint8_t* source, int64_t sourceStride, int64_t payload, int rows)
+        {
+            const int64_t bytes = payload * rows;
+            int parts = static_cast<int>(std::min<int64_t>(bytes >> 20, static_cast<int64_t>(workers.size()) + 1));
+            if (parts < 2 || rows < parts)
+            {
+                CopyRowsSerial(target, targetStride, source, sourceStride, payload, rows);
+                return;
+            }
+            std::unique_lock<std::mutex> callers(callerMutex); // one copy at a time (contexts on several threads share the pool)
+            const int share = (rows + parts - 1) / parts;
+            {
+                std::lock_guard<std::mutex> lock(mutex);
+                job = Job{ target, targetStride, source, sourceStride, payload, rows, share };
+                nextPart = 1; // part 0 is the caller's
+                partCount = parts;
+                pending = parts - 1;
+                ++generation;
+            }
+            wake.notify_all();
+            CopyRowsSerial(target, targetStride, source, sourceStride, payload, std::min(share, rows));
+            std::unique_lock<std::mutex> lock(mutex);
+            done.wait(lock, [&] { return pending == 0; });
+        }
+
+    private:
+        struct Job
+        {
+            uint8_t* target;
+            int64_t targetStride;
+            const uint8_t* source;
+            int64_t sourceStride;
+            int64_t payload;
+            int rows;
+            int share;
+        };
+
+        CopyPool()
+        {
+            const unsigned cores = std::thread::hardware_concurrency();
+            const int count = static_cast<int>(std::min<unsigned>(cores > 1 ? cores - 1 : 0, 7));
+            for (int i = 0; i < count; ++i)
+            {
+                workers.emplace_back([this] { Run(); });
+            }
+        }
+
+        ~CopyPool()
+        {
+            {
+                std::lock_guard<std::mutex> lock(mutex);
+                stopping = true;
+            }
+            wake.notify_all();
+            for (std::thread& t : workers)
+            {
+                t.join();
+            }
+        }
+
+        void Run()
+        {
+            uint64_t seen = 0;
+            std::unique_lock<std::mutex> lock(mutex);
+            for (;;)
+            {
+                wake.wait(lock, [&] { return stopping || (generation != seen && nextPart < partCount); });
+                if (stopping)
+                {
+                    return;
+                }
+                while (nextPart < partCount)
+                {
+                    const int part = nextPart++;
+                    const Job j = job;
+                    lock.unlock();
+                    const int begin = part * j.share;
+                    const int count = std::min(j.share, j.rows - begin);
+                    if (count > 0)
+                    {
+                        CopyRowsSerial(j.target + static_cast<int64_t>(begin) * j.targetStride, j.targetStride,
+                                       j.source + static_cast<int64_t>(begin) * j.sourceStride, j.sourceStride, j.payload, count);
+                    }
+                    lock.lock();
+                    if (--pending == 0)
+                    {
+                        done.notify_all();
+                    }
+                }
+                seen = generation;
+            }
+        }
+
+        std::vector<std::thread> workers;
+        std::mutex mutex, callerMutex;
+        std::condition_variable wake, done;
+        Job job{};
+        int nextPart = 0, partCount = 0, pending = 0;
+        uint64_t generation = 0;
+        bool stopping = false;
+    };
+}
+
 static void CopyRows(uint8_t* target, int64_t targetStride, const uint8_t* source, int64_t sourceStride, int64_t payload, int rows)
 {
-    const int64_t bytes = payload * rows;
-    int workers = static_cast<int>(std::min<int64_t>(bytes / (4ll << 20), 8));
-    const unsigned cores = std::thread::hardware_concurrency();
-    if (cores > 0)
-    {
-        workers = std::min<int>(workers, static_cast<int>(cores));
-    }
-    if (workers < 2 || rows < workers)
-    {
-        CopyRowsSerial(target, targetStride, source, sourceStride, payload, rows);
-        return;
-    }
-    std::vector<std::thread> threads;
-    threads.reserve(workers - 1);
-    const int share = (rows + workers - 1) / workers;
-    for (int w = 1; w < workers; ++w)
-    {
-        const int begin = w * share;
-        const int count = std::min(share, rows - begin);
-        if (count <= 0)
-        {
-            break;
-        }
-        threads.emplace_back(CopyRowsSerial, target + static_cast<int64_t>(begin) * targetStride, targetStride,
-                             source + static_cast<int64_t>(begin) * sourceStride, sourceStride, payload, count);
-    }
-    CopyRowsSerial(target, targetStride, source, sourceStride, payload, std::min(share, rows));
-    for (std::thread& t : threads)
-    {
-        t.join();
-    }
+    CopyPool::Instance().Copy(target, targetStride, source, sourceStride, payload, rows);
 }
 
 // Waits for the slot's stream work and pays what it owes the caller.

@@ -554,6 +554,7 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     table->view.compact = nullptr;
     table->view.firstBits = nullptr;
     table->view.compactCodeMask = 0;
+    table->view.compactMagic = 0;
     if (!flat.empty())
     {
         if (!Check(cudaMalloc(&table->deviceFlat, (flat.size() + 1) * sizeof(uint2)), "cudaMalloc", &table->error) ||
@@ -625,6 +626,7 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
             table->view.compact = static_cast<const uint32_t*>(table->deviceCompact);
             table->view.firstBits = static_cast<const uint32_t*>(table->deviceFirstBits);
             table->view.compactCodeMask = maxCode << kCompactLenBits;
+            table->view.compactMagic = 0x4b000000u;
             table->stats.compactBuckets = static_cast<int32_t>(compact.size());
         }
     }

@@ -83,6 +83,7 @@ struct CurveTableView
     const uint32_t* compact;
     const uint32_t* firstBits; // first_k for k = 0 .. maxCode + 1 (0 for codes that no input reaches)
     uint32_t compactCodeMask;  // ((1 << depth) - 1) << 6
+    uint32_t compactMagic;     // 0x4b000000 (the bits of 2^23), carried as data: see LookupCurveCompact
 };
 
 // Compact entries.  A random 64-bit gather from shared memory costs ~5.2 data-pipe wavefronts (two half-warp phases of

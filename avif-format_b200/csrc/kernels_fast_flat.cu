@@ -97,12 +97,14 @@ __device__ __forceinline__ void BarrierWait(uint32_t barrier, uint32_t parity)
 // steps are too dense for one bucket size, e.g. 12-bit SMPTE 428); its rare in-band samples take the exact evaluation in
 // place.  TWO_LEVEL = 2: the flat table in its compact one-word form (curve_tables.h "Compact entries") + the first_k
 // array + band bitmap: a 32-bit gather costs ~3.5 shared-memory wavefronts where the 64-bit one costs ~5.2, and that pipe
-// is what bounds this kernel.
+// is what bounds the 64-bit variant.  TWO_LEVEL = 3: the same with flatShift = 14 known at compile time (12-bit PQ).
 // INTERLEAVED = 1: the reference's own output layout (heif_channel_interleaved RGB, WriteHeifImage.cpp:1098-1130) -- the
 // codes are stored as they are, 3 x uint16 per pixel into plane Y's buffer, no matrix (XS = YS = 0 then).
 template <int CURVE, int XS, int YS, int TWO_LEVEL, int INTERLEAVED>
 __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const FastEncodeParams p, const FlatSchedule schedule)
 {
+    constexpr bool kCompact = TWO_LEVEL >= 2;
+    constexpr int kCompactShift = TWO_LEVEL == 3 ? 14 : 0;
     extern __shared__ __align__(128) uint8_t sharedBytes[];
     uint64_t* libmStorage = reinterpret_cast<uint64_t*>(sharedBytes);
     uint64_t* barriers = reinterpret_cast<uint64_t*>(sharedBytes + kSharedLibm);
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     }
 
     const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
-    if (TWO_LEVEL == 2)
+    if (kCompact)
     {
         const uint4* source = reinterpret_cast<const uint4*>(p.table.compact);
         uint4* target = reinterpret_cast<uint4*>(compactEntries);
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     const uint32_t compactTopShift = 32u - flatShift;
     const uint32_t compactBandShift = compactTopShift + kCompactLenUnitLog2;
     const uint32_t compactCodeMask = p.table.compactCodeMask;
+    const uint32_t compactMagic = p.table.compactMagic;
     uint32_t parity = 0;
 
 #pragma unroll 1
@@ -257,10 +260,11 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
             {
                 const int j = 4 * q + e;
                 bool inBand;
-                if (TWO_LEVEL == 2)
+                if (kCompact)
                 {
                     uint32_t entry;
-                    codeF[j] = LookupCurveCompact(bits[e], compactEntries, flatShift, negativeLow, span, compactTopShift, compactBandShift, compactCodeMask, inBand, entry);
+                    codeF[j] = LookupCurveCompact<kCompactShift>(bits[e], compactEntries, flatShift, negativeLow, span, compactTopShift, compactBandShift,
+                                                                 compactCodeMask, compactMagic, inBand, entry);
                 }
                 else if (TWO_LEVEL)
                 {
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
         // ---- in-band samples: one bit of the band bitmap each, two loads in flight per lane ---------------------------
         auto stagedBits = [&](int j) { return myStage[j + (j >= 12 ? kRowSegmentWords - 12 : 0)]; };
         uint32_t lowerMask = 0; // samples whose exact code is one below the table's
-        if (TWO_LEVEL == 2)
+        if (kCompact)
         {
             // flagged samples: which step, how far above its first_k, one bit of the band bitmap -- two at a time
             uint32_t pending = bandMask;
@@ -426,7 +430,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
 inline size_t TableSharedBytes(const FastEncodeParams& fp, int tableKind)
 {
     if (tableKind == 1) return 2048 + static_cast<size_t>(fp.table.bucketCount) * sizeof(uint32_t);
-    if (tableKind == 2) return (static_cast<size_t>((fp.table.flatCount + 3) & ~3) + static_cast<size_t>(fp.maxCode) + 2) * sizeof(uint32_t);
+    if (tableKind >= 2) return (static_cast<size_t>((fp.table.flatCount + 3) & ~3) + static_cast<size_t>(fp.maxCode) + 2) * sizeof(uint32_t);
     return static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
 }
 
@@ -508,7 +512,10 @@ cudaError_t LaunchFastEncodeFlatInterleaved(const FastEncodeParams& fp, int curv
 {
     if (CompactTableFits(fp))
     {
-        if (curve == kCurveLinearToPQ) return LaunchFlatKernel<kCurveLinearToPQ, 0, 0, 2, 1>(fp, smCount, stream);
+        if (curve == kCurveLinearToPQ)
+        {
+            return fp.table.flatShift == 14 ? LaunchFlatKernel<kCurveLinearToPQ, 0, 0, 3, 1>(fp, smCount, stream) : LaunchFlatKernel<kCurveLinearToPQ, 0, 0, 2, 1>(fp, smCount, stream);
+        }
         return LaunchFlatKernel<kCurveLinearToSMPTE428, 0, 0, 2, 1>(fp, smCount, stream);
     }
     if (FlatTableFits(fp))
@@ -524,7 +531,10 @@ cudaError_t LaunchFastEncodeFlat(const FastEncodeParams& fp, int curve, int xs, 
 {
     if (CompactTableFits(fp) && !fp.preferWideEntries)
     {
-        if (curve == kCurveLinearToPQ) return DispatchFlatChroma<kCurveLinearToPQ, 2>(fp, xs, ys, smCount, stream);
+        if (curve == kCurveLinearToPQ)
+        {
+            return fp.table.flatShift == 14 ? DispatchFlatChroma<kCurveLinearToPQ, 3>(fp, xs, ys, smCount, stream) : DispatchFlatChroma<kCurveLinearToPQ, 2>(fp, xs, ys, smCount, stream);
+        }
         return DispatchFlatChroma<kCurveLinearToSMPTE428, 2>(fp, xs, ys, smCount, stream);
     }
     if (FlatTableFits(fp))

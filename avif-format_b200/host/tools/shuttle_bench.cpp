@@ -104,9 +104,9 @@ namespace
         const uint8_t* source = nullptr;
         int64_t stride = 0;
         bool copy = true;
-        std::vector<void*> filled; // resident mode: buffers already holding rows
     };
     Host* g_host = nullptr;
+    std::vector<void*> g_filled; // resident mode: staging buffers that already hold rows (the shuttle keeps its buffers between calls)
 
     OSErr Advance()
     {
@@ -115,9 +115,9 @@ namespace
         const int top = r.theRect32.top, bottom = r.theRect32.bottom;
         if (!h.copy)
         {
-            for (void* p : h.filled)
+            for (void* p : g_filled)
                 if (p == r.data) return noErr;
-            h.filled.push_back(r.data);
+            g_filled.push_back(r.data);
         }
         for (int y = top; y < bottom; ++y)
         {
