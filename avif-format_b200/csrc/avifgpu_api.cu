@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -107,6 +108,9 @@ struct avifgpu_context
     cudaStream_t streams[kPipelineStreams] = {};
     cudaEvent_t sliceDone[kPipelineStreams] = {};
     cudaEvent_t rowsConsumed[kPipelineStreams] = {}; // encode: the slot's H2D of caller rows has finished
+    cudaEvent_t callRowsConsumed[2] = {};            // the last H2D of an asynchronous encode call (calls alternate between the two)
+    int64_t asyncEncodeCalls = 0;
+    bool previousCallRowsPending = false;            // callRowsConsumed[(asyncEncodeCalls - 1) & 1] guards caller memory still on the wire
 
     // Work a slot still owes the caller once its stream has drained: copies from a pinned bounce buffer into pageable
     // caller memory (libheif's planes on the encode side, pageable host rows on the decode side).
@@ -128,7 +132,6 @@ struct avifgpu_context
     SlotState slots[kPipelineStreams];
     int nextSlot = 0;
     int64_t lastTicket = 0;       // ticket of the most recent host-pointer call
-    int lastRowsSlot = -1;        // slot whose rowsConsumed event covers the last H2D of the previous asynchronous encode call
     std::string lastError;
     int64_t launches = 0;
     int smCount = 0;
@@ -546,7 +549,8 @@ AVIFGPU_EXPORT int avifgpu_create(int device_ordinal, avifgpu_context** out_ctx)
     {
         if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->sliceDone[i], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->rowsConsumed[i], cudaEventDisableTiming) != cudaSuccess)
+            cudaEventCreateWithFlags(&ctx->rowsConsumed[i], cudaEventDisableTiming) != cudaSuccess ||
+            (i < 2 && cudaEventCreateWithFlags(&ctx->callRowsConsumed[i], cudaEventDisableTiming) != cudaSuccess))
         {
             g_creationError = std::string("stream/event creation failed: ") + cudaGetErrorString(cudaGetLastError());
             avifgpu_destroy(ctx);
@@ -570,6 +574,7 @@ AVIFGPU_EXPORT void avifgpu_destroy(avifgpu_context* ctx)
         if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
         if (ctx->sliceDone[i]) cudaEventDestroy(ctx->sliceDone[i]);
         if (ctx->rowsConsumed[i]) cudaEventDestroy(ctx->rowsConsumed[i]);
+        if (i < 2 && ctx->callRowsConsumed[i]) cudaEventDestroy(ctx->callRowsConsumed[i]);
         if (ctx->deviceRows[i].ptr) cudaFree(ctx->deviceRows[i].ptr);
         if (ctx->pinnedRows[i].ptr) cudaFreeHost(ctx->pinnedRows[i].ptr);
         for (int k = 0; k < AVIFGPU_MAX_PLANES; ++k)
@@ -610,7 +615,7 @@ AVIFGPU_EXPORT int avifgpu_synchronize(avifgpu_context* ctx)
     DeviceGuard guard(ctx->device);
     const int status = ctx->Cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
     const int retired = RetireThrough(ctx, ctx->lastTicket); // pays the bounce copies asynchronous calls still owe
-    ctx->lastRowsSlot = -1;
+    ctx->previousCallRowsPending = false;
     return status != AVIFGPU_OK ? status : retired;
 }
 
@@ -880,9 +885,20 @@ static void CopyRowsSerial(uint8_t* target, int64_t targetStride, const uint8_t*
 
 // Bounce copies between pageable caller memory and the pinned slot buffers.  One core moves ~10 GB/s, a fifth of what
 // the PCIe link next to it carries, and an 8K frame owes 100 MB of plane copies: a small pool of parked threads (created
-// at the first bounce, process-wide, joined at exit) splits every copy above a megabyte by rows.
+// at the first bounce, process-wide, joined at exit) shares every batch of copies above a megabyte, cut into chunks of
+// rows that the threads -- and the caller -- pull from a common counter.
 namespace
 {
+    struct RowCopy
+    {
+        uint8_t* target;
+        int64_t targetStride;
+        const uint8_t* source;
+        int64_t sourceStride;
+        int64_t payload;
+        int rows;
+    };
+
     class CopyPool
     {
     public:
@@ -892,43 +908,47 @@ namespace
             return pool;
         }
 
-        void Copy(uint8_t* target, int64_t targetStride, const uint8_t* source, int64_t sourceStride, int64_t payload, int rows)
+        void Copy(const RowCopy* copies, int count)
         {
-            const int64_t bytes = payload * rows;
-            int parts = static_cast<int>(std::min<int64_t>(bytes >> 20, static_cast<int64_t>(workers.size()) + 1));
-            if (parts < 2 || rows < parts)
+            int64_t bytes = 0;
+            for (int i = 0; i < count; ++i)
             {
-                CopyRowsSerial(target, targetStride, source, sourceStride, payload, rows);
+                bytes += copies[i].payload * copies[i].rows;
+            }
+            if (bytes < (1ll << 20) || workers.empty())
+            {
+                for (int i = 0; i < count; ++i)
+                {
+                    CopyRowsSerial(copies[i].target, copies[i].targetStride, copies[i].source, copies[i].sourceStride, copies[i].payload, copies[i].rows);
+                }
                 return;
             }
-            std::unique_lock<std::mutex> callers(callerMutex); // one copy at a time (contexts on several threads share the pool)
-            const int share = (rows + parts - 1) / parts;
+            std::unique_lock<std::mutex> callers(callerMutex); // one batch at a time (contexts on several threads share the pool)
             {
                 std::lock_guard<std::mutex> lock(mutex);
-                job = Job{ target, targetStride, source, sourceStride, payload, rows, share };
-                nextPart = 1; // part 0 is the caller's
-                partCount = parts;
-                pending = parts - 1;
+                chunks.clear();
+                for (int i = 0; i < count; ++i)
+                {
+                    const RowCopy& c = copies[i];
+                    const int rowsPerChunk = static_cast<int>(std::max<int64_t>((256ll << 10) / std::max<int64_t>(c.payload, 1), 1));
+                    for (int begin = 0; begin < c.rows; begin += rowsPerChunk)
+                    {
+                        chunks.push_back(RowCopy{ c.target + static_cast<int64_t>(begin) * c.targetStride, c.targetStride,
+                                                  c.source + static_cast<int64_t>(begin) * c.sourceStride, c.sourceStride, c.payload,
+                                                  std::min(rowsPerChunk, c.rows - begin) });
+                    }
+                }
+                next.store(0, std::memory_order_relaxed);
+                remaining = static_cast<int>(chunks.size());
                 ++generation;
             }
             wake.notify_all();
-            CopyRowsSerial(target, targetStride, source, sourceStride, payload, std::min(share, rows));
+            Drain();
             std::unique_lock<std::mutex> lock(mutex);
-            done.wait(lock, [&] { return pending == 0; });
+            done.wait(lock, [&] { return remaining == 0; });
         }
 
     private:
-        struct Job
-        {
-            uint8_t* target;
-            int64_t targetStride;
-            const uint8_t* source;
-            int64_t sourceStride;
-            int64_t payload;
-            int rows;
-            int share;
-        };
-
         CopyPool()
         {
             const unsigned cores = std::thread::hardware_concurrency();
@@ -952,44 +972,57 @@ namespace
             }
         }
 
+        // Pulls chunks until none is left; returns how many this thread copied.
+        void Drain()
+        {
+            int copied = 0;
+            const int total = static_cast<int>(chunks.size());
+            for (;;)
+            {
+                const int i = next.fetch_add(1, std::memory_order_relaxed);
+                if (i >= total)
+                {
+                    break;
+                }
+                const RowCopy& c = chunks[i];
+                CopyRowsSerial(c.target, c.targetStride, c.source, c.sourceStride, c.payload, c.rows);
+                ++copied;
+            }
+            if (copied)
+            {
+                std::lock_guard<std::mutex> lock(mutex);
+                remaining -= copied;
+                if (remaining == 0)
+                {
+                    done.notify_all();
+                }
+            }
+        }
+
         void Run()
         {
             uint64_t seen = 0;
-            std::unique_lock<std::mutex> lock(mutex);
             for (;;)
             {
-                wake.wait(lock, [&] { return stopping || (generation != seen && nextPart < partCount); });
-                if (stopping)
                 {
-                    return;
-                }
-                while (nextPart < partCount)
-                {
-                    const int part = nextPart++;
-                    const Job j = job;
-                    lock.unlock();
-                    const int begin = part * j.share;
-                    const int count = std::min(j.share, j.rows - begin);
-                    if (count > 0)
+                    std::unique_lock<std::mutex> lock(mutex);
+                    wake.wait(lock, [&] { return stopping || generation != seen; });
+                    if (stopping)
                     {
-                        CopyRowsSerial(j.target + static_cast<int64_t>(begin) * j.targetStride, j.targetStride,
-                                       j.source + static_cast<int64_t>(begin) * j.sourceStride, j.sourceStride, j.payload, count);
+                        return;
                     }
-                    lock.lock();
-                    if (--pending == 0)
-                    {
-                        done.notify_all();
-                    }
+                    seen = generation;
                 }
-                seen = generation;
+                Drain(); // `chunks` is stable until the caller has seen remaining == 0, which needs every pulled chunk finished
             }
         }
 
         std::vector<std::thread> workers;
         std::mutex mutex, callerMutex;
         std::condition_variable wake, done;
-        Job job{};
-        int nextPart = 0, partCount = 0, pending = 0;
+        std::vector<RowCopy> chunks;
+        std::atomic<int> next{ 0 };
+        int remaining = 0;
         uint64_t generation = 0;
         bool stopping = false;
     };
@@ -997,11 +1030,12 @@ namespace
 
 static void CopyRows(uint8_t* target, int64_t targetStride, const uint8_t* source, int64_t sourceStride, int64_t payload, int rows)
 {
-    CopyPool::Instance().Copy(target, targetStride, source, sourceStride, payload, rows);
+    const RowCopy one{ target, targetStride, source, sourceStride, payload, rows };
+    CopyPool::Instance().Copy(&one, 1);
 }
 
-// Waits for the slot's stream work and pays what it owes the caller.
-static int RetireSlot(avifgpu_context* ctx, int slot)
+// Waits for the slot's stream work (its device buffers are free again after this); what it owes the caller stays owed.
+static int WaitSlot(avifgpu_context* ctx, int slot)
 {
     avifgpu_context::SlotState& state = ctx->slots[slot];
     if (!state.busy)
@@ -1009,15 +1043,43 @@ static int RetireSlot(avifgpu_context* ctx, int slot)
         return AVIFGPU_OK;
     }
     const int status = ctx->Cuda(cudaEventSynchronize(ctx->sliceDone[slot]), "cudaEventSynchronize");
-    if (status == AVIFGPU_OK)
+    if (status != AVIFGPU_OK)
     {
+        state.owed.clear();
+    }
+    state.busy = false;
+    return status;
+}
+
+// Pays what a waited-for slot owes the caller: the copies out of its pinned bounce buffers.
+static void PayOwed(avifgpu_context* ctx, int slot)
+{
+    avifgpu_context::SlotState& state = ctx->slots[slot];
+    if (!state.owed.empty())
+    {
+        RowCopy batch[AVIFGPU_MAX_PLANES + 1];
+        int count = 0;
         for (const avifgpu_context::HostCopy& c : state.owed)
         {
-            CopyRows(c.target, c.targetStride, c.source, c.sourceStride, c.payload, c.rows);
+            if (count == AVIFGPU_MAX_PLANES + 1)
+            {
+                CopyPool::Instance().Copy(batch, count);
+                count = 0;
+            }
+            batch[count++] = RowCopy{ c.target, c.targetStride, c.source, c.sourceStride, c.payload, c.rows };
         }
+        CopyPool::Instance().Copy(batch, count); // all planes of the slice share the pool's threads
     }
     state.owed.clear();
-    state.busy = false;
+}
+
+static int RetireSlot(avifgpu_context* ctx, int slot)
+{
+    const int status = WaitSlot(ctx, slot);
+    if (status == AVIFGPU_OK)
+    {
+        PayOwed(ctx, slot);
+    }
     return status;
 }
 
@@ -1028,7 +1090,7 @@ static int RetireThrough(avifgpu_context* ctx, int64_t ticket)
     for (int i = 0; i < kPipelineStreams; ++i)
     {
         const int slot = (ctx->nextSlot + i) % kPipelineStreams; // nextSlot is the oldest
-        if (ctx->slots[slot].busy && ctx->slots[slot].ticket <= ticket)
+        if ((ctx->slots[slot].busy || !ctx->slots[slot].owed.empty()) && ctx->slots[slot].ticket <= ticket)
         {
             const int status = RetireSlot(ctx, slot);
             if (result == AVIFGPU_OK) result = status;
@@ -1108,19 +1170,22 @@ static int EncodeRowsHost(avifgpu_context* ctx, const avifgpu_encode_desc* desc,
     const bool rowsPinned = IsPinned(host_rows);
     const int sliceRows = SliceRows(nrows, rowPayload);
 
-    // The rows handed to the PREVIOUS asynchronous call may be overwritten once this call returns: wait for their last H2D.
-    if (ctx->lastRowsSlot >= 0)
-    {
-        if ((status = ctx->Cuda(cudaEventSynchronize(ctx->rowsConsumed[ctx->lastRowsSlot]), "cudaEventSynchronize")) != AVIFGPU_OK) return AbandonCall(ctx, status);
-        ctx->lastRowsSlot = -1;
-    }
+    // The rows handed to the PREVIOUS asynchronous call may be overwritten once this call returns.  Their last H2D is
+    // waited for at the END of this call, after this call's own copies are queued behind it, so the link never idles
+    // at a call boundary.
+    const bool waitForPreviousRows = ctx->previousCallRowsPending;
+    const int previousRowsEvent = static_cast<int>((ctx->asyncEncodeCalls - 1) & 1);
+    ctx->previousCallRowsPending = false;
+    bool recordedCallRows = false;
 
     for (int begin = 0; begin < nrows; begin += sliceRows)
     {
         const int rows = std::min(sliceRows, nrows - begin);
         const int slot = ctx->nextSlot;
         cudaStream_t stream = ctx->streams[slot];
-        if ((status = RetireSlot(ctx, slot)) != AVIFGPU_OK) return AbandonCall(ctx, status);
+        // The slot's previous slice: wait for the GPU, but pay its bounce copies only after this slice's H2D and kernel are
+        // queued -- the host then copies while the link and the SMs work (its D2H, which reuses the bounce buffers, comes last).
+        if ((status = WaitSlot(ctx, slot)) != AVIFGPU_OK) return AbandonCall(ctx, status);
         ctx->nextSlot = (slot + 1) % kPipelineStreams;
 
         if ((status = ctx->EnsureDevice(ctx->deviceRows[slot], static_cast<size_t>(deviceRowStride) * rows)) != AVIFGPU_OK) return AbandonCall(ctx, status);
@@ -1139,6 +1204,12 @@ static int EncodeRowsHost(avifgpu_context* ctx, const avifgpu_encode_desc* desc,
                                                   static_cast<size_t>(rows), cudaMemcpyHostToDevice, stream),
                                 "H2D rows")) != AVIFGPU_OK) return AbandonCall(ctx, status);
         if ((status = ctx->Cuda(cudaEventRecord(ctx->rowsConsumed[slot], stream), "cudaEventRecord")) != AVIFGPU_OK) return AbandonCall(ctx, status);
+        if (!wait && rowsPinned && begin + sliceRows >= nrows)
+        {
+            // the caller's own memory is on the wire until this H2D, the last of the call: the NEXT call waits for it before it returns
+            if ((status = ctx->Cuda(cudaEventRecord(ctx->callRowsConsumed[ctx->asyncEncodeCalls & 1], stream), "cudaEventRecord")) != AVIFGPU_OK) return AbandonCall(ctx, status);
+            recordedCallRows = true;
+        }
 
         EncodeParams p = base;
         p.rows = ctx->deviceRows[slot].ptr;
@@ -1168,6 +1239,7 @@ static int EncodeRowsHost(avifgpu_context* ctx, const avifgpu_encode_desc* desc,
         }
         ctx->launches += launched;
 
+        PayOwed(ctx, slot); // the previous slice's planes leave the bounce buffers now
         avifgpu_context::SlotState& state = ctx->slots[slot];
         for (int k = 0; k < AVIFGPU_MAX_PLANES; ++k)
         {
@@ -1195,16 +1267,20 @@ static int EncodeRowsHost(avifgpu_context* ctx, const avifgpu_encode_desc* desc,
         if ((status = ctx->Cuda(cudaEventRecord(ctx->sliceDone[slot], stream), "cudaEventRecord")) != AVIFGPU_OK) return AbandonCall(ctx, status);
         state.busy = true;
         state.ticket = ticket;
-        if (!wait && rowsPinned)
-        {
-            ctx->lastRowsSlot = slot; // the caller's own memory is on the wire until this event
-        }
+    }
+    if (waitForPreviousRows)
+    {
+        if ((status = ctx->Cuda(cudaEventSynchronize(ctx->callRowsConsumed[previousRowsEvent]), "cudaEventSynchronize")) != AVIFGPU_OK) return AbandonCall(ctx, status);
     }
     if (wait)
     {
-        ctx->lastRowsSlot = -1;
         status = RetireThrough(ctx, ticket);
         return status == AVIFGPU_OK ? AVIFGPU_OK : AbandonCall(ctx, status);
+    }
+    if (recordedCallRows)
+    {
+        ctx->asyncEncodeCalls += 1;
+        ctx->previousCallRowsPending = true;
     }
     return AVIFGPU_OK;
 }
@@ -1382,10 +1458,7 @@ AVIFGPU_EXPORT int avifgpu_wait(avifgpu_context* ctx, int64_t ticket)
     if (ticket <= 0 || ticket >= ctx->lastTicket)
     {
         ticket = ctx->lastTicket;
-        if (ctx->lastRowsSlot >= 0)
-        {
-            ctx->lastRowsSlot = -1; // everything is about to be drained
-        }
+        ctx->previousCallRowsPending = false; // everything is about to be drained
     }
     const int status = RetireThrough(ctx, ticket);
     return status == AVIFGPU_OK ? AVIFGPU_OK : AbandonCall(ctx, status);

@@ -82,18 +82,17 @@ __device__ __forceinline__ float LookupCurveFlat(uint32_t bits, const uint2* __r
     return LookupCurveFlat(bits, flat, shift, negativeLow, span, inBand, entry);
 }
 
-// Compact look-up (curve_tables.h "Compact entries").  topShift = 32 - flatShift, bandShift = topShift + 5.
+// Compact look-up (curve_tables.h "Compact entries").  topShift = 32 - flatShift.
 // SHIFT != 0 fixes flatShift at compile time (the shifts become immediates and entry + (bits << topShift) a single
 // multiply-add on the FMA pipe); `magic` is 0x4b000000 handed in as a run-time value so that (entry & codeMask) | magic
-// stays ONE three-input logic instruction.  Twelve instructions and one 32-bit shared-memory load per sample; the code
+// stays ONE three-input logic instruction.  Eleven instructions and one 32-bit shared-memory load per sample; the code
 // comes out as a float like LookupCurveFlat's.
 template <int SHIFT>
 __device__ __forceinline__ float LookupCurveCompact(uint32_t bits, const uint32_t* __restrict__ compact, uint32_t shift, int32_t negativeLow, int32_t span,
-                                                    uint32_t topShift, uint32_t bandShift, uint32_t codeMask, uint32_t magic, bool& inBand, uint32_t& entryOut)
+                                                    uint32_t topShift, uint32_t codeMask, uint32_t magic, bool& inBand, uint32_t& entryOut)
 {
     const uint32_t s = SHIFT != 0 ? static_cast<uint32_t>(SHIFT) : shift;
     const uint32_t top = SHIFT != 0 ? 32u - static_cast<uint32_t>(SHIFT) : topShift;
-    const uint32_t band = SHIFT != 0 ? 32u - static_cast<uint32_t>(SHIFT) + kCompactLenUnitLog2 : bandShift;
     const int32_t index = __viaddmin_s32_relu(static_cast<int32_t>(bits) >> s, negativeLow, span);
     const uint32_t entry = compact[index];
     entryOut = entry;
@@ -106,7 +105,7 @@ __device__ __forceinline__ float LookupCurveCompact(uint32_t bits, const uint32_
     {
         code += 1.0f;
     }
-    inBand = (t >> band) < (entry & ((1u << kCompactLenBits) - 1u));
+    inBand = t < (entry << (32u - kCompactLenBits)); // distance from the band start < lenq units
     return code;
 }
 
@@ -131,8 +130,8 @@ __device__ __forceinline__ uint32_t LookupCurveCodeCompactResolved(uint32_t bits
     const uint32_t topShift = 32u - table.flatShift;
     uint32_t entry;
     const float code = LookupCurveCompact<0>(bits, table.compact, table.flatShift, -static_cast<int32_t>(table.flatLow),
-                                             static_cast<int32_t>(table.flatHigh - table.flatLow), topShift, topShift + kCompactLenUnitLog2, table.compactCodeMask,
-                                             0x4b000000u, inBand, entry);
+                                             static_cast<int32_t>(table.flatHigh - table.flatLow), topShift, table.compactCodeMask, 0x4b000000u, inBand,
+                                             entry);
     uint32_t result = static_cast<uint32_t>(code);
     if (inBand)
     {

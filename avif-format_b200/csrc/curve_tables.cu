@@ -482,6 +482,8 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
                 {
                     const uint32_t topShift = 32u - static_cast<uint32_t>(shift);
                     const uint32_t lenMax = (1u << kCompactLenBits) - 1u;
+                    const uint32_t unitLog2 = static_cast<uint32_t>(shift) - kCompactLenBits; // flatShift >= kMinShift = 6
+                    uint32_t longest = 0;
                     bool fits = true;
                     compact.resize(count);
                     size_t at = 0;
@@ -517,12 +519,19 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
                         {
                             field = static_cast<uint32_t>(at); // no step: code = steps below
                         }
-                        const uint32_t lenq = (inBandFloats + (1u << kCompactLenUnitLog2) - 1u) >> kCompactLenUnitLog2;
+                        const uint32_t lenq = (inBandFloats + (1u << unitLog2) - 1u) >> unitLog2;
                         fits = lenq <= lenMax && field <= maxCode;
+                        longest = std::max(longest, lenq << unitLog2);
                         compact[b] = (top << topShift) | (field << kCompactLenBits) | lenq;
                     }
-                    // the band bitmap answers bits - first_k < 2^stride for every banded step: the rounded-up test must stay inside it
-                    fits = fits && (1u << bandStrideLog2) >= (1u << kCompactLenUnitLog2);
+                    // the band bitmap answers bits - first_k < 2^stride for every banded step: a band rounded up to the unit (plus
+                    // the part of it that lies in the previous bucket) must stay inside it
+                    (void)longest;
+                    while (fits && (1u << bandStrideLog2) < table->stats.widestBand + (2u << unitLog2))
+                    {
+                        ++bandStrideLog2;
+                    }
+                    fits = fits && ((static_cast<uint64_t>(codeCount) << bandStrideLog2) / 8u) <= kBandBitmapMaxBytes;
                     if (!fits)
                     {
                         compact.clear();

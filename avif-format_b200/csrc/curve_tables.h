@@ -91,16 +91,16 @@ struct CurveTableView
 // is also kept in a one-word form, S = flatShift, D = depth (needs S + D + 6 <= 32):
 //     bits 31 .. 32-S   step bucket: 2^S - off, off = first_k - bucketStart in (0, 2^S);  otherwise 0
 //     bits D+5 .. 6     step bucket: k - 1;  otherwise the code of every float of the bucket (before band corrections)
-//     bits 5 .. 0       lenq: the in-band floats of the bucket are those less than 32 * lenq above the band start
+//     bits 5 .. 0       lenq: the in-band floats of the bucket are those less than lenq * 2^(S-6) above the band start
 //                       (band start = first_k for a step bucket, the bucket start for the tail of a band that began in
 //                       the previous bucket or for a step sitting exactly on the bucket start)
 // With t = entry + (bits << (32 - S)): the carry out of bit 31 says bits >= first_k, so code = field + carry, and the top
-// S bits of t are the distance from the band start, so in band <=> (t >> (37 - S)) < lenq.  The test is a superset:
-// a sample below first_k whose wrapped distance happens to be small is flagged too, and lenq rounds the band up to 32
-// floats; the band bitmap (indexed by k and bits - first_k, filled over its whole stride) gives the exact code for every
-// flagged sample, and ResolveCompactInBand leaves the unflagged-worthy ones as they are.
+// S bits of t are the distance from the band start, so in band <=> t < (entry << 26) -- the band length in units of
+// 2^(S-6) floats (256 for S = 14) is what makes that a shift and ONE compare.  The test is a superset: a sample below
+// first_k whose wrapped distance happens to be small is flagged too, and lenq rounds the band up to the unit; the band
+// bitmap (indexed by k and bits - first_k, filled over its whole stride) gives the exact code for every flagged sample,
+// and ResolveCompactInBand leaves the ones flagged by the superset alone.
 constexpr uint32_t kCompactLenBits = 6;
-constexpr uint32_t kCompactLenUnitLog2 = 5;
 
 struct CurveTableStats
 {

@@ -215,7 +215,6 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     const uint32_t bandStrideLog2 = p.table.bandStrideLog2;
     const uint32_t* __restrict__ bandBits = p.table.bandBits;
     const uint32_t compactTopShift = 32u - flatShift;
-    const uint32_t compactBandShift = compactTopShift + kCompactLenUnitLog2;
     const uint32_t compactCodeMask = p.table.compactCodeMask;
     const uint32_t compactMagic = p.table.compactMagic;
     uint32_t parity = 0;
@@ -263,8 +262,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
                 if (kCompact)
                 {
                     uint32_t entry;
-                    codeF[j] = LookupCurveCompact<kCompactShift>(bits[e], compactEntries, flatShift, negativeLow, span, compactTopShift, compactBandShift,
-                                                                 compactCodeMask, compactMagic, inBand, entry);
+                    codeF[j] = LookupCurveCompact<kCompactShift>(bits[e], compactEntries, flatShift, negativeLow, span, compactTopShift, compactCodeMask,
+                                                                 compactMagic, inBand, entry);
                 }
                 else if (TWO_LEVEL)
                 {

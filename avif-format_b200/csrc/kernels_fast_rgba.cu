@@ -1,4 +1,5 @@
-// kernels_fast_rgba.cu -- float RGBA hosts -> planar YCbCr + alpha plane through the flat step table and the band bitmap
+// kernels_fast_rgba.cu -- float RGBA hosts -> planar YCbCr + alpha plane through the step table (compact one-word entries
+// where the table has them, else the 64-bit flat entries; curve_tables.h) and the band bitmap
 // (CreateHeifImageRGBThirtyTwoBit's alpha branch, WriteHeifImage.cpp:1039-1077, fused with the libheif stage).
 //
 // Same warp tile as kernels_fast_flat.cu (2 rows x 128 pixels, a lane owns 4 adjacent pixels in both rows), but 16 bytes
@@ -25,15 +26,34 @@ constexpr int kStagePerWarp = 32 * kLaneStrideWords * 4;
 constexpr int kSharedLimit = 227 * 1024;
 __host__ __device__ constexpr int RgbaFixedBytes() { return kSharedLibm + kRgbaWarps * kStagePerWarp; }
 
-template <int CURVE, int XS, int YS>
+// COMPACT = 1: compact table + first_k array in shared memory (kernels_fast_flat.cu has the commentary).
+template <int CURVE, int XS, int YS, int COMPACT>
 __global__ void __launch_bounds__(kRgbaThreads, 1) EncodeRgbaF32FlatKernel(const FastEncodeParams p)
 {
     extern __shared__ __align__(16) uint8_t sharedBytes[];
     uint64_t* libmStorage = reinterpret_cast<uint64_t*>(sharedBytes);
     uint32_t* stageAll = reinterpret_cast<uint32_t*>(sharedBytes + kSharedLibm);
     uint2* flatEntries = reinterpret_cast<uint2*>(sharedBytes + RgbaFixedBytes());
+    uint32_t* compactEntries = reinterpret_cast<uint32_t*>(sharedBytes + RgbaFixedBytes());
+    uint32_t* firstBits = compactEntries + ((p.table.flatCount + 3) & ~3);
 
     const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
+    if (COMPACT)
+    {
+        const uint4* source = reinterpret_cast<const uint4*>(p.table.compact);
+        uint4* target = reinterpret_cast<uint4*>(compactEntries);
+        const int quads = (p.table.flatCount + 3) / 4;
+#pragma unroll 8
+        for (int i = threadIdx.x; i < quads; i += blockDim.x)
+        {
+            target[i] = __ldg(source + i);
+        }
+        for (int i = threadIdx.x; i <= p.maxCode + 1; i += blockDim.x)
+        {
+            firstBits[i] = p.table.firstBits[i];
+        }
+    }
+    else
     {
         const uint4* source = reinterpret_cast<const uint4*>(p.table.flat);
         uint4* target = reinterpret_cast<uint4*>(flatEntries);
@@ -54,6 +74,9 @@ __global__ void __launch_bounds__(kRgbaThreads, 1) EncodeRgbaF32FlatKernel(const
     const int32_t span = static_cast<int32_t>(p.table.flatHigh - p.table.flatLow);
     const uint32_t bandStrideLog2 = p.table.bandStrideLog2;
     const uint32_t* __restrict__ bandBits = p.table.bandBits;
+    const uint32_t compactTopShift = 32u - flatShift;
+    const uint32_t compactCodeMask = p.table.compactCodeMask;
+    const uint32_t compactMagic = p.table.compactMagic;
 
     const int tilesX = (p.width + kTilePixels - 1) / kTilePixels;
     const int tileRows = (p.rowCount + 1) / 2;
@@ -136,7 +159,15 @@ __global__ void __launch_bounds__(kRgbaThreads, 1) EncodeRgbaF32FlatKernel(const
         for (int j = 0; j < kValuesPerLane; ++j)
         {
             bool inBand;
-            codeF[j] = LookupCurveFlat(colourBits[j], flatEntries, flatShift, negativeLow, span, inBand);
+            if (COMPACT)
+            {
+                uint32_t entry;
+                codeF[j] = LookupCurveCompact<0>(colourBits[j], compactEntries, flatShift, negativeLow, span, compactTopShift, compactCodeMask, compactMagic, inBand, entry);
+            }
+            else
+            {
+                codeF[j] = LookupCurveFlat(colourBits[j], flatEntries, flatShift, negativeLow, span, inBand);
+            }
             asm("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q or.b32 %0, %0, %2; }" : "+r"(bandMask) : "r"(static_cast<uint32_t>(inBand)), "r"(1u << j));
             largest = max(largest, static_cast<int32_t>(colourBits[j]));
         }
@@ -151,6 +182,20 @@ __global__ void __launch_bounds__(kRgbaThreads, 1) EncodeRgbaF32FlatKernel(const
                 const int j = __ffs(static_cast<int>(pending)) - 1;
                 pending &= pending - 1;
                 const uint32_t bits = myStage[j];
+                if (COMPACT)
+                {
+                    const int32_t bucket = __viaddmin_s32_relu(static_cast<int32_t>(bits) >> flatShift, negativeLow, span);
+                    const uint32_t entry = compactEntries[bucket];
+                    const uint32_t k = ((entry & compactCodeMask) >> kCompactLenBits) + ((entry >> compactTopShift) != 0 ? 1u : 0u);
+                    const uint32_t distance = bits - firstBits[k];
+                    if (k != 0 && distance < (1u << bandStrideLog2)) // else flagged by the superset test only
+                    {
+                        const uint32_t bitIndex = (k << bandStrideLog2) + distance;
+                        const uint32_t word = __ldg(bandBits + (bitIndex >> 5));
+                        lowerMask |= (((word >> (bitIndex & 31u)) & 1u) ^ 1u) << j;
+                    }
+                    continue;
+                }
                 bool inBand;
                 uint2 entry;
                 LookupCurveFlat(bits, flatEntries, flatShift, negativeLow, span, inBand, entry);
@@ -206,13 +251,19 @@ __global__ void __launch_bounds__(kRgbaThreads, 1) EncodeRgbaF32FlatKernel(const
     }
 }
 
-template <int CURVE, int XS, int YS>
+size_t RgbaTableBytes(const FastEncodeParams& fp, bool compact)
+{
+    return compact ? (static_cast<size_t>((fp.table.flatCount + 3) & ~3) + static_cast<size_t>(fp.maxCode) + 2) * sizeof(uint32_t)
+                   : static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
+}
+
+template <int CURVE, int XS, int YS, int COMPACT>
 cudaError_t LaunchRgbaKernel(const FastEncodeParams& fp, int smCount, cudaStream_t stream)
 {
-    const size_t shared = static_cast<size_t>(RgbaFixedBytes()) + static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
+    const size_t shared = static_cast<size_t>(RgbaFixedBytes()) + RgbaTableBytes(fp, COMPACT != 0);
     static std::atomic<uint64_t> configuredDevices{ 0 }; // per instantiation
     {
-        const cudaError_t e = AllowDynamicShared(EncodeRgbaF32FlatKernel<CURVE, XS, YS>, kSharedLimit, configuredDevices);
+        const cudaError_t e = AllowDynamicShared(EncodeRgbaF32FlatKernel<CURVE, XS, YS, COMPACT>, kSharedLimit, configuredDevices);
         if (e != cudaSuccess)
         {
             return e;
@@ -228,16 +279,16 @@ cudaError_t LaunchRgbaKernel(const FastEncodeParams& fp, int smCount, cudaStream
     {
         blocks = smCount;
     }
-    EncodeRgbaF32FlatKernel<CURVE, XS, YS><<<static_cast<unsigned>(blocks), kRgbaThreads, shared, stream>>>(fp);
+    EncodeRgbaF32FlatKernel<CURVE, XS, YS, COMPACT><<<static_cast<unsigned>(blocks), kRgbaThreads, shared, stream>>>(fp);
     return cudaGetLastError();
 }
 
-template <int CURVE>
+template <int CURVE, int COMPACT>
 cudaError_t DispatchRgbaChroma(const FastEncodeParams& fp, int xs, int ys, int smCount, cudaStream_t stream)
 {
-    if (xs == 1 && ys == 1) return LaunchRgbaKernel<CURVE, 1, 1>(fp, smCount, stream);
-    if (xs == 1) return LaunchRgbaKernel<CURVE, 1, 0>(fp, smCount, stream);
-    return LaunchRgbaKernel<CURVE, 0, 0>(fp, smCount, stream);
+    if (xs == 1 && ys == 1) return LaunchRgbaKernel<CURVE, 1, 1, COMPACT>(fp, smCount, stream);
+    if (xs == 1) return LaunchRgbaKernel<CURVE, 1, 0, COMPACT>(fp, smCount, stream);
+    return LaunchRgbaKernel<CURVE, 0, 0, COMPACT>(fp, smCount, stream);
 }
 
 } // namespace
@@ -250,8 +301,13 @@ bool RgbaEncodeApplies(const FastEncodeParams& fp)
 
 cudaError_t LaunchFastEncodeRgba(const FastEncodeParams& fp, int curve, int xs, int ys, int smCount, cudaStream_t stream)
 {
-    if (curve == kCurveLinearToPQ) return DispatchRgbaChroma<kCurveLinearToPQ>(fp, xs, ys, smCount, stream);
-    return DispatchRgbaChroma<kCurveLinearToSMPTE428>(fp, xs, ys, smCount, stream);
+    if (fp.table.compact != nullptr && fp.table.firstBits != nullptr && !fp.preferWideEntries)
+    {
+        if (curve == kCurveLinearToPQ) return DispatchRgbaChroma<kCurveLinearToPQ, 1>(fp, xs, ys, smCount, stream);
+        return DispatchRgbaChroma<kCurveLinearToSMPTE428, 1>(fp, xs, ys, smCount, stream);
+    }
+    if (curve == kCurveLinearToPQ) return DispatchRgbaChroma<kCurveLinearToPQ, 0>(fp, xs, ys, smCount, stream);
+    return DispatchRgbaChroma<kCurveLinearToSMPTE428, 0>(fp, xs, ys, smCount, stream);
 }
 
 } // namespace avifgpu

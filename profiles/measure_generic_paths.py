@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
 """Device-resident throughput of configurations outside BASELINE.json's bench lines (they run wherever the dispatcher
-sends them): 8-bit and 16-bit decodes, 8-bit encode, at 8K.  Prints one JSON line per case.
+sends them).  Every launch converts a stack of 8K frames tall enough that its input + output exceed the 126 MB L2
+several times over (7680 x 17280 for the 8-bit paths, 7680 x 8640 otherwise), and three such sets rotate, so the GB/s
+figures are HBM figures.  Prints one JSON line per case.
 
     python profiles/measure_generic_paths.py
 """
@@ -16,7 +18,8 @@ import torch  # noqa: E402
 import avifgpu  # noqa: E402
 from avifgpu import abi  # noqa: E402
 
-W, H = 7680, 4320
+W, H = 7680, 4320 * 2
+H8 = 4320 * 4  # 8-bit paths move 1.5 - 8 bytes per pixel: four frames per launch
 dev = torch.device("cuda", 0)
 gpu = avifgpu.Context(0)
 g = torch.Generator(device=dev)
@@ -37,6 +40,7 @@ def timed(fn, steps=30):
 
 
 def decode_case(name, bit_depth, host_depth, chroma, nclx, bytes_per_px, alpha=False):
+    H = H8 if bit_depth == 8 else globals()["H"]
     desc = abi.DecodeDesc(W, H, abi.COLORSPACE_YCBCR, chroma, bit_depth, abi.ALPHA_STRAIGHT if alpha else abi.ALPHA_NONE, host_depth, nclx)
     shapes = abi.decode_plane_shapes(desc)
     dt = torch.uint8 if bit_depth == 8 else torch.int16
@@ -57,6 +61,7 @@ def decode_case(name, bit_depth, host_depth, chroma, nclx, bytes_per_px, alpha=F
 
 
 def encode_case(name, host_depth, channels, image_depth, chroma, nclx, bytes_per_px, alpha=abi.ALPHA_NONE):
+    H = H8 if host_depth == 8 else globals()["H"]
     desc = abi.EncodeDesc(W, H, host_depth, channels, alpha, image_depth, abi.TRANSFER_CLIP, 80, abi.LAYOUT_PLANAR_YCBCR, chroma,
                           abi.DOWN_FILTER_BOX, abi.GRAY16_LUT, nclx)
     shapes = abi.encode_plane_shapes(desc)
@@ -119,6 +124,7 @@ def mono_rgb_cases():
                                                          ("decode mono 10-bit -> Gray16 (a16)", abi.COLORSPACE_MONOCHROME, 10, 16, 4),
                                                          ("decode planar RGB 8-bit -> RGB8 (a18)", abi.COLORSPACE_RGB, 8, 8, 6),
                                                          ("decode planar RGB 10-bit -> RGB16 (a18)", abi.COLORSPACE_RGB, 10, 16, 12)):
+        H = H8 if bit_depth == 8 else globals()["H"]
         desc = abi.DecodeDesc(W, H, colorspace, abi.CHROMA_444, bit_depth, abi.ALPHA_NONE, host_depth, abi.Nclx(1, 1, 13, 0 if colorspace == abi.COLORSPACE_RGB else 6, 1))
         shapes = abi.decode_plane_shapes(desc)
         dt = torch.uint8 if bit_depth == 8 else torch.int16
@@ -137,6 +143,7 @@ def mono_rgb_cases():
         ms = timed(run)
         print(json.dumps({"case": name, "ms": ms, "gpx_s": W * H / ms / 1e6, "gb_s": W * H * bpp / ms / 1e6}))
     for name, host_depth, depth, bpp in (("encode Gray8 -> 8-bit Y (a4)", 8, 8, 2), ("encode Gray8 -> 10-bit Y (a4)", 8, 10, 3)):
+        H = H8
         desc = abi.EncodeDesc(W, H, host_depth, 1, abi.ALPHA_NONE, depth)
         shapes = abi.encode_plane_shapes(desc)
         sets = []
@@ -153,12 +160,47 @@ def mono_rgb_cases():
         ms = timed(run)
         print(json.dumps({"case": name, "ms": ms, "gpx_s": W * H / ms / 1e6, "gb_s": W * H * bpp / ms / 1e6}))
 
+
+def float_decode_table_cases():
+    # float hosts reading planar RGB / monochrome images: kernels_fast_decode_table.cu (per-code EOTF table in shared memory)
+    pq = abi.Nclx(1, abi.PRIMARIES_BT2020, abi.TRANSFER_CHAR_PQ, 0, 1)
+    hlg = abi.Nclx(1, abi.PRIMARIES_BT2020, abi.TRANSFER_CHAR_HLG, 0, 1)
+    for name, colorspace, nclx, ootf, bpp in (("decode planar RGB 10-bit PQ -> RGB32f (a18)", abi.COLORSPACE_RGB, pq, 0, 6 + 12),
+                                              ("decode planar RGB 10-bit HLG + OOTF -> RGB32f (a18)", abi.COLORSPACE_RGB, hlg, 1, 6 + 12),
+                                              ("decode mono 12-bit PQ -> Gray32f (a16)", abi.COLORSPACE_MONOCHROME, pq, 0, 2 + 4)):
+        depth = 12 if colorspace == abi.COLORSPACE_MONOCHROME else 10
+        desc = abi.DecodeDesc(W, H, colorspace, abi.CHROMA_444 if colorspace == abi.COLORSPACE_RGB else abi.CHROMA_MONOCHROME, depth, abi.ALPHA_NONE, 32, nclx,
+                              hlg_apply_ootf=ootf)
+        shapes = abi.decode_plane_shapes(desc)
+        ch = abi.decode_host_channels(desc)
+        sets = []
+        for _ in range(3):
+            planes = [None if s is None else torch.randint(0, 1 << depth, s, generator=g, device=dev, dtype=torch.int32).to(torch.int16) for s in shapes]
+            out = torch.empty((H, W * ch), dtype=torch.float32, device=dev)
+            sets.append((avifgpu.planes_from_tensors(planes), planes, out))
+        i = [0]
+
+        def run():
+            s_ = sets[i[0] % 3]
+            i[0] += 1
+            gpu.decode_device(desc, s_[0], s_[2].data_ptr(), s_[2].stride(0) * 4)
+        ms = timed(run, steps=12)
+        print(json.dumps({"case": name, "ms": ms, "gpx_s": W * H / ms / 1e6, "gb_s": W * H * bpp / ms / 1e6}))
+
+
 mono_rgb_cases()
+float_decode_table_cases()
+# premultiplied alpha on the integer hosts (BASELINE config 4's second variant): tuned kernel with the verified premultiply
+encode_case("encode RGBA16 premultiplied -> 10-bit 4:2:2 + A (config 4, premultiplied alpha) (a2, a5)", 16, 4, 10, abi.CHROMA_422, None, 8 + 6,
+            alpha=abi.ALPHA_PREMULTIPLIED)
+encode_case("encode RGBA16 straight -> 10-bit 4:2:2 + A (config 4's own variant, same frame) (a2)", 16, 4, 10, abi.CHROMA_422, None, 8 + 6,
+            alpha=abi.ALPHA_STRAIGHT)
+encode_case("encode RGBA8 premultiplied -> 8-bit 4:2:0 + A (a3, a5)", 8, 4, 8, abi.CHROMA_420, None, 4 + 2.5, alpha=abi.ALPHA_PREMULTIPLIED)
 for tables in (False, True):
     tag = "step tables" if tables else "exact powf"
     float_encode_case(f"encode RGBA32f -> 12-bit PQ 4:2:0 + A, {tag} (a1)", 4, abi.LAYOUT_PLANAR_YCBCR, 16 + 5, tables)
-    float_encode_case(f"encode RGB32f -> interleaved RGB 12-bit PQ (reference layout), generic kernel, {tag} (a1)", 3, abi.LAYOUT_REFERENCE, 12 + 6, tables)
+    float_encode_case(f"encode RGB32f -> interleaved RGB 12-bit PQ (the reference's own layout), {tag} (a1)", 3, abi.LAYOUT_REFERENCE, 12 + 6, tables)
 float_encode_case("encode RGB32f -> 10-bit PQ 4:2:0, tuned kernel (config 2 at 10 bits)", 3, abi.LAYOUT_PLANAR_YCBCR, 15, True, depth=10)
 float_encode_case("encode RGB32f -> 12-bit PQ @ 1000 nit 4:2:0, tuned kernel (config 2 at another peak)", 3, abi.LAYOUT_PLANAR_YCBCR, 15, True, peak=1000)
-float_encode_case("encode RGB32f -> 12-bit SMPTE 428 4:2:0 (two-level table kernel)", 3, abi.LAYOUT_PLANAR_YCBCR, 15, True, transfer=abi.TRANSFER_SMPTE428)
+float_encode_case("encode RGB32f -> 12-bit SMPTE 428 4:2:0 (two-level table in the copy-engine kernel)", 3, abi.LAYOUT_PLANAR_YCBCR, 15, True, transfer=abi.TRANSFER_SMPTE428)
 float_encode_case("encode RGB32f -> 12-bit clip 4:2:0 (no curve)", 3, abi.LAYOUT_PLANAR_YCBCR, 15, True, transfer=abi.TRANSFER_CLIP)
