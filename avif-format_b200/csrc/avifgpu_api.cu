@@ -952,7 +952,7 @@ namespace
         CopyPool()
         {
             const unsigned cores = std::thread::hardware_concurrency();
-            const int count = static_cast<int>(std::min<unsigned>(cores > 1 ? cores - 1 : 0, 7));
+            const int count = static_cast<int>(std::min<unsigned>(cores > 1 ? cores - 1 : 0, 15)); // 16 copying threads with the caller: ~60 GB/s, past the PCIe link they feed
             for (int i = 0; i < count; ++i)
             {
                 workers.emplace_back([this] { Run(); });
