@@ -26,6 +26,7 @@ int LaunchEncodeGeneric(const EncodeParams& params, int hostDepth, void* stream)
 int LaunchDecodeGeneric(const DecodeParams& params, void* stream);
 int LaunchEncodeFast(const EncodeParams& params, int hostDepth, void* stream);   // 0 = not applicable
 int LaunchEncodeFastInteger(const EncodeParams& params, int hostDepth, void* stream); // 0 = not applicable
+int LaunchEncodeFastGray32(const EncodeParams& params, int hostDepth, void* stream);  // 0 = not applicable
 cudaError_t BuildGray16Lut(uint16_t* deviceLut, int smpte428, uint32_t maxCode, void* stream);
 long long VerifyHlgDivisions(void* stream);
 long long VerifyFastPremultiply(uint32_t maxCode, void* stream);
@@ -61,6 +62,11 @@ int LaunchEncode(const EncodeParams& params, int hostDepth, void* stream)
         return fast;
     }
     fast = LaunchEncodeFastInteger(params, hostDepth, stream);
+    if (fast != 0)
+    {
+        return fast;
+    }
+    fast = LaunchEncodeFastGray32(params, hostDepth, stream);
     if (fast != 0)
     {
         return fast;

@@ -1,0 +1,237 @@
+// kernels_fast_gray32.cu -- Gray(+A) float hosts -> Y (+ Alpha) planes: CreateHeifImageGrayThirtyTwoBit
+// (WriteHeifImage.cpp:502-627; gray knows the PQ and clip transfers only, :578-588).
+//
+// One sample per pixel goes through the curve, so this is a streaming kernel: a thread converts 4 adjacent pixels
+// (one or two 128-bit loads, 64-bit stores), the PQ code comes from the compact step table in shared memory
+// (curve_tables.h; flagged samples are resolved from first_k and the band bitmap on the spot, +inf / NaN take the exact
+// evaluation), the clip transfer is the quantiser alone.  4 + 2 (or 8 + 4) bytes per pixel: HBM-bound.
+#include "kernels_fast_common.cuh"
+#include "../../include/avifgpu.h"
+
+namespace avifgpu
+{
+
+using namespace avifpix;
+using avifmath::LibmTables;
+
+namespace
+{
+
+constexpr int kGrayThreads = 256;
+
+struct Gray32Params
+{
+    const uint8_t* rows;
+    int64_t rowStride;
+    uint8_t* planeY;
+    int64_t strideY;
+    uint8_t* planeA;
+    int64_t strideA;
+    int32_t groupsPerRow; // 4 pixels each
+    int32_t rowCount;
+    int32_t premultiply;
+    float pqMultiplier;
+    float maxCodeFloat;
+    int32_t maxCode;
+    CurveTableView table;
+};
+
+// CHANNELS 1 (Gray) or 2 (Gray + alpha); PQ = 1: LinearToPQ through the compact table, 0: clip.
+template <int CHANNELS, int PQ>
+__global__ void __launch_bounds__(kGrayThreads) EncodeGrayF32Kernel(const Gray32Params p)
+{
+    extern __shared__ __align__(16) uint8_t sharedBytes[];
+    uint64_t* libmStorage = reinterpret_cast<uint64_t*>(sharedBytes);
+    uint32_t* compactEntries = reinterpret_cast<uint32_t*>(sharedBytes + 768);
+    uint32_t* firstBits = compactEntries + ((p.table.flatCount + 3) & ~3);
+    const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
+    if (PQ)
+    {
+        const uint4* source = reinterpret_cast<const uint4*>(p.table.compact);
+        uint4* target = reinterpret_cast<uint4*>(compactEntries);
+        const int quads = (p.table.flatCount + 3) / 4;
+        for (int i = threadIdx.x; i < quads; i += blockDim.x)
+        {
+            target[i] = __ldg(source + i);
+        }
+        for (int i = threadIdx.x; i <= p.maxCode + 1; i += blockDim.x)
+        {
+            firstBits[i] = p.table.firstBits[i];
+        }
+    }
+    __syncthreads();
+
+    const uint32_t shift = p.table.flatShift;
+    const int32_t negativeLow = -static_cast<int32_t>(p.table.flatLow);
+    const int32_t span = static_cast<int32_t>(p.table.flatHigh - p.table.flatLow);
+    const uint32_t topShift = 32u - shift;
+
+    const auto curveCode = [&](float value) -> uint32_t
+    {
+        if (!PQ)
+        {
+            return FloatToCode(value, p.maxCodeFloat);
+        }
+        const uint32_t bits = __float_as_uint(value);
+        if (static_cast<int32_t>(bits) > 0x7f7fffff)
+        {
+            return ExactCurveCode<kCurveLinearToPQ>(value, p.pqMultiplier, p.maxCodeFloat, t); // +inf / NaN
+        }
+        bool inBand;
+        uint32_t entry;
+        uint32_t code = static_cast<uint32_t>(LookupCurveCompact<0>(bits, compactEntries, shift, negativeLow, span, topShift, p.table.compactCodeMask,
+                                                                    p.table.compactMagic, inBand, entry));
+        if (inBand)
+        {
+            code = ResolveCompactInBand(bits, entry, code, topShift, p.table.compactCodeMask, firstBits, p.table.bandBits, p.table.bandStrideLog2);
+        }
+        return code;
+    };
+
+    const long long groups = static_cast<long long>(p.groupsPerRow) * p.rowCount;
+    for (long long group = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; group < groups;
+         group += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const long long row = group / p.groupsPerRow;
+        const long long column = (group - row * p.groupsPerRow) * 4;
+        const float4* source = reinterpret_cast<const float4*>(p.rows + row * p.rowStride + column * (4 * CHANNELS));
+        float gray[4], alpha[4];
+        if (CHANNELS == 1)
+        {
+            const float4 v = __ldcs(source);
+            gray[0] = v.x; gray[1] = v.y; gray[2] = v.z; gray[3] = v.w;
+        }
+        else
+        {
+            const float4 a = __ldcs(source), b = __ldcs(source + 1);
+            gray[0] = a.x; alpha[0] = a.y; gray[1] = a.z; alpha[1] = a.w;
+            gray[2] = b.x; alpha[2] = b.y; gray[3] = b.z; alpha[3] = b.w;
+        }
+        uint32_t yCode[4], aCode[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            float value = gray[i];
+            if (CHANNELS == 2)
+            {
+                // WriteHeifImage.cpp:556-575
+                const float a = ClampF(alpha[i], 0.0f, 1.0f);
+                if (p.premultiply && a < 1.0f)
+                {
+                    value = (a == 0) ? 0.0f : PremultiplyColor(ClampF(value, 0.0f, 1.0f), a, 1.0f);
+                }
+                aCode[i] = FloatToCode(a, p.maxCodeFloat);
+            }
+            else
+            {
+                value = ClampF(value, 0.0f, 1.0f); // WriteHeifImage.cpp:602
+            }
+            yCode[i] = curveCode(value);
+        }
+        __stcs(reinterpret_cast<uint2*>(p.planeY + row * p.strideY + column * 2), make_uint2(yCode[0] | (yCode[1] << 16), yCode[2] | (yCode[3] << 16)));
+        if (CHANNELS == 2)
+        {
+            __stcs(reinterpret_cast<uint2*>(p.planeA + row * p.strideA + column * 2), make_uint2(aCode[0] | (aCode[1] << 16), aCode[2] | (aCode[3] << 16)));
+        }
+    }
+}
+
+bool Aligned(const void* p, int64_t stride, int alignment)
+{
+    return (reinterpret_cast<uintptr_t>(p) % alignment) == 0 && (stride % alignment) == 0;
+}
+
+template <int CHANNELS, int PQ>
+cudaError_t LaunchGray32(const Gray32Params& gp, size_t shared, int smCount, cudaStream_t stream)
+{
+    static std::atomic<uint64_t> configuredDevices{ 0 };
+    {
+        const cudaError_t e = AllowDynamicShared(EncodeGrayF32Kernel<CHANNELS, PQ>, 100 * 1024, configuredDevices);
+        if (e != cudaSuccess)
+        {
+            return e;
+        }
+    }
+    const long long groups = static_cast<long long>(gp.groupsPerRow) * gp.rowCount;
+    long long blocks = (groups + kGrayThreads - 1) / kGrayThreads;
+    const long long cap = static_cast<long long>(smCount) * 2; // every CTA stages its own table: few, long-lived CTAs
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    EncodeGrayF32Kernel<CHANNELS, PQ><<<static_cast<unsigned>(blocks), kGrayThreads, shared, stream>>>(gp);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+int LaunchEncodeGeneric(const EncodeParams& params, int hostDepth, void* stream);
+
+// Returns the number of kernels launched, 0 if this configuration is not covered, or a negative status.
+int LaunchEncodeFastGray32(const EncodeParams& p, int hostDepth, void* streamHandle)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(streamHandle);
+    if (hostDepth != 32 || p.planar || p.channels > 2 || p.imageDepth <= 8 || p.hlgInverseOotf || p.rowMatrixEnabled)
+    {
+        return 0;
+    }
+    const bool pq = p.transfer == AVIFGPU_TRANSFER_PQ;
+    if (!pq && p.transfer != AVIFGPU_TRANSFER_CLIP)
+    {
+        return 0; // the reference rejects anything else for gray (WriteHeifImage.cpp:586-587): the generic kernel's business
+    }
+    if (pq && (p.curveTable == nullptr || p.curveTable->compact == nullptr || p.curveTable->firstBits == nullptr || p.curveTable->bandBits == nullptr))
+    {
+        return 0; // no verified compact table: the generic exact kernel serves it
+    }
+    const int width4 = p.width & ~3;
+    if (width4 < 4 || p.rowCount < 1 || !Aligned(p.rows, p.rowStride, 16) || !Aligned(p.plane[0], p.planeStride[0], 8) ||
+        (p.channels == 2 && !Aligned(p.plane[3], p.planeStride[3], 8)))
+    {
+        return 0;
+    }
+    Gray32Params gp{};
+    gp.rows = static_cast<const uint8_t*>(p.rows);
+    gp.rowStride = p.rowStride;
+    gp.planeY = static_cast<uint8_t*>(p.plane[0]);
+    gp.strideY = p.planeStride[0];
+    gp.planeA = static_cast<uint8_t*>(p.plane[3]);
+    gp.strideA = p.planeStride[3];
+    gp.groupsPerRow = width4 / 4;
+    gp.rowCount = p.rowCount;
+    gp.premultiply = p.premultiply;
+    gp.pqMultiplier = p.pqMultiplier;
+    gp.maxCodeFloat = p.maxCodeFloat;
+    gp.maxCode = static_cast<int32_t>(p.maxCode);
+    size_t shared = 768;
+    if (pq)
+    {
+        gp.table = *p.curveTable;
+        shared += (static_cast<size_t>((gp.table.flatCount + 3) & ~3) + static_cast<size_t>(p.maxCode) + 2) * sizeof(uint32_t);
+        if (shared > 100 * 1024)
+        {
+            return 0;
+        }
+    }
+    const int smCount = p.smCount > 0 ? p.smCount : 148;
+    cudaError_t e;
+    if (p.channels == 2) e = pq ? LaunchGray32<2, 1>(gp, shared, smCount, stream) : LaunchGray32<2, 0>(gp, shared, smCount, stream);
+    else e = pq ? LaunchGray32<1, 1>(gp, shared, smCount, stream) : LaunchGray32<1, 0>(gp, shared, smCount, stream);
+    if (e != cudaSuccess)
+    {
+        return ReportLaunchFailure(static_cast<int>(e));
+    }
+    int launched = 1;
+    if (width4 < p.width)
+    {
+        EncodeParams strip = p;
+        strip.rows = static_cast<const uint8_t*>(p.rows) + static_cast<int64_t>(width4) * (4 * p.channels);
+        strip.width = p.width - width4;
+        strip.plane[0] = static_cast<uint8_t*>(p.plane[0]) + static_cast<int64_t>(width4) * 2;
+        if (p.channels == 2) strip.plane[3] = static_cast<uint8_t*>(p.plane[3]) + static_cast<int64_t>(width4) * 2;
+        const int n = LaunchEncodeGeneric(strip, hostDepth, streamHandle);
+        if (n < 0) return n;
+        launched += n;
+    }
+    return launched;
+}
+
+} // namespace avifgpu

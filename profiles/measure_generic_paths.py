@@ -85,7 +85,7 @@ def encode_case(name, host_depth, channels, image_depth, chroma, nclx, bytes_per
 
 
 def float_encode_case(name, channels, layout, bytes_per_px, tables, depth=12, peak=80, transfer=abi.TRANSFER_PQ):
-    alpha = abi.ALPHA_STRAIGHT if channels == 4 else abi.ALPHA_NONE
+    alpha = abi.ALPHA_STRAIGHT if channels in (2, 4) else abi.ALPHA_NONE
     nclx = abi.Nclx(1, abi.PRIMARIES_BT2020, abi.TRANSFER_CHAR_PQ, abi.MATRIX_BT2020_NCL, 1)
     desc = abi.EncodeDesc(W, H, 32, channels, alpha, depth, transfer, peak, layout, abi.CHROMA_420 if layout == abi.LAYOUT_PLANAR_YCBCR else abi.CHROMA_444,
                           abi.DOWN_FILTER_BOX, abi.GRAY16_LUT, nclx)
@@ -204,3 +204,8 @@ float_encode_case("encode RGB32f -> 10-bit PQ 4:2:0, tuned kernel (config 2 at 1
 float_encode_case("encode RGB32f -> 12-bit PQ @ 1000 nit 4:2:0, tuned kernel (config 2 at another peak)", 3, abi.LAYOUT_PLANAR_YCBCR, 15, True, peak=1000)
 float_encode_case("encode RGB32f -> 12-bit SMPTE 428 4:2:0 (two-level table in the copy-engine kernel)", 3, abi.LAYOUT_PLANAR_YCBCR, 15, True, transfer=abi.TRANSFER_SMPTE428)
 float_encode_case("encode RGB32f -> 12-bit clip 4:2:0 (no curve)", 3, abi.LAYOUT_PLANAR_YCBCR, 15, True, transfer=abi.TRANSFER_CLIP)
+# Gray(+A) float hosts (row a4 at 32 bits): kernels_fast_gray32.cu, PQ through the compact step table / clip
+float_encode_case("encode Gray32f -> 12-bit PQ Y (a4)", 1, abi.LAYOUT_REFERENCE, 4 + 2, True)
+float_encode_case("encode GrayA32f -> 12-bit PQ Y + A (a4)", 2, abi.LAYOUT_REFERENCE, 8 + 4, True)
+float_encode_case("encode Gray32f -> 12-bit clip Y (a4)", 1, abi.LAYOUT_REFERENCE, 4 + 2, True, transfer=abi.TRANSFER_CLIP)
+float_encode_case("encode Gray32f -> 12-bit PQ Y, exact powf (a4)", 1, abi.LAYOUT_REFERENCE, 4 + 2, False)
