@@ -562,6 +562,7 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
     table->view.bandStrideLog2 = 0;
     table->view.compact = nullptr;
     table->view.firstBits = nullptr;
+    table->view.compactImageBytes = 0;
     table->view.compactCodeMask = 0;
     table->view.compactMagic = 0;
     if (!flat.empty())
@@ -622,18 +623,22 @@ bool BuildCurveTable(int curve, int param, int depth, void* streamHandle, CurveT
             {
                 firstBits[step.k] = step.first;
             }
-            if (!Check(cudaMalloc(&table->deviceCompact, (compact.size() + 4) * sizeof(uint32_t)), "cudaMalloc", &table->error) ||
-                !Check(cudaMalloc(&table->deviceFirstBits, firstBits.size() * sizeof(uint32_t)), "cudaMalloc", &table->error) ||
-                !Check(cudaMemsetAsync(table->deviceCompact, 0, (compact.size() + 4) * sizeof(uint32_t), stream), "memset", &table->error) ||
-                !Check(cudaMemcpyAsync(table->deviceCompact, compact.data(), compact.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "H2D", &table->error) ||
-                !Check(cudaMemcpyAsync(table->deviceFirstBits, firstBits.data(), firstBits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "H2D", &table->error) ||
+            // one allocation = the kernels' shared-memory image (CurveTableView::compactImageBytes)
+            const size_t paddedCompact = (compact.size() + 3u) & ~static_cast<size_t>(3u);
+            const size_t paddedFirst = (firstBits.size() + 3u) & ~static_cast<size_t>(3u);
+            std::vector<uint32_t> image(paddedCompact + paddedFirst, 0u);
+            std::copy(compact.begin(), compact.end(), image.begin());
+            std::copy(firstBits.begin(), firstBits.end(), image.begin() + static_cast<std::ptrdiff_t>(paddedCompact));
+            if (!Check(cudaMalloc(&table->deviceCompact, image.size() * sizeof(uint32_t)), "cudaMalloc", &table->error) ||
+                !Check(cudaMemcpyAsync(table->deviceCompact, image.data(), image.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "H2D", &table->error) ||
                 !Check(cudaStreamSynchronize(stream), "compact table upload", &table->error))
             {
                 FreeCurveTable(table);
                 return false;
             }
             table->view.compact = static_cast<const uint32_t*>(table->deviceCompact);
-            table->view.firstBits = static_cast<const uint32_t*>(table->deviceFirstBits);
+            table->view.firstBits = table->view.compact + paddedCompact;
+            table->view.compactImageBytes = static_cast<uint32_t>(image.size() * sizeof(uint32_t));
             table->view.compactCodeMask = maxCode << kCompactLenBits;
             table->view.compactMagic = 0x4b000000u;
             table->stats.compactBuckets = static_cast<int32_t>(compact.size());

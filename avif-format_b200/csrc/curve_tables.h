@@ -82,6 +82,10 @@ struct CurveTableView
     // nullptr.  See "Compact entries" below.
     const uint32_t* compact;
     const uint32_t* firstBits; // first_k for k = 0 .. maxCode + 1 (0 for codes that no input reaches)
+    // compact and firstBits are one device allocation, the shared-memory image of the kernels that use them:
+    // [flatCount words, padded to a multiple of 4][maxCode + 2 words, padded to a multiple of 4] -- so one thread can
+    // hand the whole table to the copy engine (cp.async.bulk wants 16-byte multiples).  firstBits == compact + (padded count).
+    uint32_t compactImageBytes;
     uint32_t compactCodeMask;  // ((1 << depth) - 1) << 6
     uint32_t compactMagic;     // 0x4b000000 (the bits of 2^23), carried as data: see LookupCurveCompact
 };

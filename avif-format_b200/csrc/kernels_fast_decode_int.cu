@@ -11,6 +11,7 @@
 //     sample the site covers (both rows of a 4:2:0 site); same float expressions, same association;
 //   * premultiplied alpha, odd starting rows of a 4:2:0 block, depths above 12 bits and unaligned buffers stay with the
 //     generic kernel.
+#include "group_walk.cuh"
 #include "kernel_params.h"
 #include "pixel_math.cuh"
 #include "../../include/avifgpu.h"
@@ -408,12 +409,11 @@ __global__ void __launch_bounds__(kStreamThreads) StreamDecodeKernel(const Strea
     // source planes: mono -> Y (, A at index 3); RGB -> R, G, B (, A)
     constexpr int kColours = MONO ? 1 : 3;
     constexpr bool kAlpha = CHANNELS > kColours;
-    const long long groups = static_cast<long long>(p.groupsPerRow) * p.rowCount;
-    for (long long group = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; group < groups;
-         group += static_cast<long long>(gridDim.x) * blockDim.x)
+    for (GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.groupsPerRow, p.rowCount);
+         walk.Inside(p.rowCount); walk.Advance(p.rowCount))
     {
-        const long long row = group / p.groupsPerRow;
-        const long long column = (group - row * p.groupsPerRow) * 8;
+        const long long row = walk.row;
+        const long long column = static_cast<long long>(walk.column) * 8;
         Raw8<SampleT> raw[CHANNELS];
 #pragma unroll
         for (int c = 0; c < CHANNELS; ++c)

@@ -11,6 +11,7 @@
 // ColorTransfer.cpp:192-205) and the integer-domain un-premultiplication the reference applies BEFORE the table
 // (ReadHeifImage.cpp:1049-1066, YuvDecode.cpp:247-260).
 // A thread converts 8 adjacent pixels: one 128-bit load per plane, 128-bit stores.
+#include "group_walk.cuh"
 #include "kernel_params.h"
 #include "../../include/avifgpu.h"
 
@@ -76,12 +77,11 @@ __global__ void __launch_bounds__(kTableThreads) TableDecodeF32Kernel(const Tabl
 
     constexpr int kChannels = COLOURS + ALPHA;
     const float maxCodeFloat = static_cast<float>(p.maxCode);
-    const long long groups = static_cast<long long>(p.groupsPerRow) * p.rowCount;
-    for (long long group = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; group < groups;
-         group += static_cast<long long>(gridDim.x) * blockDim.x)
+    for (GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.groupsPerRow, p.rowCount);
+         walk.Inside(p.rowCount); walk.Advance(p.rowCount))
     {
-        const long long row = group / p.groupsPerRow;
-        const long long column = (group - row * p.groupsPerRow) * 8;
+        const long long row = walk.row;
+        const long long column = static_cast<long long>(walk.column) * 8;
         uint4 raw[kChannels];
 #pragma unroll
         for (int c = 0; c < kChannels; ++c)

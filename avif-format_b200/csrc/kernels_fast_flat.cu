@@ -34,7 +34,10 @@ constexpr int kFlatThreads = kFlatWarps * 32;
 constexpr int kRowSegmentBytes = kTilePixels * 12;      // one tile row of RGB32f
 constexpr int kStageBytesPerWarp = 2 * kRowSegmentBytes; // both rows, linear
 constexpr int kRowSegmentWords = kRowSegmentBytes / 4;
-constexpr int kSharedBarriers = 256;                     // kFlatWarps x 8 bytes, padded
+constexpr int kSharedBarriers = 256;                     // kFlatWarps x 8 bytes, padded; the last slot is the table's barrier
+constexpr int kTableBarrierSlot = kSharedBarriers / 8 - 1;
+static_assert(kFlatWarps <= kTableBarrierSlot, "the warps' barriers and the table's share kSharedBarriers");
+constexpr uint32_t kTableCopyChunk = 16384;              // bytes per bulk copy of the table image
 constexpr int kSharedLimit = 227 * 1024;
 __host__ __device__ constexpr int FlatFixedBytes() { return kSharedLibm + kSharedBarriers + kFlatWarps * kStageBytesPerWarp; }
 
@@ -49,6 +52,11 @@ struct FlatSchedule
     int32_t segmentRows, longSegments; // segment s holds segmentRows (+ 1 if s < longSegments) tile rows
     int32_t lastColumnBytes;          // row-segment bytes of the last tile column (width need not be a multiple of 128)
     int32_t unpairedTileRow;          // tile row whose second image row does not exist (odd row count), or -1
+    // Run lengths differ by one tile row.  With the warps of a CTA on adjacent items a CTA is all long runs or all short
+    // ones, and the launch ends when the long CTAs do (config 2: 45 of 148 CTAs run 32 tile rounds, the rest 31, a 3 us
+    // tail).  scatter = 1 deals the items round-robin over the CTAs instead (item = warp * CTAs + CTA): every CTA gets
+    // the same mix, so the extra round is run by 8-9 warps per SM rather than by 28 on a third of the SMs.
+    int32_t scatter;
 };
 
 __device__ __forceinline__ uint32_t SharedAddress(const void* pointer) { return static_cast<uint32_t>(__cvta_generic_to_shared(pointer)); }
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     uint8_t* stageAll = sharedBytes + kSharedLibm + kSharedBarriers;
     uint2* flatEntries = reinterpret_cast<uint2*>(sharedBytes + FlatFixedBytes());
     uint32_t* compactEntries = reinterpret_cast<uint32_t*>(sharedBytes + FlatFixedBytes());                                  // TWO_LEVEL == 2 ...
-    uint32_t* firstBits = compactEntries + ((p.table.flatCount + 3) & ~3);                                                   // ... then first_k per code
+    const uint32_t* firstBits = compactEntries + ((p.table.flatCount + 3) & ~3);                                             // ... then first_k per code
     uint2* octaves = reinterpret_cast<uint2*>(sharedBytes + FlatFixedBytes());            // TWO_LEVEL: 256 entries ...
     uint32_t* bucketWords = reinterpret_cast<uint32_t*>(sharedBytes + FlatFixedBytes() + 2048); // ... then the bucket words
 
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
 
     const int tilesX = schedule.tilesX;
     const int warpCount = schedule.warpCount;
-    const int firstItem = static_cast<int>(blockIdx.x) * kFlatWarps + warpInBlock;
+    const int firstItem = schedule.scatter ? warpInBlock * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x) * kFlatWarps + warpInBlock;
     constexpr int kChromaRowsPerTile = YS ? 1 : 2;
     constexpr int kChromaTileBytes = XS ? kTilePixels : 2 * kTilePixels;
 
@@ -153,6 +161,23 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     auto columnBytes = [&](int column) { return column == tilesX - 1 ? static_cast<uint32_t>(schedule.lastColumnBytes) : static_cast<uint32_t>(kRowSegmentBytes); };
     auto sourceOffsetOf = [&](int row, int column) { return static_cast<int64_t>(row) * 2 * p.rowStride + static_cast<int64_t>(column) * kRowSegmentBytes; };
 
+    const uint32_t tableBarrier = SharedAddress(barriers + kTableBarrierSlot);
+    if (kCompact && threadIdx.x == 0)
+    {
+        // The compact table and first_k are one image in global memory laid out like the shared one (curve_tables.h):
+        // the copy engine stages it while the warps set up; staging it with ordinary loads kept every SM busy for ~7 us
+        // of a ~100 us launch (148 CTAs walking the same 67 KB in step).
+        BarrierInit(tableBarrier, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t imageBytes = p.table.compactImageBytes;
+        BarrierExpect(tableBarrier, imageBytes);
+        const uint32_t target = SharedAddress(compactEntries);
+        const uint8_t* source = reinterpret_cast<const uint8_t*>(p.table.compact);
+        for (uint32_t offset = 0; offset < imageBytes; offset += kTableCopyChunk)
+        {
+            BulkCopyToShared(target + offset, source + offset, min(kTableCopyChunk, imageBytes - offset), tableBarrier);
+        }
+    }
     if (ElectOne())
     {
         BarrierInit(barrier, 1);
@@ -171,18 +196,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
     if (kCompact)
     {
-        const uint4* source = reinterpret_cast<const uint4*>(p.table.compact);
-        uint4* target = reinterpret_cast<uint4*>(compactEntries);
-        const int quads = (p.table.flatCount + 3) / 4;
-#pragma unroll 8
-        for (int i = threadIdx.x; i < quads; i += blockDim.x)
-        {
-            target[i] = __ldg(source + i);
-        }
-        for (int i = threadIdx.x; i <= p.maxCode + 1; i += blockDim.x)
-        {
-            firstBits[i] = p.table.firstBits[i];
-        }
+        // in flight (above)
     }
     else if (TWO_LEVEL)
     {
@@ -207,7 +221,11 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
             target[i] = __ldg(source + i);
         }
     }
-    __syncthreads();
+    __syncthreads(); // the libm tables, the barriers' initialisation
+    if (kCompact)
+    {
+        BarrierWait(tableBarrier, 0);
+    }
 
     const uint32_t flatShift = p.table.flatShift;
     const int32_t negativeLow = -static_cast<int32_t>(p.table.flatLow);
@@ -429,7 +447,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
 inline size_t TableSharedBytes(const FastEncodeParams& fp, int tableKind)
 {
     if (tableKind == 1) return 2048 + static_cast<size_t>(fp.table.bucketCount) * sizeof(uint32_t);
-    if (tableKind >= 2) return (static_cast<size_t>((fp.table.flatCount + 3) & ~3) + static_cast<size_t>(fp.maxCode) + 2) * sizeof(uint32_t);
+    if (tableKind >= 2) return fp.table.compactImageBytes;
     return static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
 }
 
@@ -467,6 +485,8 @@ cudaError_t LaunchFlatKernel(const FastEncodeParams& fp, int smCount, cudaStream
     schedule.longSegments = schedule.tileRows % schedule.segments;
     schedule.lastColumnBytes = (fp.width - (schedule.tilesX - 1) * kTilePixels) * 12;
     schedule.unpairedTileRow = (fp.rowCount & 1) ? fp.rowCount / 2 : -1;
+    static const bool scatterOff = []() { const char* v = getenv("AVIFGPU_FLAT_SCATTER"); return v != nullptr && v[0] == '0'; }(); // A/B measurements
+    schedule.scatter = scatterOff ? 0 : 1;
     EncodeRgbF32FlatKernel<CURVE, XS, YS, TWO_LEVEL, INTERLEAVED><<<static_cast<unsigned>(blocks), kFlatThreads, shared, stream>>>(fp, schedule);
     return cudaGetLastError();
 }

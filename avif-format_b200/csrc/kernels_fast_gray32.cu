@@ -5,6 +5,7 @@
 // (one or two 128-bit loads, 64-bit stores), the PQ code comes from the compact step table in shared memory
 // (curve_tables.h; flagged samples are resolved from first_k and the band bitmap on the spot, +inf / NaN take the exact
 // evaluation), the clip transfer is the quantiser alone.  4 + 2 (or 8 + 4) bytes per pixel: HBM-bound.
+#include "group_walk.cuh"
 #include "kernels_fast_common.cuh"
 #include "../../include/avifgpu.h"
 
@@ -17,7 +18,9 @@ using avifmath::LibmTables;
 namespace
 {
 
-constexpr int kGrayThreads = 256;
+constexpr int kGrayTableThreads = 1024; // PQ: one CTA per SM stages the table once and keeps 32 warps on it
+constexpr int kGrayClipThreads = 256;   // clip: no table, many small CTAs
+constexpr int kGroupsInFlight = 2;      // groups (4 pixels each) a thread loads before it converts the first
 
 struct Gray32Params
 {
@@ -36,30 +39,51 @@ struct Gray32Params
     CurveTableView table;
 };
 
+__device__ __forceinline__ uint32_t SharedAddressOf(const void* pointer) { return static_cast<uint32_t>(__cvta_generic_to_shared(pointer)); }
+
 // CHANNELS 1 (Gray) or 2 (Gray + alpha); PQ = 1: LinearToPQ through the compact table, 0: clip.
 template <int CHANNELS, int PQ>
-__global__ void __launch_bounds__(kGrayThreads) EncodeGrayF32Kernel(const Gray32Params p)
+__global__ void __launch_bounds__(PQ ? kGrayTableThreads : kGrayClipThreads) EncodeGrayF32Kernel(const Gray32Params p)
 {
     extern __shared__ __align__(16) uint8_t sharedBytes[];
     uint64_t* libmStorage = reinterpret_cast<uint64_t*>(sharedBytes);
-    uint32_t* compactEntries = reinterpret_cast<uint32_t*>(sharedBytes + 768);
-    uint32_t* firstBits = compactEntries + ((p.table.flatCount + 3) & ~3);
-    const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
-    if (PQ)
+    uint64_t* tableBarrierStorage = reinterpret_cast<uint64_t*>(sharedBytes + 768);
+    uint32_t* compactEntries = reinterpret_cast<uint32_t*>(sharedBytes + 768 + 16);
+    const uint32_t* firstBits = compactEntries + ((p.table.flatCount + 3) & ~3);
+    if (PQ && threadIdx.x == 0)
     {
-        const uint4* source = reinterpret_cast<const uint4*>(p.table.compact);
-        uint4* target = reinterpret_cast<uint4*>(compactEntries);
-        const int quads = (p.table.flatCount + 3) / 4;
-        for (int i = threadIdx.x; i < quads; i += blockDim.x)
+        // the table image (compact entries + first_k, curve_tables.h) goes through the copy engine
+        const uint32_t barrier = SharedAddressOf(tableBarrierStorage);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barrier), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t imageBytes = p.table.compactImageBytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barrier), "r"(imageBytes) : "memory");
+        const uint32_t target = SharedAddressOf(compactEntries);
+        const uint8_t* source = reinterpret_cast<const uint8_t*>(p.table.compact);
+        for (uint32_t offset = 0; offset < imageBytes; offset += 16384u)
         {
-            target[i] = __ldg(source + i);
-        }
-        for (int i = threadIdx.x; i <= p.maxCode + 1; i += blockDim.x)
-        {
-            firstBits[i] = p.table.firstBits[i];
+            const uint32_t bytes = min(16384u, imageBytes - offset);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(target + offset),
+                         "l"(source + offset), "r"(bytes), "r"(barrier)
+                         : "memory");
         }
     }
+    const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
     __syncthreads();
+    if (PQ)
+    {
+        const uint32_t barrier = SharedAddressOf(tableBarrierStorage);
+        asm volatile(
+            "{\n"
+            ".reg .pred done;\n"
+            "TABLE_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], 0;\n"
+            "@done bra TABLE_READY;\n"
+            "bra TABLE_WAIT;\n"
+            "TABLE_READY:\n"
+            "}\n" ::"r"(barrier)
+            : "memory");
+    }
 
     const uint32_t shift = p.table.flatShift;
     const int32_t negativeLow = -static_cast<int32_t>(p.table.flatLow);
@@ -88,50 +112,76 @@ __global__ void __launch_bounds__(kGrayThreads) EncodeGrayF32Kernel(const Gray32
         return code;
     };
 
-    const long long groups = static_cast<long long>(p.groupsPerRow) * p.rowCount;
-    for (long long group = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; group < groups;
-         group += static_cast<long long>(gridDim.x) * blockDim.x)
+    GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.groupsPerRow, p.rowCount);
+    while (walk.Inside(p.rowCount))
     {
-        const long long row = group / p.groupsPerRow;
-        const long long column = (group - row * p.groupsPerRow) * 4;
-        const float4* source = reinterpret_cast<const float4*>(p.rows + row * p.rowStride + column * (4 * CHANNELS));
-        float gray[4], alpha[4];
-        if (CHANNELS == 1)
-        {
-            const float4 v = __ldcs(source);
-            gray[0] = v.x; gray[1] = v.y; gray[2] = v.z; gray[3] = v.w;
-        }
-        else
-        {
-            const float4 a = __ldcs(source), b = __ldcs(source + 1);
-            gray[0] = a.x; alpha[0] = a.y; gray[1] = a.z; alpha[1] = a.w;
-            gray[2] = b.x; alpha[2] = b.y; gray[3] = b.z; alpha[3] = b.w;
-        }
-        uint32_t yCode[4], aCode[4];
+        float4 loaded[kGroupsInFlight][CHANNELS];
+        long long planeOffsetY[kGroupsInFlight], planeOffsetA[kGroupsInFlight];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int u = 0; u < kGroupsInFlight; ++u)
         {
-            float value = gray[i];
-            if (CHANNELS == 2)
+            planeOffsetY[u] = -1;
+            planeOffsetA[u] = 0;
+            if (walk.Inside(p.rowCount))
             {
-                // WriteHeifImage.cpp:556-575
-                const float a = ClampF(alpha[i], 0.0f, 1.0f);
-                if (p.premultiply && a < 1.0f)
+                const long long row = walk.row;
+                const long long column = static_cast<long long>(walk.column) * 4;
+                const float4* source = reinterpret_cast<const float4*>(p.rows + row * p.rowStride + column * (4 * CHANNELS));
+#pragma unroll
+                for (int c = 0; c < CHANNELS; ++c)
                 {
-                    value = (a == 0) ? 0.0f : PremultiplyColor(ClampF(value, 0.0f, 1.0f), a, 1.0f);
+                    loaded[u][c] = __ldcs(source + c);
                 }
-                aCode[i] = FloatToCode(a, p.maxCodeFloat);
+                planeOffsetY[u] = row * p.strideY + column * 2;
+                planeOffsetA[u] = row * p.strideA + column * 2;
+            }
+            walk.Advance(p.rowCount);
+        }
+#pragma unroll
+        for (int u = 0; u < kGroupsInFlight; ++u)
+        {
+            if (planeOffsetY[u] < 0)
+            {
+                continue;
+            }
+            float gray[4], alpha[4];
+            if (CHANNELS == 1)
+            {
+                const float4 v = loaded[u][0];
+                gray[0] = v.x; gray[1] = v.y; gray[2] = v.z; gray[3] = v.w;
             }
             else
             {
-                value = ClampF(value, 0.0f, 1.0f); // WriteHeifImage.cpp:602
+                const float4 a = loaded[u][0], b = loaded[u][CHANNELS - 1];
+                gray[0] = a.x; alpha[0] = a.y; gray[1] = a.z; alpha[1] = a.w;
+                gray[2] = b.x; alpha[2] = b.y; gray[3] = b.z; alpha[3] = b.w;
             }
-            yCode[i] = curveCode(value);
-        }
-        __stcs(reinterpret_cast<uint2*>(p.planeY + row * p.strideY + column * 2), make_uint2(yCode[0] | (yCode[1] << 16), yCode[2] | (yCode[3] << 16)));
-        if (CHANNELS == 2)
-        {
-            __stcs(reinterpret_cast<uint2*>(p.planeA + row * p.strideA + column * 2), make_uint2(aCode[0] | (aCode[1] << 16), aCode[2] | (aCode[3] << 16)));
+            uint32_t yCode[4], aCode[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                float value = gray[i];
+                if (CHANNELS == 2)
+                {
+                    // WriteHeifImage.cpp:556-575
+                    const float a = ClampF(alpha[i], 0.0f, 1.0f);
+                    if (p.premultiply && a < 1.0f)
+                    {
+                        value = (a == 0) ? 0.0f : PremultiplyColor(ClampF(value, 0.0f, 1.0f), a, 1.0f);
+                    }
+                    aCode[i] = FloatToCode(a, p.maxCodeFloat);
+                }
+                else
+                {
+                    value = ClampF(value, 0.0f, 1.0f); // WriteHeifImage.cpp:602
+                }
+                yCode[i] = curveCode(value);
+            }
+            __stcs(reinterpret_cast<uint2*>(p.planeY + planeOffsetY[u]), make_uint2(yCode[0] | (yCode[1] << 16), yCode[2] | (yCode[3] << 16)));
+            if (CHANNELS == 2)
+            {
+                __stcs(reinterpret_cast<uint2*>(p.planeA + planeOffsetA[u]), make_uint2(aCode[0] | (aCode[1] << 16), aCode[2] | (aCode[3] << 16)));
+            }
         }
     }
 }
@@ -152,12 +202,13 @@ cudaError_t LaunchGray32(const Gray32Params& gp, size_t shared, int smCount, cud
             return e;
         }
     }
+    constexpr int kThreads = PQ ? kGrayTableThreads : kGrayClipThreads;
     const long long groups = static_cast<long long>(gp.groupsPerRow) * gp.rowCount;
-    long long blocks = (groups + kGrayThreads - 1) / kGrayThreads;
-    const long long cap = static_cast<long long>(smCount) * 2; // every CTA stages its own table: few, long-lived CTAs
+    long long blocks = (groups + kThreads - 1) / kThreads;
+    const long long cap = PQ ? static_cast<long long>(smCount) : static_cast<long long>(smCount) * 8; // a table per CTA: one long-lived CTA per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    EncodeGrayF32Kernel<CHANNELS, PQ><<<static_cast<unsigned>(blocks), kGrayThreads, shared, stream>>>(gp);
+    EncodeGrayF32Kernel<CHANNELS, PQ><<<static_cast<unsigned>(blocks), kThreads, shared, stream>>>(gp);
     return cudaGetLastError();
 }
 
@@ -201,11 +252,11 @@ int LaunchEncodeFastGray32(const EncodeParams& p, int hostDepth, void* streamHan
     gp.pqMultiplier = p.pqMultiplier;
     gp.maxCodeFloat = p.maxCodeFloat;
     gp.maxCode = static_cast<int32_t>(p.maxCode);
-    size_t shared = 768;
+    size_t shared = 768 + 16;
     if (pq)
     {
         gp.table = *p.curveTable;
-        shared += (static_cast<size_t>((gp.table.flatCount + 3) & ~3) + static_cast<size_t>(p.maxCode) + 2) * sizeof(uint32_t);
+        shared += gp.table.compactImageBytes;
         if (shared > 100 * 1024)
         {
             return 0;

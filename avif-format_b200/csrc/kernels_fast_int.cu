@@ -9,6 +9,7 @@
 //   RGB(A)16 -> planar YCbCr   the 16-bit -> N-bit mapping is evaluated arithmetically (it is four float
 //                              operations), the forward matrix and the 4:2:2 / 4:2:0 down-filter are fused, a
 //                              thread converts 8 pixels (x 2 rows for 4:2:0).
+#include "group_walk.cuh"
 #include "kernel_params.h"
 #include "../../include/avifgpu.h"
 
@@ -87,20 +88,19 @@ __global__ void __launch_bounds__(kLutThreads, 1) EncodeGray16LutKernel(const Gr
     __syncthreads();
 
     constexpr int kUnroll = 4;
-    const long long chunks = static_cast<long long>(p.chunksPerRow) * p.rowCount;
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; base < chunks; base += stride * kUnroll)
+    // the thread's chunks are first + n * stride, n = 0, 1, ...: four at a time so that four loads are in flight
+    GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.chunksPerRow, p.rowCount);
+    while (walk.Inside(p.rowCount))
     {
         uint4 in[kUnroll];
         long long outOffset[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
         {
-            const long long chunk = base + u * stride;
-            if (chunk < chunks)
+            if (walk.Inside(p.rowCount))
             {
-                const long long row = chunk / p.chunksPerRow;
-                const long long column = chunk - row * p.chunksPerRow;
+                const long long row = walk.row;
+                const long long column = walk.column;
                 in[u] = __ldcs(reinterpret_cast<const uint4*>(p.rows + row * p.rowStride + column * 16));
                 outOffset[u] = row * p.strideY + column * 16;
             }
@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) EncodeGray16LutKernel(const Gr
                 in[u] = make_uint4(0u, 0u, 0u, 0u);
                 outOffset[u] = -1;
             }
+            walk.Advance(p.rowCount);
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
@@ -258,12 +259,12 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
         }
         __syncthreads();
     }
-    const long long groups = static_cast<long long>(p.groupsPerRow) * ((p.rowCount + YS) >> YS);
-    for (long long group = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; group < groups;
-         group += static_cast<long long>(gridDim.x) * blockDim.x)
+    const int32_t rowPairs = (p.rowCount + YS) >> YS;
+    for (GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.groupsPerRow, rowPairs);
+         walk.Inside(rowPairs); walk.Advance(rowPairs))
     {
-        const long long rowPair = group / p.groupsPerRow;
-        const int column = static_cast<int>(group - rowPair * p.groupsPerRow); // in units of 8 pixels
+        const long long rowPair = walk.row;
+        const int column = walk.column; // in units of 8 pixels
         const long long y0 = rowPair << YS;
 
         uint32_t words[kRows][kWordsPerRow];
@@ -430,12 +431,11 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeGrayIntKernel(const Rgb16Pa
         }
         __syncthreads();
     }
-    const long long groups = static_cast<long long>(p.groupsPerRow) * p.rowCount;
-    for (long long group = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; group < groups;
-         group += static_cast<long long>(gridDim.x) * blockDim.x)
+    for (GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.groupsPerRow, p.rowCount);
+         walk.Inside(p.rowCount); walk.Advance(p.rowCount))
     {
-        const long long row = group / p.groupsPerRow;
-        const long long column = group - row * p.groupsPerRow;
+        const long long row = walk.row;
+        const long long column = walk.column;
         uint32_t words[kWordsPerRow];
         const uint8_t* source = p.rows + row * p.rowStride + column * (kWordsPerRow * 4);
 #pragma unroll

@@ -26,8 +26,13 @@ g = torch.Generator(device=dev)
 g.manual_seed(1)
 
 
+ONE_LAUNCH = os.environ.get("AVIFGPU_MEASURE_ONE_LAUNCH") == "1"  # under ncu: one warm launch, one measured launch per case
+
+
 def timed(fn, steps=30):
-    for _ in range(3):
+    if ONE_LAUNCH:
+        steps = 1
+    for _ in range(1 if ONE_LAUNCH else 3):
         fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
