@@ -358,6 +358,24 @@ AVIF_HD float PowfImpl(float x, float y, const LibmTables& t)
     return signBias ? -result : result;
 }
 
+// True when powf(x, y) may go through PowfModerateExponent for every x whose sign bit is clear.
+inline bool PowfExponentIsModerate(float y) { return y == y && y != 0.0f && (y < 0.0f ? -y : y) < 0.8f; }
+
+// powf(x, y) for an exponent the caller has checked once (PowfExponentIsModerate: finite, non-zero, |y| < 0.8) and a
+// base whose sign bit is clear -- the HLG OOTF's powf(luma, gamma - 1), gamma = 1.2 at 1000 nit.  For a normal x,
+// |log2 x| <= 128, so |y log2 x| < 102.4 and glibc's |y log2 x| >= 126 screen cannot fire; y needs no screening at all.
+// What is left is the main path of PowfImpl, operation for operation; x = 0, subnormal, inf and NaN take PowfImpl itself.
+AVIF_HD float PowfModerateExponent(float x, float y, const LibmTables& t)
+{
+    const uint32_t ix = AsUint(x);
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u)
+    {
+        return PowfImpl<true>(x, y, t);
+    }
+    const double ylogx = static_cast<double>(y) * Log2Inline(ix, t);
+    return Exp2Inline(ylogx, t);
+}
+
 AVIF_HD float Powf(float x, float y, const LibmTables& t) { return PowfImpl<false>(x, y, t); }
 
 // Powf for a base whose sign bit is known to be clear.

@@ -14,6 +14,7 @@
 //     +inf / NaN take the exact glibc-identical evaluation;
 //   * forward matrix, quantisation, chroma down-filter and stores: StoreTile (kernels_fast_common.cuh).
 #include "kernels_fast_common.cuh"
+#include "table_staging.cuh"
 #include "../../include/avifgpu.h"
 
 namespace avifgpu
@@ -21,6 +22,7 @@ namespace avifgpu
 
 using namespace avifpix;
 using namespace fastenc;
+using namespace staging;
 using avifmath::LibmTables;
 
 namespace
@@ -37,7 +39,6 @@ constexpr int kRowSegmentWords = kRowSegmentBytes / 4;
 constexpr int kSharedBarriers = 256;                     // kFlatWarps x 8 bytes, padded; the last slot is the table's barrier
 constexpr int kTableBarrierSlot = kSharedBarriers / 8 - 1;
 static_assert(kFlatWarps <= kTableBarrierSlot, "the warps' barriers and the table's share kSharedBarriers");
-constexpr uint32_t kTableCopyChunk = 16384;              // bytes per bulk copy of the table image
 constexpr int kSharedLimit = 227 * 1024;
 __host__ __device__ constexpr int FlatFixedBytes() { return kSharedLibm + kSharedBarriers + kFlatWarps * kStageBytesPerWarp; }
 
@@ -59,46 +60,12 @@ struct FlatSchedule
     int32_t scatter;
 };
 
-__device__ __forceinline__ uint32_t SharedAddress(const void* pointer) { return static_cast<uint32_t>(__cvta_generic_to_shared(pointer)); }
-
 // One lane of the (converged) warp.
 __device__ __forceinline__ bool ElectOne()
 {
     uint32_t elected;
     asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(elected));
     return elected != 0;
-}
-
-__device__ __forceinline__ void BarrierInit(uint32_t barrier, uint32_t arrivals)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barrier), "r"(arrivals) : "memory");
-}
-
-__device__ __forceinline__ void BarrierExpect(uint32_t barrier, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barrier), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void BulkCopyToShared(uint32_t target, const void* source, uint32_t bytes, uint32_t barrier)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(target), "l"(source), "r"(bytes),
-                 "r"(barrier)
-                 : "memory");
-}
-
-__device__ __forceinline__ void BarrierWait(uint32_t barrier, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred done;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n"
-        "@done bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(barrier),
-        "r"(parity)
-        : "memory");
 }
 
 // TWO_LEVEL = 0: the flat table (64-bit entries) + band bitmap.  TWO_LEVEL = 1: the per-binade two-level table (curves whose
@@ -161,27 +128,14 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     auto columnBytes = [&](int column) { return column == tilesX - 1 ? static_cast<uint32_t>(schedule.lastColumnBytes) : static_cast<uint32_t>(kRowSegmentBytes); };
     auto sourceOffsetOf = [&](int row, int column) { return static_cast<int64_t>(row) * 2 * p.rowStride + static_cast<int64_t>(column) * kRowSegmentBytes; };
 
-    const uint32_t tableBarrier = SharedAddress(barriers + kTableBarrierSlot);
     if (kCompact && threadIdx.x == 0)
     {
-        // The compact table and first_k are one image in global memory laid out like the shared one (curve_tables.h):
-        // the copy engine stages it while the warps set up; staging it with ordinary loads kept every SM busy for ~7 us
-        // of a ~100 us launch (148 CTAs walking the same 67 KB in step).
-        BarrierInit(tableBarrier, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t imageBytes = p.table.compactImageBytes;
-        BarrierExpect(tableBarrier, imageBytes);
-        const uint32_t target = SharedAddress(compactEntries);
-        const uint8_t* source = reinterpret_cast<const uint8_t*>(p.table.compact);
-        for (uint32_t offset = 0; offset < imageBytes; offset += kTableCopyChunk)
-        {
-            BulkCopyToShared(target + offset, source + offset, min(kTableCopyChunk, imageBytes - offset), tableBarrier);
-        }
+        BeginTableImageCopy(p.table, compactEntries, barriers + kTableBarrierSlot); // table_staging.cuh
     }
     if (ElectOne())
     {
         BarrierInit(barrier, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        BarrierInitFence();
         if (firstItem < schedule.items)
         {
             int column, rowBegin, rowEnd;
@@ -224,7 +178,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) EncodeRgbF32FlatKernel(const 
     __syncthreads(); // the libm tables, the barriers' initialisation
     if (kCompact)
     {
-        BarrierWait(tableBarrier, 0);
+        WaitTableImage(barriers + kTableBarrierSlot);
     }
 
     const uint32_t flatShift = p.table.flatShift;

@@ -7,6 +7,7 @@
 // evaluation), the clip transfer is the quantiser alone.  4 + 2 (or 8 + 4) bytes per pixel: HBM-bound.
 #include "group_walk.cuh"
 #include "kernels_fast_common.cuh"
+#include "table_staging.cuh"
 #include "../../include/avifgpu.h"
 
 namespace avifgpu
@@ -39,8 +40,6 @@ struct Gray32Params
     CurveTableView table;
 };
 
-__device__ __forceinline__ uint32_t SharedAddressOf(const void* pointer) { return static_cast<uint32_t>(__cvta_generic_to_shared(pointer)); }
-
 // CHANNELS 1 (Gray) or 2 (Gray + alpha); PQ = 1: LinearToPQ through the compact table, 0: clip.
 template <int CHANNELS, int PQ>
 __global__ void __launch_bounds__(PQ ? kGrayTableThreads : kGrayClipThreads) EncodeGrayF32Kernel(const Gray32Params p)
@@ -52,37 +51,13 @@ __global__ void __launch_bounds__(PQ ? kGrayTableThreads : kGrayClipThreads) Enc
     const uint32_t* firstBits = compactEntries + ((p.table.flatCount + 3) & ~3);
     if (PQ && threadIdx.x == 0)
     {
-        // the table image (compact entries + first_k, curve_tables.h) goes through the copy engine
-        const uint32_t barrier = SharedAddressOf(tableBarrierStorage);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barrier), "r"(1) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t imageBytes = p.table.compactImageBytes;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barrier), "r"(imageBytes) : "memory");
-        const uint32_t target = SharedAddressOf(compactEntries);
-        const uint8_t* source = reinterpret_cast<const uint8_t*>(p.table.compact);
-        for (uint32_t offset = 0; offset < imageBytes; offset += 16384u)
-        {
-            const uint32_t bytes = min(16384u, imageBytes - offset);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(target + offset),
-                         "l"(source + offset), "r"(bytes), "r"(barrier)
-                         : "memory");
-        }
+        staging::BeginTableImageCopy(p.table, compactEntries, tableBarrierStorage); // table_staging.cuh
     }
     const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
     __syncthreads();
     if (PQ)
     {
-        const uint32_t barrier = SharedAddressOf(tableBarrierStorage);
-        asm volatile(
-            "{\n"
-            ".reg .pred done;\n"
-            "TABLE_WAIT:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], 0;\n"
-            "@done bra TABLE_READY;\n"
-            "bra TABLE_WAIT;\n"
-            "TABLE_READY:\n"
-            "}\n" ::"r"(barrier)
-            : "memory");
+        staging::WaitTableImage(tableBarrierStorage);
     }
 
     const uint32_t shift = p.table.flatShift;

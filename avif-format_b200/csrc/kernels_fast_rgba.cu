@@ -7,6 +7,7 @@
 // each, issued one tile ahead) and only the 24 colour samples of a lane -- after the clamp / premultiplication, the
 // values the curve actually sees -- are parked in shared memory for the band-bitmap probes.  One CTA of 16 warps per SM.
 #include "kernels_fast_common.cuh"
+#include "table_staging.cuh"
 #include "../../include/avifgpu.h"
 
 namespace avifgpu
@@ -24,7 +25,8 @@ constexpr int kRgbaThreads = kRgbaWarps * 32;
 constexpr int kLaneStrideWords = 28; // 24 colour samples + padding: 16-byte aligned, conflict-free for STS.128
 constexpr int kStagePerWarp = 32 * kLaneStrideWords * 4;
 constexpr int kSharedLimit = 227 * 1024;
-__host__ __device__ constexpr int RgbaFixedBytes() { return kSharedLibm + kRgbaWarps * kStagePerWarp; }
+constexpr int kTableBarrierBytes = 16; // the table image's mbarrier, padded
+__host__ __device__ constexpr int RgbaFixedBytes() { return kSharedLibm + kTableBarrierBytes + kRgbaWarps * kStagePerWarp; }
 
 // COMPACT = 1: compact table + first_k array in shared memory (kernels_fast_flat.cu has the commentary).
 template <int CURVE, int XS, int YS, int COMPACT>
@@ -32,28 +34,18 @@ __global__ void __launch_bounds__(kRgbaThreads, 1) EncodeRgbaF32FlatKernel(const
 {
     extern __shared__ __align__(16) uint8_t sharedBytes[];
     uint64_t* libmStorage = reinterpret_cast<uint64_t*>(sharedBytes);
-    uint32_t* stageAll = reinterpret_cast<uint32_t*>(sharedBytes + kSharedLibm);
+    uint64_t* tableBarrier = reinterpret_cast<uint64_t*>(sharedBytes + kSharedLibm);
+    uint32_t* stageAll = reinterpret_cast<uint32_t*>(sharedBytes + kSharedLibm + kTableBarrierBytes);
     uint2* flatEntries = reinterpret_cast<uint2*>(sharedBytes + RgbaFixedBytes());
     uint32_t* compactEntries = reinterpret_cast<uint32_t*>(sharedBytes + RgbaFixedBytes());
-    uint32_t* firstBits = compactEntries + ((p.table.flatCount + 3) & ~3);
+    const uint32_t* firstBits = compactEntries + ((p.table.flatCount + 3) & ~3);
 
-    const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
-    if (COMPACT)
+    if (COMPACT && threadIdx.x == 0)
     {
-        const uint4* source = reinterpret_cast<const uint4*>(p.table.compact);
-        uint4* target = reinterpret_cast<uint4*>(compactEntries);
-        const int quads = (p.table.flatCount + 3) / 4;
-#pragma unroll 8
-        for (int i = threadIdx.x; i < quads; i += blockDim.x)
-        {
-            target[i] = __ldg(source + i);
-        }
-        for (int i = threadIdx.x; i <= p.maxCode + 1; i += blockDim.x)
-        {
-            firstBits[i] = p.table.firstBits[i];
-        }
+        staging::BeginTableImageCopy(p.table, compactEntries, tableBarrier); // table_staging.cuh
     }
-    else
+    const LibmTables t = avifmath::StageLibmTables(libmStorage, threadIdx.x, blockDim.x);
+    if (!COMPACT)
     {
         const uint4* source = reinterpret_cast<const uint4*>(p.table.flat);
         uint4* target = reinterpret_cast<uint4*>(flatEntries);
@@ -64,7 +56,7 @@ __global__ void __launch_bounds__(kRgbaThreads, 1) EncodeRgbaF32FlatKernel(const
             target[i] = __ldg(source + i);
         }
     }
-    __syncthreads();
+    __syncthreads(); // the libm tables, the table barrier's initialisation
 
     const int lane = threadIdx.x & 31;
     const int warpInBlock = threadIdx.x >> 5;
@@ -105,7 +97,11 @@ __global__ void __launch_bounds__(kRgbaThreads, 1) EncodeRgbaF32FlatKernel(const
             raw[4 + q] = second ? __ldg(reinterpret_cast<const uint4*>(r1 + 16 * q)) : zero;
         }
     };
-    loadTile(tileRow, tileX, firstTile < tileCount);
+    loadTile(tileRow, tileX, firstTile < tileCount); // in flight while the table image lands
+    if (COMPACT)
+    {
+        staging::WaitTableImage(tableBarrier);
+    }
 
 #pragma unroll 1
     for (int tile = firstTile; tile < tileCount; tile += warpCount)
@@ -253,8 +249,7 @@ __global__ void __launch_bounds__(kRgbaThreads, 1) EncodeRgbaF32FlatKernel(const
 
 size_t RgbaTableBytes(const FastEncodeParams& fp, bool compact)
 {
-    return compact ? (static_cast<size_t>((fp.table.flatCount + 3) & ~3) + static_cast<size_t>(fp.maxCode) + 2) * sizeof(uint32_t)
-                   : static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
+    return compact ? static_cast<size_t>(fp.table.compactImageBytes) : static_cast<size_t>((fp.table.flatCount + 1) / 2) * sizeof(uint4);
 }
 
 template <int CURVE, int XS, int YS, int COMPACT>
