@@ -406,6 +406,18 @@ __global__ void __launch_bounds__(kStreamThreads) StreamDecodeKernel(const Strea
         }
         __syncthreads();
     }
+    // An 8-bit full-range monochrome image read by an 8-bit host: the table maps every code to itself (checked, not
+    // assumed) and the kernel is a strided copy -- eight shared-memory look-ups per 8 bytes otherwise bound it.
+    bool identityLuma = false;
+    if (MONO && kHost8)
+    {
+        bool mine = true;
+        for (uint32_t i = threadIdx.x; i <= p.maxCode; i += blockDim.x)
+        {
+            mine = mine && lutY[i] == i;
+        }
+        identityLuma = __syncthreads_and(mine ? 1 : 0) != 0;
+    }
     // source planes: mono -> Y (, A at index 3); RGB -> R, G, B (, A)
     constexpr int kColours = MONO ? 1 : 3;
     constexpr bool kAlpha = CHANNELS > kColours;
@@ -434,7 +446,10 @@ __global__ void __launch_bounds__(kStreamThreads) StreamDecodeKernel(const Strea
                     const bool isAlpha = kAlpha && c == CHANNELS - 1;
                     if (!isAlpha)
                     {
-                        v = lutY[kHost8 ? v : min(v, p.maxCode)];
+                        if (!(kHost8 && identityLuma))
+                        {
+                            v = lutY[kHost8 ? v : min(v, p.maxCode)];
+                        }
                     }
                     else if (!kHost8)
                     {

@@ -65,28 +65,6 @@ __global__ void __launch_bounds__(PQ ? kGrayTableThreads : kGrayClipThreads) Enc
     const int32_t span = static_cast<int32_t>(p.table.flatHigh - p.table.flatLow);
     const uint32_t topShift = 32u - shift;
 
-    const auto curveCode = [&](float value) -> uint32_t
-    {
-        if (!PQ)
-        {
-            return FloatToCode(value, p.maxCodeFloat);
-        }
-        const uint32_t bits = __float_as_uint(value);
-        if (static_cast<int32_t>(bits) > 0x7f7fffff)
-        {
-            return ExactCurveCode<kCurveLinearToPQ>(value, p.pqMultiplier, p.maxCodeFloat, t); // +inf / NaN
-        }
-        bool inBand;
-        uint32_t entry;
-        uint32_t code = static_cast<uint32_t>(LookupCurveCompact<0>(bits, compactEntries, shift, negativeLow, span, topShift, p.table.compactCodeMask,
-                                                                    p.table.compactMagic, inBand, entry));
-        if (inBand)
-        {
-            code = ResolveCompactInBand(bits, entry, code, topShift, p.table.compactCodeMask, firstBits, p.table.bandBits, p.table.bandStrideLog2);
-        }
-        return code;
-    };
-
     GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.groupsPerRow, p.rowCount);
     while (walk.Inside(p.rowCount))
     {
@@ -97,6 +75,11 @@ __global__ void __launch_bounds__(PQ ? kGrayTableThreads : kGrayClipThreads) Enc
         {
             planeOffsetY[u] = -1;
             planeOffsetA[u] = 0;
+#pragma unroll
+            for (int c = 0; c < CHANNELS; ++c)
+            {
+                loaded[u][c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
             if (walk.Inside(p.rowCount))
             {
                 const long long row = walk.row;
@@ -112,13 +95,13 @@ __global__ void __launch_bounds__(PQ ? kGrayTableThreads : kGrayClipThreads) Enc
             }
             walk.Advance(p.rowCount);
         }
+        // ---- the values the curve sees, the alpha codes ---------------------------------------------------------------
+        constexpr int kSamples = 4 * kGroupsInFlight;
+        float value[kSamples];
+        uint32_t aCode[kSamples];
 #pragma unroll
         for (int u = 0; u < kGroupsInFlight; ++u)
         {
-            if (planeOffsetY[u] < 0)
-            {
-                continue;
-            }
             float gray[4], alpha[4];
             if (CHANNELS == 1)
             {
@@ -131,31 +114,108 @@ __global__ void __launch_bounds__(PQ ? kGrayTableThreads : kGrayClipThreads) Enc
                 gray[0] = a.x; alpha[0] = a.y; gray[1] = a.z; alpha[1] = a.w;
                 gray[2] = b.x; alpha[2] = b.y; gray[3] = b.z; alpha[3] = b.w;
             }
-            uint32_t yCode[4], aCode[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
             {
-                float value = gray[i];
+                float v = gray[i];
                 if (CHANNELS == 2)
                 {
                     // WriteHeifImage.cpp:556-575
                     const float a = ClampF(alpha[i], 0.0f, 1.0f);
                     if (p.premultiply && a < 1.0f)
                     {
-                        value = (a == 0) ? 0.0f : PremultiplyColor(ClampF(value, 0.0f, 1.0f), a, 1.0f);
+                        v = (a == 0) ? 0.0f : PremultiplyColor(ClampF(v, 0.0f, 1.0f), a, 1.0f);
                     }
-                    aCode[i] = FloatToCode(a, p.maxCodeFloat);
+                    aCode[4 * u + i] = FloatToCode(a, p.maxCodeFloat);
                 }
                 else
                 {
-                    value = ClampF(value, 0.0f, 1.0f); // WriteHeifImage.cpp:602
+                    v = ClampF(v, 0.0f, 1.0f); // WriteHeifImage.cpp:602
                 }
-                yCode[i] = curveCode(value);
+                value[4 * u + i] = v; // a group past the image was loaded as zeros
             }
-            __stcs(reinterpret_cast<uint2*>(p.planeY + planeOffsetY[u]), make_uint2(yCode[0] | (yCode[1] << 16), yCode[2] | (yCode[3] << 16)));
+        }
+
+        // ---- float -> code: all look-ups first, then the few flagged samples, then +inf / NaN ------------------------------
+        uint32_t yCode[kSamples];
+        if (!PQ)
+        {
+#pragma unroll
+            for (int j = 0; j < kSamples; ++j)
+            {
+                yCode[j] = FloatToCode(value[j], p.maxCodeFloat);
+            }
+        }
+        else
+        {
+            uint32_t flagged = 0;
+            int32_t largest = 0;
+#pragma unroll
+            for (int j = 0; j < kSamples; ++j)
+            {
+                const uint32_t bits = __float_as_uint(value[j]);
+                bool inBand;
+                uint32_t entry;
+                yCode[j] = static_cast<uint32_t>(LookupCurveCompact<0>(bits, compactEntries, shift, negativeLow, span, topShift, p.table.compactCodeMask,
+                                                                       p.table.compactMagic, inBand, entry));
+                flagged |= inBand ? (1u << j) : 0u;
+                largest = max(largest, static_cast<int32_t>(bits));
+            }
+            uint32_t lower = 0; // samples whose exact code is one below the table's
+            while (flagged != 0)
+            {
+                const int j = __ffs(static_cast<int>(flagged)) - 1;
+                flagged &= flagged - 1;
+                uint32_t bits = __float_as_uint(value[0]);
+#pragma unroll
+                for (int k = 1; k < kSamples; ++k)
+                {
+                    bits = (j == k) ? __float_as_uint(value[k]) : bits;
+                }
+                // the sample's step and its distance from first_k, then one bit of the band bitmap (curve_lookup.cuh ResolveCompactInBand)
+                const int32_t bucket = __viaddmin_s32_relu(static_cast<int32_t>(bits) >> shift, negativeLow, span);
+                const uint32_t entry = compactEntries[bucket];
+                const uint32_t step = ((entry & p.table.compactCodeMask) >> kCompactLenBits) + ((entry >> topShift) != 0 ? 1u : 0u);
+                const uint32_t distance = bits - firstBits[step];
+                if (step != 0 && distance < (1u << p.table.bandStrideLog2))
+                {
+                    const uint32_t index = (step << p.table.bandStrideLog2) + distance;
+                    const uint32_t word = __ldg(p.table.bandBits + (index >> 5));
+                    // step or step - 1; the table said field + carry, which is `step` whenever bits >= first_k
+                    lower |= ((word >> (index & 31u)) & 1u) ? 0u : (1u << j);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kSamples; ++j)
+            {
+                yCode[j] -= (lower >> j) & 1u;
+            }
+            if (largest > 0x7f7fffff)
+            {
+#pragma unroll
+                for (int j = 0; j < kSamples; ++j)
+                {
+                    if (static_cast<int32_t>(__float_as_uint(value[j])) > 0x7f7fffff)
+                    {
+                        yCode[j] = ExactCurveCode<kCurveLinearToPQ>(value[j], p.pqMultiplier, p.maxCodeFloat, t); // +inf / NaN
+                    }
+                }
+            }
+        }
+
+#pragma unroll
+        for (int u = 0; u < kGroupsInFlight; ++u)
+        {
+            if (planeOffsetY[u] < 0)
+            {
+                continue;
+            }
+            __stcs(reinterpret_cast<uint2*>(p.planeY + planeOffsetY[u]),
+                   make_uint2(yCode[4 * u] | (yCode[4 * u + 1] << 16), yCode[4 * u + 2] | (yCode[4 * u + 3] << 16)));
             if (CHANNELS == 2)
             {
-                __stcs(reinterpret_cast<uint2*>(p.planeA + planeOffsetA[u]), make_uint2(aCode[0] | (aCode[1] << 16), aCode[2] | (aCode[3] << 16)));
+                __stcs(reinterpret_cast<uint2*>(p.planeA + planeOffsetA[u]),
+                       make_uint2(aCode[4 * u] | (aCode[4 * u + 1] << 16), aCode[4 * u + 2] | (aCode[4 * u + 3] << 16)));
             }
         }
     }

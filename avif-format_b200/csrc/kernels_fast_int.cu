@@ -88,19 +88,22 @@ __global__ void __launch_bounds__(kLutThreads, 1) EncodeGray16LutKernel(const Gr
     __syncthreads();
 
     constexpr int kUnroll = 4;
-    // the thread's chunks are first + n * stride, n = 0, 1, ...: four at a time so that four loads are in flight
-    GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.chunksPerRow, p.rowCount);
-    while (walk.Inside(p.rowCount))
+    const long long chunks = static_cast<long long>(p.chunksPerRow) * p.rowCount;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    // (measured: walking row / column incrementally, group_walk.cuh, makes THIS loop slower -- 0.86 vs 0.95 of the HBM
+    // peak; the division is hidden under four loads in flight and a 16-bit look-up per sample)
+    for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; base < chunks; base += stride * kUnroll)
     {
         uint4 in[kUnroll];
         long long outOffset[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
         {
-            if (walk.Inside(p.rowCount))
+            const long long chunk = base + u * stride;
+            if (chunk < chunks)
             {
-                const long long row = walk.row;
-                const long long column = walk.column;
+                const long long row = chunk / p.chunksPerRow;
+                const long long column = chunk - row * p.chunksPerRow;
                 in[u] = __ldcs(reinterpret_cast<const uint4*>(p.rows + row * p.rowStride + column * 16));
                 outOffset[u] = row * p.strideY + column * 16;
             }
@@ -109,7 +112,6 @@ __global__ void __launch_bounds__(kLutThreads, 1) EncodeGray16LutKernel(const Gr
                 in[u] = make_uint4(0u, 0u, 0u, 0u);
                 outOffset[u] = -1;
             }
-            walk.Advance(p.rowCount);
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)

@@ -57,10 +57,10 @@ AVIF_HD float PQToLinear(float value, float luminanceMultiplier, const LibmTable
         return 0.0f;
     }
     // 1 / m2 = 0.0127: no exponent screens (PowfModerateExponent); a -0.0 or NaN base takes the full function inside it.
-    // The second base is MaxF(.., +0) over a positive denominator: its sign bit is clear.
+    // The second base can be negative (value above ~2: the denominator changes sign) and its exponent is 6.3: the full powf.
     const float x = avifmath::PowfModerateExponent(value, PqConstants::inv_m2, t);
     const float normalizedLinear =
-        avifmath::PowfOfNonNegative(MaxF(x - PqConstants::c1, 0.0f) / (PqConstants::c2 - PqConstants::c3 * x), PqConstants::inv_m1, t);
+        avifmath::Powf(MaxF(x - PqConstants::c1, 0.0f) / (PqConstants::c2 - PqConstants::c3 * x), PqConstants::inv_m1, t);
     return normalizedLinear * luminanceMultiplier;
 }
 
