@@ -20,7 +20,10 @@ using avifmath::LibmTables;
 namespace
 {
 
-constexpr int kRgbaWarps = 16;
+#ifndef AVIF_RGBA_WARPS
+#define AVIF_RGBA_WARPS 16
+#endif
+constexpr int kRgbaWarps = AVIF_RGBA_WARPS;
 constexpr int kRgbaThreads = kRgbaWarps * 32;
 constexpr int kLaneStrideWords = 28; // 24 colour samples + padding: 16-byte aligned, conflict-free for STS.128
 constexpr int kStagePerWarp = 32 * kLaneStrideWords * 4;
