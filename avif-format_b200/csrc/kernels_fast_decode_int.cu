@@ -425,37 +425,9 @@ __global__ void __launch_bounds__(kStreamThreads) StreamDecodeKernel(const Strea
     // before it converts the first (ncu: 2048 threads x 8 bytes per SM in flight is too little; planar RGB8 +4 %).  With
     // 16-byte groups one at a time is better (two in flight cost registers and occupancy: planar RGB 10-bit -12 %).
     constexpr int kInFlight = kHost8 ? 4 : 1;
-    GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.groupsPerRow, p.rowCount);
-    while (walk.Inside(p.rowCount))
+    // one group: 8 samples per plane -> 8 host pixels at `target`
+    const auto convertGroup = [&](const Raw8<SampleT>(&raw)[CHANNELS], uint8_t* target)
     {
-        Raw8<SampleT> rawAll[kInFlight][CHANNELS];
-        long long targetOffset[kInFlight];
-#pragma unroll
-        for (int u = 0; u < kInFlight; ++u)
-        {
-            targetOffset[u] = -1;
-            if (walk.Inside(p.rowCount))
-            {
-                const long long row = walk.row;
-                const long long column = static_cast<long long>(walk.column) * 8;
-#pragma unroll
-                for (int c = 0; c < CHANNELS; ++c)
-                {
-                    const int planeIndex = (kAlpha && c == CHANNELS - 1) ? 3 : c;
-                    rawAll[u][c] = LoadEight<SampleT>(p.plane[planeIndex] + row * p.planeStride[planeIndex] + column * static_cast<long long>(sizeof(SampleT)));
-                }
-                targetOffset[u] = row * p.rowStride + column * static_cast<long long>(CHANNELS * sizeof(SampleT));
-            }
-            walk.Advance(p.rowCount);
-        }
-#pragma unroll
-        for (int u = 0; u < kInFlight; ++u)
-        {
-        if (targetOffset[u] < 0)
-        {
-            continue;
-        }
-        const Raw8<SampleT>(&raw)[CHANNELS] = rawAll[u];
         uint32_t samples[8 * CHANNELS];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -500,7 +472,6 @@ __global__ void __launch_bounds__(kStreamThreads) StreamDecodeKernel(const Strea
                 words[w] = samples[2 * w] | (samples[2 * w + 1] << 16);
             }
         }
-        uint8_t* target = p.rows + targetOffset[u];
         if (kWords % 4 == 0)
         {
 #pragma unroll
@@ -517,6 +488,53 @@ __global__ void __launch_bounds__(kStreamThreads) StreamDecodeKernel(const Strea
                 __stcs(reinterpret_cast<uint2*>(target) + q, make_uint2(words[2 * q], words[2 * q + 1]));
             }
         }
+    };
+    const auto loadGroup = [&](Raw8<SampleT>(&raw)[CHANNELS], long long row, long long column)
+    {
+#pragma unroll
+        for (int c = 0; c < CHANNELS; ++c)
+        {
+            const int planeIndex = (kAlpha && c == CHANNELS - 1) ? 3 : c;
+            raw[c] = LoadEight<SampleT>(p.plane[planeIndex] + row * p.planeStride[planeIndex] + column * static_cast<long long>(sizeof(SampleT)));
+        }
+    };
+    GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.groupsPerRow, p.rowCount);
+    if (kInFlight == 1)
+    {
+        for (; walk.Inside(p.rowCount); walk.Advance(p.rowCount))
+        {
+            const long long row = walk.row;
+            const long long column = static_cast<long long>(walk.column) * 8;
+            Raw8<SampleT> raw[CHANNELS];
+            loadGroup(raw, row, column);
+            convertGroup(raw, p.rows + row * p.rowStride + column * static_cast<long long>(CHANNELS * sizeof(SampleT)));
+        }
+        return;
+    }
+    while (walk.Inside(p.rowCount))
+    {
+        Raw8<SampleT> rawAll[kInFlight][CHANNELS];
+        long long targetOffset[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u)
+        {
+            targetOffset[u] = -1;
+            if (walk.Inside(p.rowCount))
+            {
+                const long long row = walk.row;
+                const long long column = static_cast<long long>(walk.column) * 8;
+                loadGroup(rawAll[u], row, column);
+                targetOffset[u] = row * p.rowStride + column * static_cast<long long>(CHANNELS * sizeof(SampleT));
+            }
+            walk.Advance(p.rowCount);
+        }
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u)
+        {
+            if (targetOffset[u] >= 0)
+            {
+                convertGroup(rawAll[u], p.rows + targetOffset[u]);
+            }
         }
     }
 }

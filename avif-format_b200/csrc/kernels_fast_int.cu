@@ -127,7 +127,6 @@ __global__ void __launch_bounds__(kLutThreads, 1) EncodeGray16LutKernel(const Gr
 // ---- RGB(A)16 -> planar YCbCr ---------------------------------------------------------------------------------------
 
 constexpr int kRgbThreads = 256;
-constexpr int kLutCopies = 32; // one per shared-memory bank
 constexpr float kTwo23 = 8388608.0f;
 
 // (float)v for v < 2^23 without the conversion instruction.
@@ -210,7 +209,7 @@ __device__ __forceinline__ float SampleToBiasedCode(uint32_t v, const Rgb16Param
     {
         return __uint_as_float(0x4b000000u | v);
     }
-    return hostLut[v << 5]; // the lane's own copy (kLutCopies): conflict-free whatever the 32 samples are
+    return hostLut[v];
 }
 
 __device__ __forceinline__ uint32_t BiasedToCode(float biased) { return __float_as_uint(biased) & 0x7fffffu; }
@@ -253,19 +252,17 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
     constexpr int kWordsPerRow = CHANNELS * 2 * static_cast<int>(sizeof(HostT)); // 8 pixels x CHANNELS samples / 4 bytes
     constexpr int kVectorWords = (kWordsPerRow % 4 == 0) ? 4 : 2;                 // 128-bit loads where the row chunk allows
     constexpr int kPlaneBytes = static_cast<int>(sizeof(PlaneT));
-    // 8-bit host into a deeper image: the 256 codes, one copy per shared-memory bank (entry v of lane L at [v * 32 + L]).
-    // A warp's 32 random bytes hit 32 different banks; with a single copy the look-up was 3-4 wavefronts and the kernel
-    // sat at 92 % of the shared-memory pipe (profiles/r2_other_kernels_ncu.md).
-    __shared__ float hostLutStorage[(sizeof(HostT) == 1 && sizeof(PlaneT) == 2) ? 256 * kLutCopies : 1];
+    // (one copy: a copy per shared-memory bank makes the look-up conflict-free but costs every CTA 32 KB and 8192 table
+    // entries to fill -- measured slower, 724 -> 694 Gpx/s for RGB8 -> 10-bit 4:2:0 and 1711 -> 1377 for Gray8 -> 10-bit)
+    __shared__ float hostLut[(sizeof(HostT) == 1 && sizeof(PlaneT) == 2) ? 256 : 1];
     if (sizeof(HostT) == 1 && sizeof(PlaneT) == 2)
     {
-        for (uint32_t i = threadIdx.x; i < 256u * kLutCopies; i += blockDim.x)
+        for (uint32_t v = threadIdx.x; v < 256; v += blockDim.x)
         {
-            hostLutStorage[i] = __uint_as_float(0x4b000000u | DepthLutEntry(i / kLutCopies, 255.0f, p.maxCode));
+            hostLut[v] = __uint_as_float(0x4b000000u | DepthLutEntry(v, 255.0f, p.maxCode));
         }
         __syncthreads();
     }
-    const float* hostLut = hostLutStorage + ((sizeof(HostT) == 1 && sizeof(PlaneT) == 2) ? (threadIdx.x & 31) : 0);
     const int32_t rowPairs = (p.rowCount + YS) >> YS;
     for (GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.groupsPerRow, rowPairs);
          walk.Inside(rowPairs); walk.Advance(rowPairs))
@@ -429,19 +426,15 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeGrayIntKernel(const Rgb16Pa
     constexpr int kWordsPerRow = CHANNELS * 2 * static_cast<int>(sizeof(HostT)); // 8 pixels x CHANNELS samples / 4 bytes
     constexpr int kVectorWords = (kWordsPerRow % 4 == 0) ? 4 : 2;
     constexpr int kPlaneBytes = static_cast<int>(sizeof(PlaneT));
-    // 8-bit host into a deeper image: the 256 codes, one copy per shared-memory bank (entry v of lane L at [v * 32 + L]).
-    // A warp's 32 random bytes hit 32 different banks; with a single copy the look-up was 3-4 wavefronts and the kernel
-    // sat at 92 % of the shared-memory pipe (profiles/r2_other_kernels_ncu.md).
-    __shared__ float hostLutStorage[(sizeof(HostT) == 1 && sizeof(PlaneT) == 2) ? 256 * kLutCopies : 1];
+    __shared__ float hostLut[(sizeof(HostT) == 1 && sizeof(PlaneT) == 2) ? 256 : 1];
     if (sizeof(HostT) == 1 && sizeof(PlaneT) == 2)
     {
-        for (uint32_t i = threadIdx.x; i < 256u * kLutCopies; i += blockDim.x)
+        for (uint32_t v = threadIdx.x; v < 256; v += blockDim.x)
         {
-            hostLutStorage[i] = __uint_as_float(0x4b000000u | DepthLutEntry(i / kLutCopies, 255.0f, p.maxCode));
+            hostLut[v] = __uint_as_float(0x4b000000u | DepthLutEntry(v, 255.0f, p.maxCode));
         }
         __syncthreads();
     }
-    const float* hostLut = hostLutStorage + ((sizeof(HostT) == 1 && sizeof(PlaneT) == 2) ? (threadIdx.x & 31) : 0);
     for (GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.groupsPerRow, p.rowCount);
          walk.Inside(p.rowCount); walk.Advance(p.rowCount))
     {

@@ -27,6 +27,11 @@ g.manual_seed(1)
 
 
 ONE_LAUNCH = os.environ.get("AVIFGPU_MEASURE_ONE_LAUNCH") == "1"  # under ncu: one warm launch, one measured launch per case
+ONLY = os.environ.get("AVIFGPU_MEASURE_ONLY")  # run only the cases whose name contains this text
+
+
+def wanted(name):
+    return ONLY is None or ONLY in name
 
 
 def timed(fn, steps=30):
@@ -45,6 +50,8 @@ def timed(fn, steps=30):
 
 
 def decode_case(name, bit_depth, host_depth, chroma, nclx, bytes_per_px, alpha=False):
+    if not wanted(name):
+        return
     H = H8 if bit_depth == 8 else globals()["H"]
     desc = abi.DecodeDesc(W, H, abi.COLORSPACE_YCBCR, chroma, bit_depth, abi.ALPHA_STRAIGHT if alpha else abi.ALPHA_NONE, host_depth, nclx)
     shapes = abi.decode_plane_shapes(desc)
@@ -66,6 +73,8 @@ def decode_case(name, bit_depth, host_depth, chroma, nclx, bytes_per_px, alpha=F
 
 
 def encode_case(name, host_depth, channels, image_depth, chroma, nclx, bytes_per_px, alpha=abi.ALPHA_NONE):
+    if not wanted(name):
+        return
     H = H8 if host_depth == 8 else globals()["H"]
     desc = abi.EncodeDesc(W, H, host_depth, channels, alpha, image_depth, abi.TRANSFER_CLIP, 80, abi.LAYOUT_PLANAR_YCBCR, chroma,
                           abi.DOWN_FILTER_BOX, abi.GRAY16_LUT, nclx)
@@ -90,6 +99,8 @@ def encode_case(name, host_depth, channels, image_depth, chroma, nclx, bytes_per
 
 
 def float_encode_case(name, channels, layout, bytes_per_px, tables, depth=12, peak=80, transfer=abi.TRANSFER_PQ):
+    if not wanted(name):
+        return
     alpha = abi.ALPHA_STRAIGHT if channels in (2, 4) else abi.ALPHA_NONE
     nclx = abi.Nclx(1, abi.PRIMARIES_BT2020, abi.TRANSFER_CHAR_PQ, abi.MATRIX_BT2020_NCL, 1)
     desc = abi.EncodeDesc(W, H, 32, channels, alpha, depth, transfer, peak, layout, abi.CHROMA_420 if layout == abi.LAYOUT_PLANAR_YCBCR else abi.CHROMA_444,
@@ -129,6 +140,8 @@ def mono_rgb_cases():
                                                          ("decode mono 10-bit -> Gray16 (a16)", abi.COLORSPACE_MONOCHROME, 10, 16, 4),
                                                          ("decode planar RGB 8-bit -> RGB8 (a18)", abi.COLORSPACE_RGB, 8, 8, 6),
                                                          ("decode planar RGB 10-bit -> RGB16 (a18)", abi.COLORSPACE_RGB, 10, 16, 12)):
+        if not wanted(name):
+            continue
         H = H8 if bit_depth == 8 else globals()["H"]
         desc = abi.DecodeDesc(W, H, colorspace, abi.CHROMA_444, bit_depth, abi.ALPHA_NONE, host_depth, abi.Nclx(1, 1, 13, 0 if colorspace == abi.COLORSPACE_RGB else 6, 1))
         shapes = abi.decode_plane_shapes(desc)
@@ -148,6 +161,8 @@ def mono_rgb_cases():
         ms = timed(run)
         print(json.dumps({"case": name, "ms": ms, "gpx_s": W * H / ms / 1e6, "gb_s": W * H * bpp / ms / 1e6}))
     for name, host_depth, depth, bpp in (("encode Gray8 -> 8-bit Y (a4)", 8, 8, 2), ("encode Gray8 -> 10-bit Y (a4)", 8, 10, 3)):
+        if not wanted(name):
+            continue
         H = H8
         desc = abi.EncodeDesc(W, H, host_depth, 1, abi.ALPHA_NONE, depth)
         shapes = abi.encode_plane_shapes(desc)
@@ -173,6 +188,8 @@ def float_decode_table_cases():
     for name, colorspace, nclx, ootf, bpp in (("decode planar RGB 10-bit PQ -> RGB32f (a18)", abi.COLORSPACE_RGB, pq, 0, 6 + 12),
                                               ("decode planar RGB 10-bit HLG + OOTF -> RGB32f (a18)", abi.COLORSPACE_RGB, hlg, 1, 6 + 12),
                                               ("decode mono 12-bit PQ -> Gray32f (a16)", abi.COLORSPACE_MONOCHROME, pq, 0, 2 + 4)):
+        if not wanted(name):
+            continue
         depth = 12 if colorspace == abi.COLORSPACE_MONOCHROME else 10
         desc = abi.DecodeDesc(W, H, colorspace, abi.CHROMA_444 if colorspace == abi.COLORSPACE_RGB else abi.CHROMA_MONOCHROME, depth, abi.ALPHA_NONE, 32, nclx,
                               hlg_apply_ootf=ootf)
