@@ -144,10 +144,17 @@ cudaError_t LaunchTable(const TableDecodeParams& tp, int smCount, cudaStream_t s
 {
     const long long groups = static_cast<long long>(tp.groupsPerRow) * tp.rowCount;
     long long blocks = (groups + kTableThreads - 1) / kTableThreads;
-    const long long cap = static_cast<long long>(smCount) * 4; // each CTA pays for its own table: keep them few and long-lived
+    const size_t shared = 768 + (ALPHA ? 2 : 1) * sizeof(float) * (static_cast<size_t>(1) << tp.bitDepth);
+    // each CTA pays for its own table: exactly as many as are resident at once (4 at 52 registers, 8 at 32), long-lived
+    int residentPerSm = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&residentPerSm, TableDecodeF32Kernel<COLOURS, ALPHA>, kTableThreads, shared) != cudaSuccess || residentPerSm < 1)
+    {
+        (void)cudaGetLastError();
+        residentPerSm = 4;
+    }
+    const long long cap = static_cast<long long>(smCount) * residentPerSm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    const size_t shared = 768 + (ALPHA ? 2 : 1) * sizeof(float) * (static_cast<size_t>(1) << tp.bitDepth);
     TableDecodeF32Kernel<COLOURS, ALPHA><<<static_cast<unsigned>(blocks), kTableThreads, shared, stream>>>(tp);
     return cudaGetLastError();
 }

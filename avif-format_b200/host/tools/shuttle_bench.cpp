@@ -4,8 +4,10 @@
 // heap-backed heif_image (pageable memory with padded strides, like libheif's), the GPU path is whatever the shuttle
 // uses.  bench.py runs it for its `e2e_shuttle` figure.
 //
-//   shuttle_bench <c2|c4> <width> <height> <steps> <copy|resident> <fresh|warm> [device ...]
+//   shuttle_bench <c2|c3|c4> <width> <height> <steps> <copy|resident> <fresh|warm> [device ...]
 //
+//   c3        the read side: ReadHeifImageRGBThirtyTwoBit on a 10-bit HLG 4:2:0 image (Read.cpp:587-630); the host takes the
+//             rows it is offered (copy: memcpy into a pageable frame; resident: leaves them in the staging buffer)
 //   copy      advanceState memcpy's the requested rows out of a pageable source frame (what any real host at least does)
 //   resident  advanceState leaves the staging buffers as they are after their first fill: the host's own cost removed,
 //             what remains is the shuttle + the library (the figure to hold against bench.py's e2e)
@@ -102,6 +104,7 @@ namespace
         FormatRecord record{};
         BufferProcs procs{};
         const uint8_t* source = nullptr;
+        uint8_t* sink = nullptr;
         int64_t stride = 0;
         bool copy = true;
     };
@@ -126,6 +129,24 @@ namespace
         }
         return noErr;
     }
+
+    // the read side: the plug-in hands rows [top, bottom) to the host
+    OSErr Take()
+    {
+        Host& h = *g_host;
+        FormatRecord& r = h.record;
+        if (!h.copy || r.data == nullptr)
+        {
+            return noErr;
+        }
+        const int top = r.theRect32.top, bottom = r.theRect32.bottom;
+        for (int y = top; y < bottom; ++y)
+        {
+            std::memcpy(h.sink + static_cast<int64_t>(y) * h.stride, static_cast<const uint8_t*>(r.data) + static_cast<int64_t>(y - top) * r.rowBytes,
+                        static_cast<size_t>(h.stride));
+        }
+        return noErr;
+    }
     Boolean Abort() { return 0; }
     void Progress(int32, int32) {}
 }
@@ -134,7 +155,7 @@ int main(int argc, char** argv)
 {
     if (argc < 7)
     {
-        std::fprintf(stderr, "usage: shuttle_bench <c2|c4> <width> <height> <steps> <copy|resident> <fresh|warm> [device ...]\n");
+        std::fprintf(stderr, "usage: shuttle_bench <c2|c3|c4> <width> <height> <steps> <copy|resident> <fresh|warm> [device ...]\n");
         return 2;
     }
     const std::string workload = argv[1];
@@ -144,8 +165,9 @@ int main(int argc, char** argv)
     std::vector<int32_t> devices;
     for (int i = 7; i < argc; ++i) devices.push_back(std::atoi(argv[i]));
     const bool c2 = workload == "c2";
-    const int channels = c2 ? 3 : 4;
-    const int depth = c2 ? 32 : 16;
+    const bool c3 = workload == "c3";
+    const int channels = (c2 || c3) ? 3 : 4;
+    const int depth = (c2 || c3) ? 32 : 16;
     const int64_t stride = static_cast<int64_t>(w) * channels * (depth / 8);
 
     if (g_warm)
@@ -158,7 +180,11 @@ int main(int argc, char** argv)
     // synthetic frame: finite, in range, different everywhere (a 64-bit LCG), pageable memory like a host's tiles
     std::vector<uint8_t> frame(static_cast<size_t>(stride) * h);
     uint64_t state = 0x9e3779b97f4a7c15ull;
-    if (c2)
+    if (c3)
+    {
+        std::memset(frame.data(), 0, frame.size()); // the host's frame: touched once, then written by Take()
+    }
+    else if (c2)
     {
         float* v = reinterpret_cast<float*>(frame.data());
         for (size_t i = 0; i < frame.size() / 4; ++i)
@@ -193,6 +219,39 @@ int main(int argc, char** argv)
 
         double best = 1e30, total = 0.0, hostSeconds = 0.0;
         avifgpu_host::ShuttleTimes times{};
+        // c3: the decoded image libheif would hand over -- 10-bit Y, Cb, Cr planes (4:2:0) in pageable memory, padded strides
+        heif_image* decoded = nullptr;
+        heif_color_profile_nclx nclx{};
+        LoadUIOptions load{};
+        if (c3)
+        {
+            const bool arena = g_warm;
+            g_warm = false; // the source planes are libheif's own allocation, never the recycled arena
+            heif_image_create(w, h, heif_colorspace_YCbCr, heif_chroma_420, &decoded);
+            const int cw = (w + 1) / 2, ch = (h + 1) / 2;
+            heif_image_add_plane(decoded, heif_channel_Y, w, h, 10);
+            heif_image_add_plane(decoded, heif_channel_Cb, cw, ch, 10);
+            heif_image_add_plane(decoded, heif_channel_Cr, cw, ch, 10);
+            g_warm = arena;
+            const heif_channel planeChannels[3] = { heif_channel_Y, heif_channel_Cb, heif_channel_Cr };
+            for (int k = 0; k < 3; ++k)
+            {
+                int planeStride = 0;
+                uint8_t* p = heif_image_get_plane(decoded, planeChannels[k], &planeStride);
+                const int pw = k ? cw : w, ph = k ? ch : h;
+                for (int y = 0; y < ph; ++y)
+                {
+                    uint16_t* row = reinterpret_cast<uint16_t*>(p + static_cast<int64_t>(y) * planeStride);
+                    for (int x = 0; x < pw; ++x)
+                    {
+                        state = state * 6364136223846793005ull + 1442695040888963407ull;
+                        row[x] = static_cast<uint16_t>((state >> 33) & 1023u);
+                    }
+                }
+            }
+            nclx.color_primaries = 9; nclx.transfer_characteristics = 18; nclx.matrix_coefficients = 9; nclx.full_range_flag = 1; // BT.2020 / HLG / NCL / full
+            load.hlg.applyOOTF = true; load.hlg.displayGamma = 1.2f; load.hlg.nominalPeakBrightness = 1000; load.pq.nominalPeakBrightness = 80;
+        }
         for (int step = -1; step < steps; ++step) // step -1 = warm-up (allocations, table state)
         {
             Host host;
@@ -202,17 +261,26 @@ int main(int argc, char** argv)
             host.record.imageSize32.v = h;
             host.record.HostSupports32BitCoordinates = 1;
             host.record.PluginUsing32BitCoordinates = 1;
-            host.record.advanceState = Advance;
+            host.record.advanceState = c3 ? Take : Advance;
             host.record.abortProc = Abort;
             host.record.progressProc = Progress;
             host.record.bufferProcs = &host.procs;
             host.source = frame.data();
+            host.sink = frame.data();
             host.stride = stride;
             host.copy = copy;
             g_host = &host;
             const auto start = std::chrono::steady_clock::now();
-            ScopedHeifImage image = c2 ? CreateHeifImageRGBThirtyTwoBit(&host.record, alpha, VPoint{ h, w }, options)
-                                       : CreateHeifImageRGBSixteenBit(&host.record, alpha, VPoint{ h, w }, options);
+            ScopedHeifImage image;
+            if (c3)
+            {
+                ReadHeifImageRGBThirtyTwoBit(decoded, AlphaState::None, &nclx, load, &host.record);
+            }
+            else
+            {
+                image = c2 ? CreateHeifImageRGBThirtyTwoBit(&host.record, alpha, VPoint{ h, w }, options)
+                           : CreateHeifImageRGBSixteenBit(&host.record, alpha, VPoint{ h, w }, options);
+            }
             const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
             if (step >= 0)
             {
@@ -221,6 +289,10 @@ int main(int argc, char** argv)
                 times = avifgpu_host::LastShuttleTimes();
                 hostSeconds += times.host;
             }
+        }
+        if (decoded != nullptr)
+        {
+            heif_image_release(decoded);
         }
         const double pixels = static_cast<double>(w) * h;
         std::printf("{\"workload\": \"%s\", \"width\": %d, \"height\": %d, \"steps\": %d, \"host\": \"%s\", \"gpus\": %d, "

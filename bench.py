@@ -471,7 +471,9 @@ def run_shuttle_bench(wl_key, w, h, steps, devices):
     try:
         subprocess.run(cmd, check=True, capture_output=True, timeout=300)
         out = {}
-        for host, pages in (("resident", "warm"), ("resident", "fresh"), ("copy", "fresh")):
+        # the read side (c3) has no planes to allocate: its source planes are the decoder's, filled before the clock starts
+        variants = (("resident", "warm"), ("copy", "warm")) if wl_key == "c3" else (("resident", "warm"), ("resident", "fresh"), ("copy", "fresh"))
+        for host, pages in variants:
             done = subprocess.run([exe, wl_key, str(w), str(h), str(steps), host, pages] + [str(d) for d in devices], capture_output=True, text=True,
                                   timeout=600)
             out[f"host_{host}_planes_{pages}"] = json.loads(done.stdout.strip().splitlines()[-1])
@@ -588,8 +590,11 @@ def run_b200(args, workload, rank, world, local_rank):
         tile = run_tile_block(torch, dist, gpu, avifgpu, device, rank, world, max(3, min(args.steps, 10)), workload=wl)
 
     shuttle = None
-    if rank == 0 and not args.no_shuttle and wl.key in ("c2", "c4"):
+    if rank == 0 and not args.no_shuttle and wl.key in ("c2", "c3", "c4"):
         shuttle = {"one_gpu": run_shuttle_bench(wl.key, wl.w, wl.rows_total, 5, [local_rank])}
+        if wl.key == "c2" and world == 1:
+            # the read side beside it: ReadHeifImageRGBThirtyTwoBit on config 3's image (8K 10-bit HLG 4:2:0 -> RGB32f)
+            shuttle["one_gpu_read_side_c3"] = run_shuttle_bench("c3", wl.w, wl.rows_total, 5, [local_rank])
     if dist is not None:
         dist.barrier()
     if rank == 0 and world > 1 and not args.no_shuttle and wl.key in ("c2", "c4"):

@@ -224,6 +224,48 @@ def test_gray16_lut_every_input(gpu, port):
 
 # ---- float decode (kernels_fast_decode.cu) -------------------------------------------------------------------------------
 
+@pytest.mark.parametrize("channels", [1, 2])
+def test_every_float_through_the_gray_float_kernel(gpu, gpu_exact, channels):
+    """kernels_fast_gray32.cu over every bit pattern from +0 through the NaNs into the first negative values, against the
+    generic exact kernel of a context that never builds tables.  Gray alone is clamped to [0, 1] before the curve
+    (WriteHeifImage.cpp:602), so that run pins the clamp and the table below 1.0; Gray + straight alpha (alpha = 1.0) is
+    not clamped and takes every float through the table, the band bitmap and the +inf / NaN route."""
+    import torch
+    import avifgpu
+    dev = torch.device("cuda", gpu.device)
+    if torch.cuda.get_device_properties(dev).total_memory < 60 * 2**30:
+        pytest.skip("needs ~40 GB of device memory")
+    w = 4096
+    h = ((1 << 31) // w + 2) & ~1
+    alpha = abi.ALPHA_STRAIGHT if channels == 2 else abi.ALPHA_NONE
+    desc = abi.EncodeDesc(w, h, 32, channels, alpha, 12, abi.TRANSFER_PQ, 80)
+    rows = torch.empty((h, w * channels), dtype=torch.float32, device=dev)
+    bits = rows.view(torch.int32).view(h * w, channels)
+    chunk = 1 << 27
+    for start in range(0, h * w, chunk):
+        n = min(chunk, h * w - start)
+        bits[start:start + n, 0] = torch.arange(start, start + n, dtype=torch.int64, device=dev).to(torch.int32)  # wraps past 2^31
+        if channels == 2:
+            bits[start:start + n, 1] = 0x3f800000
+    shapes = abi.encode_plane_shapes(desc)
+    fast = [None if s is None else torch.full(s, -1, dtype=torch.int16, device=dev) for s in shapes]
+    before_fast = gpu.launch_count()
+    gpu.encode_device(desc, rows.data_ptr(), rows.stride(0) * 4, avifgpu.planes_from_tensors(fast))
+    assert gpu.launch_count() - before_fast == 1  # the tuned kernel alone (width is a multiple of 4)
+    backing = [None if s is None else torch.full((s[0], s[1] + 1), -1, dtype=torch.int16, device=dev) for s in shapes]
+    exact = [None if t is None else t[:, 1:] for t in backing]  # 2-byte aligned origins: the launcher takes the generic kernel
+    gpu_exact.encode_device(desc, rows.data_ptr(), rows.stride(0) * 4, avifgpu.planes_from_tensors(exact))
+    torch.cuda.synchronize(dev)
+    for k, plane in enumerate(fast):
+        if plane is None:
+            continue
+        differing = int((plane != exact[k]).sum().item())
+        assert differing == 0, f"plane {k}: {differing} of {plane.numel()} codes differ"
+    codes = exact[0].reshape(-1)[:0x3f800000].to(torch.int32) & 0xffff  # +0 .. 1.0: monotone up to the one-code flips inside bands
+    assert int(codes.min().item()) == 0 and bool((codes[1:] >= codes[:-1] - 1).all().item())
+    assert int((exact[0].reshape(-1)[0x3f800000].to(torch.int32) & 0xffff).item()) > 2000  # 1.0 at 80 nit: mid-scale
+
+
 @pytest.mark.parametrize("w,h", [(4, 2), (5, 3), (128, 2), (131, 7), (260, 9), (1024, 16)])
 @pytest.mark.parametrize("chroma", [abi.CHROMA_420, abi.CHROMA_422, abi.CHROMA_444])
 def test_ycc_to_rgb32_fast_kernel(gpu, port, w, h, chroma):
@@ -247,6 +289,26 @@ def test_ycc_to_rgb32_fast_kernel(gpu, port, w, h, chroma):
             gpu.decode(desc, planes, y0=0, nrows=1, out=out[0:1])
             gpu.decode(desc, planes, y0=1, nrows=h - 1, out=out[1:])
             assert cases.same_bits(expected, out)
+
+
+@pytest.mark.parametrize("gamma,peak", [(1.2, 1000), (0.85, 100), (1.0, 334), (1.79, 25000), (1.8, 27000), (2.5, 100000)])
+def test_hlg_ootf_exponents_on_both_sides_of_the_screen_free_powf(gpu, port, gamma, peak):
+    """The tuned decode kernel's OOTF calls powf without its exponent screens when |gamma - 1| is in (0, 0.8)
+    (device_math.cuh PowfModerateExponent); gamma = 1 (exponent 0), 1.8 and 2.5 go to the generic kernel.  Either way the
+    float samples are the reference's, bit for bit -- black pixels (luma 0) included."""
+    w, h = 260, 8
+    nclx = cases.NCLX_2020_HLG(1)
+    for chroma, alpha in ((abi.CHROMA_420, abi.ALPHA_NONE), (abi.CHROMA_444, abi.ALPHA_STRAIGHT)):
+        desc = abi.DecodeDesc(w, h, abi.COLORSPACE_YCBCR, chroma, 10, alpha, 32, nclx, hlg_apply_ootf=1, hlg_display_gamma=gamma, hlg_peak_nits=peak)
+        planes = cases.code_planes(cases.rng_for(f"ootf_{gamma}_{chroma}"), desc, overshoot=True)
+        planes[0][0, :8] = 0  # black: luma 0 under neutral chroma -> powf(0, gamma - 1), +inf for gamma < 1, then 0 * inf
+        planes[1][0, :8 >> (0 if chroma == abi.CHROMA_444 else 1)] = 512
+        planes[2][0, :8 >> (0 if chroma == abi.CHROMA_444 else 1)] = 512
+        expected = port.decode(desc, planes, threads=4)
+        got = gpu.decode(desc, planes)
+        e, g = expected.view(np.uint32).ravel(), got.view(np.uint32).ravel()
+        both_nan = np.isnan(expected.ravel()) & np.isnan(got.ravel())  # 0 * inf: a NaN on both sides, the payload is the FPU's
+        assert np.array_equal(e[~both_nan], g[~both_nan]) and np.array_equal(np.isnan(expected), np.isnan(got)), (gamma, chroma, int((e != g).sum()))
 
 
 # ---- every float through the production kernel ---------------------------------------------------------------------------
