@@ -15,8 +15,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <deque>
-#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -206,8 +204,6 @@ private:
     bool active = false;
 };
 
-struct CopyBatch; // the copy pool's unit of work (below)
-
 struct avifgpu_context
 {
     int device = -1;
@@ -234,10 +230,6 @@ struct avifgpu_context
         bool busy = false;
         int64_t ticket = 0;
         std::vector<HostCopy> owed;
-        // Set by the stream callback that follows the slice's D2H (SubmitOwedCopies): the copy pool is already moving the
-        // bounce buffers into the caller's memory when the caller next looks at the slot.  Read only after sliceDone.
-        std::shared_ptr<CopyBatch> owedBatch;
-        bool owedSubmitted = false;
     };
     SlotState slots[kPipelineStreams];
     int nextSlot = 0;
@@ -680,7 +672,6 @@ AVIFGPU_EXPORT void avifgpu_destroy(avifgpu_context* ctx)
     }
     DeviceGuard guard(ctx->device);
     cudaDeviceSynchronize();
-    (void)RetireThrough(ctx, INT64_MAX); // copies the pool still owes the caller read the pinned buffers freed below
     for (int i = 0; i < kPipelineStreams; ++i)
     {
         if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
@@ -996,9 +987,7 @@ static void CopyRowsSerial(uint8_t* target, int64_t targetStride, const uint8_t*
     }
 }
 
-// Bounce copies between pageable caller memory and the pinned slot buffers.  (Batches are queued: a slice's copies into the
-// caller's memory are submitted by a stream callback the moment its D2H completes and run on the pool's threads while the
-// caller queues the next slices -- see SubmitOwedCopies.)  One core moves ~10 GB/s, a fifth of what
+// Bounce copies between pageable caller memory and the pinned slot buffers.  One core moves ~10 GB/s, a fifth of what
 // the PCIe link next to it carries, and an 8K frame owes 100 MB of plane copies: a small pool of parked threads (created
 // at the first bounce, process-wide, joined at exit) shares every batch of copies above a megabyte, cut into chunks of
 // rows that the threads -- and the caller -- pull from a common counter.
@@ -1023,12 +1012,45 @@ namespace
             return pool;
         }
 
-        // Queues the copies and returns at once; nullptr when they were small enough to do on the spot.  The pool's threads
-        // start on them immediately; Wait() lends the calling thread as well and returns when the last chunk has landed.
-        std::shared_ptr<CopyBatch> Submit(const RowCopy* copies, int count);
-        void Wait(const std::shared_ptr<CopyBatch>& batch);
-
-        void Copy(const RowCopy* copies, int count) { Wait(Submit(copies, count)); }
+        void Copy(const RowCopy* copies, int count)
+        {
+            int64_t bytes = 0;
+            for (int i = 0; i < count; ++i)
+            {
+                bytes += copies[i].payload * copies[i].rows;
+            }
+            if (bytes < (1ll << 20) || workers.empty())
+            {
+                for (int i = 0; i < count; ++i)
+                {
+                    CopyRowsSerial(copies[i].target, copies[i].targetStride, copies[i].source, copies[i].sourceStride, copies[i].payload, copies[i].rows);
+                }
+                return;
+            }
+            std::unique_lock<std::mutex> callers(callerMutex); // one batch at a time (contexts on several threads share the pool)
+            {
+                std::lock_guard<std::mutex> lock(mutex);
+                chunks.clear();
+                for (int i = 0; i < count; ++i)
+                {
+                    const RowCopy& c = copies[i];
+                    const int rowsPerChunk = static_cast<int>(std::max<int64_t>((256ll << 10) / std::max<int64_t>(c.payload, 1), 1));
+                    for (int begin = 0; begin < c.rows; begin += rowsPerChunk)
+                    {
+                        chunks.push_back(RowCopy{ c.target + static_cast<int64_t>(begin) * c.targetStride, c.targetStride,
+                                                  c.source + static_cast<int64_t>(begin) * c.sourceStride, c.sourceStride, c.payload,
+                                                  std::min(rowsPerChunk, c.rows - begin) });
+                    }
+                }
+                next.store(0, std::memory_order_relaxed);
+                remaining = static_cast<int>(chunks.size());
+                ++generation;
+            }
+            wake.notify_all();
+            Drain();
+            std::unique_lock<std::mutex> lock(mutex);
+            done.wait(lock, [&] { return remaining == 0; });
+        }
 
     private:
         CopyPool()
@@ -1054,121 +1076,60 @@ namespace
             }
         }
 
-        void Drain(CopyBatch& batch);
-        void Run();
-
-        std::vector<std::thread> workers;
-        std::mutex mutex;
-        std::condition_variable wake, done;
-        std::deque<std::shared_ptr<CopyBatch>> pending; // batches that may still have chunks nobody has taken
-        bool stopping = false;
-    };
-}
-
-struct CopyBatch
-{
-    std::vector<RowCopy> chunks;
-    std::atomic<int> next{ 0 };      // first chunk nobody has taken
-    std::atomic<int> remaining{ 0 }; // chunks not yet copied
-};
-
-std::shared_ptr<CopyBatch> CopyPool::Submit(const RowCopy* copies, int count)
-{
-    int64_t bytes = 0;
-    for (int i = 0; i < count; ++i)
-    {
-        bytes += copies[i].payload * copies[i].rows;
-    }
-    if (bytes < (1ll << 20) || workers.empty())
-    {
-        for (int i = 0; i < count; ++i)
+        // Pulls chunks until none is left; returns how many this thread copied.
+        void Drain()
         {
-            CopyRowsSerial(copies[i].target, copies[i].targetStride, copies[i].source, copies[i].sourceStride, copies[i].payload, copies[i].rows);
-        }
-        return nullptr;
-    }
-    std::shared_ptr<CopyBatch> batch = std::make_shared<CopyBatch>();
-    for (int i = 0; i < count; ++i)
-    {
-        const RowCopy& c = copies[i];
-        const int rowsPerChunk = static_cast<int>(std::max<int64_t>((256ll << 10) / std::max<int64_t>(c.payload, 1), 1));
-        for (int begin = 0; begin < c.rows; begin += rowsPerChunk)
-        {
-            batch->chunks.push_back(RowCopy{ c.target + static_cast<int64_t>(begin) * c.targetStride, c.targetStride,
-                                             c.source + static_cast<int64_t>(begin) * c.sourceStride, c.sourceStride, c.payload,
-                                             std::min(rowsPerChunk, c.rows - begin) });
-        }
-    }
-    batch->remaining.store(static_cast<int>(batch->chunks.size()), std::memory_order_relaxed);
-    {
-        std::lock_guard<std::mutex> lock(mutex);
-        pending.push_back(batch);
-    }
-    wake.notify_all();
-    return batch;
-}
-
-// Pulls chunks of `batch` until none is left to take.
-void CopyPool::Drain(CopyBatch& batch)
-{
-    int copied = 0;
-    const int total = static_cast<int>(batch.chunks.size());
-    for (;;)
-    {
-        const int i = batch.next.fetch_add(1, std::memory_order_relaxed);
-        if (i >= total)
-        {
-            break;
-        }
-        const RowCopy& c = batch.chunks[i];
-        CopyRowsSerial(c.target, c.targetStride, c.source, c.sourceStride, c.payload, c.rows);
-        ++copied;
-    }
-    if (copied && batch.remaining.fetch_sub(copied, std::memory_order_acq_rel) == copied)
-    {
-        std::lock_guard<std::mutex> lock(mutex); // the waiter checks `remaining` under this mutex: no lost wake-up
-        done.notify_all();
-    }
-}
-
-void CopyPool::Wait(const std::shared_ptr<CopyBatch>& batch)
-{
-    if (!batch)
-    {
-        return;
-    }
-    Drain(*batch);
-    std::unique_lock<std::mutex> lock(mutex);
-    done.wait(lock, [&] { return batch->remaining.load(std::memory_order_acquire) == 0; });
-}
-
-void CopyPool::Run()
-{
-    for (;;)
-    {
-        std::shared_ptr<CopyBatch> batch;
-        {
-            std::unique_lock<std::mutex> lock(mutex);
+            int copied = 0;
+            const int total = static_cast<int>(chunks.size());
             for (;;)
             {
-                while (!pending.empty() && pending.front()->next.load(std::memory_order_relaxed) >= static_cast<int>(pending.front()->chunks.size()))
+                const int i = next.fetch_add(1, std::memory_order_relaxed);
+                if (i >= total)
                 {
-                    pending.pop_front(); // every chunk taken (its last copies may still be running: the handles keep it alive)
-                }
-                if (stopping)
-                {
-                    return;
-                }
-                if (!pending.empty())
-                {
-                    batch = pending.front();
                     break;
                 }
-                wake.wait(lock);
+                const RowCopy& c = chunks[i];
+                CopyRowsSerial(c.target, c.targetStride, c.source, c.sourceStride, c.payload, c.rows);
+                ++copied;
+            }
+            if (copied)
+            {
+                std::lock_guard<std::mutex> lock(mutex);
+                remaining -= copied;
+                if (remaining == 0)
+                {
+                    done.notify_all();
+                }
             }
         }
-        Drain(*batch);
-    }
+
+        void Run()
+        {
+            uint64_t seen = 0;
+            for (;;)
+            {
+                {
+                    std::unique_lock<std::mutex> lock(mutex);
+                    wake.wait(lock, [&] { return stopping || generation != seen; });
+                    if (stopping)
+                    {
+                        return;
+                    }
+                    seen = generation;
+                }
+                Drain(); // `chunks` is stable until the caller has seen remaining == 0, which needs every pulled chunk finished
+            }
+        }
+
+        std::vector<std::thread> workers;
+        std::mutex mutex, callerMutex;
+        std::condition_variable wake, done;
+        std::vector<RowCopy> chunks;
+        std::atomic<int> next{ 0 };
+        int remaining = 0;
+        uint64_t generation = 0;
+        bool stopping = false;
+    };
 }
 
 static void CopyRows(uint8_t* target, int64_t targetStride, const uint8_t* source, int64_t sourceStride, int64_t payload, int rows)
@@ -1188,12 +1149,6 @@ static int WaitSlot(avifgpu_context* ctx, int slot)
     const int status = ctx->Cuda(cudaEventSynchronize(ctx->sliceDone[slot]), "cudaEventSynchronize");
     if (status != AVIFGPU_OK)
     {
-        if (state.owedSubmitted)
-        {
-            CopyPool::Instance().Wait(state.owedBatch);
-        }
-        state.owedBatch.reset();
-        state.owedSubmitted = false;
         state.owed.clear();
     }
     state.busy = false;
@@ -1201,34 +1156,10 @@ static int WaitSlot(avifgpu_context* ctx, int slot)
 }
 
 // Pays what a waited-for slot owes the caller: the copies out of its pinned bounce buffers.
-// Stream callback (cudaLaunchHostFunc, queued right after a slice's D2H copies and before its sliceDone event): hands the
-// slice's bounce -> caller copies to the pool.  Runs on a driver thread: no CUDA calls, returns at once.
-static void CUDART_CB SubmitOwedCopies(void* userData)
-{
-    avifgpu_context::SlotState& state = *static_cast<avifgpu_context::SlotState*>(userData);
-    RowCopy batch[AVIFGPU_MAX_PLANES + 1];
-    int count = 0;
-    for (const avifgpu_context::HostCopy& c : state.owed)
-    {
-        if (count == AVIFGPU_MAX_PLANES + 1)
-        {
-            break; // never more than the planes of one slice
-        }
-        batch[count++] = RowCopy{ c.target, c.targetStride, c.source, c.sourceStride, c.payload, c.rows };
-    }
-    state.owedBatch = CopyPool::Instance().Submit(batch, count);
-    state.owedSubmitted = true;
-}
-
-// After the slot's sliceDone: its owed copies are under way (or done); wait for the last chunk.
 static void PayOwed(avifgpu_context* ctx, int slot)
 {
     avifgpu_context::SlotState& state = ctx->slots[slot];
-    if (state.owedSubmitted)
-    {
-        CopyPool::Instance().Wait(state.owedBatch);
-    }
-    else if (!state.owed.empty())
+    if (!state.owed.empty())
     {
         RowCopy batch[AVIFGPU_MAX_PLANES + 1];
         int count = 0;
@@ -1243,8 +1174,6 @@ static void PayOwed(avifgpu_context* ctx, int slot)
         }
         CopyPool::Instance().Copy(batch, count); // all planes of the slice share the pool's threads
     }
-    state.owedBatch.reset();
-    state.owedSubmitted = false;
     state.owed.clear();
 }
 
@@ -1280,12 +1209,6 @@ static int AbandonCall(avifgpu_context* ctx, int status)
     for (int i = 0; i < kPipelineStreams; ++i)
     {
         cudaStreamSynchronize(ctx->streams[i]);
-        if (ctx->slots[i].owedSubmitted)
-        {
-            CopyPool::Instance().Wait(ctx->slots[i].owedBatch); // the pool may be writing caller memory: not past this return
-        }
-        ctx->slots[i].owedBatch.reset();
-        ctx->slots[i].owedSubmitted = false;
         ctx->slots[i].owed.clear();
         ctx->slots[i].busy = false;
     }
@@ -1445,8 +1368,6 @@ static int EncodeRowsHost(avifgpu_context* ctx, const avifgpu_encode_desc* desc,
                                                       static_cast<size_t>(planeRows[k]), cudaMemcpyDeviceToHost, stream),
                                     "D2H plane")) != AVIFGPU_OK) return AbandonCall(ctx, status);
         }
-        if (!state.owed.empty() &&
-            (status = ctx->Cuda(cudaLaunchHostFunc(stream, SubmitOwedCopies, &state), "cudaLaunchHostFunc")) != AVIFGPU_OK) return AbandonCall(ctx, status);
         if ((status = ctx->Cuda(cudaEventRecord(ctx->sliceDone[slot], stream), "cudaEventRecord")) != AVIFGPU_OK) return AbandonCall(ctx, status);
         state.busy = true;
         state.ticket = ticket;
@@ -1615,8 +1536,6 @@ static int DecodeRowsHost(avifgpu_context* ctx, const avifgpu_decode_desc* desc,
                                                   static_cast<size_t>(deviceRowStride), static_cast<size_t>(rowPayload),
                                                   static_cast<size_t>(rows), cudaMemcpyDeviceToHost, stream),
                                 "D2H rows")) != AVIFGPU_OK) return AbandonCall(ctx, status);
-        if (!state.owed.empty() &&
-            (status = ctx->Cuda(cudaLaunchHostFunc(stream, SubmitOwedCopies, &state), "cudaLaunchHostFunc")) != AVIFGPU_OK) return AbandonCall(ctx, status);
         if ((status = ctx->Cuda(cudaEventRecord(ctx->sliceDone[slot], stream), "cudaEventRecord")) != AVIFGPU_OK) return AbandonCall(ctx, status);
         state.busy = true;
         state.ticket = ticket;
