@@ -21,9 +21,6 @@
 #include <thread>
 #include <vector>
 
-#if defined(__linux__)
-#include <sched.h>
-#endif
 
 namespace avifgpu
 {
@@ -112,97 +109,6 @@ namespace
     // (pageable caller memory) while the other two are on the wire.
     constexpr int kPipelineStreams = 3;
 }
-
-// Page-locked staging memory belongs on the NUMA node the GPU hangs off: on a two-socket host a DMA from the far socket
-// runs well below the link's 53 GB/s (measured: the same 8K frame through the shuttle in 10.6 ms or 8.1 ms depending on
-// where the process happened to run).  cudaHostAlloc takes its pages from the node of the calling CPU, so the allocating
-// thread moves onto the GPU's local CPUs (sysfs local_cpulist of the PCI device, intersected with the CPUs the process
-// may use) for the duration of the call.  Linux only; anywhere else, or on any failure, nothing changes.
-class GpuLocalAffinity
-{
-public:
-    explicit GpuLocalAffinity(int device)
-    {
-#if defined(__linux__)
-        cpu_set_t local;
-        if (!LocalCpus(device, &local) || sched_getaffinity(0, sizeof(previous), &previous) != 0)
-        {
-            return;
-        }
-        cpu_set_t wanted;
-        CPU_AND(&wanted, &local, &previous);
-        if (CPU_COUNT(&wanted) == 0 || CPU_EQUAL(&wanted, &previous))
-        {
-            return;
-        }
-        active = sched_setaffinity(0, sizeof(wanted), &wanted) == 0;
-#else
-        (void)device;
-#endif
-    }
-    ~GpuLocalAffinity()
-    {
-#if defined(__linux__)
-        if (active)
-        {
-            sched_setaffinity(0, sizeof(previous), &previous);
-        }
-#endif
-    }
-    GpuLocalAffinity(const GpuLocalAffinity&) = delete;
-    GpuLocalAffinity& operator=(const GpuLocalAffinity&) = delete;
-
-private:
-#if defined(__linux__)
-    static bool LocalCpus(int device, cpu_set_t* out)
-    {
-        char busId[32] = {};
-        if (device < 0 || cudaDeviceGetPCIBusId(busId, static_cast<int>(sizeof(busId)), device) != cudaSuccess)
-        {
-            (void)cudaGetLastError();
-            return false;
-        }
-        std::string path = "/sys/bus/pci/devices/";
-        for (const char* c = busId; *c; ++c)
-        {
-            path += static_cast<char>((*c >= 'A' && *c <= 'F') ? *c - 'A' + 'a' : *c);
-        }
-        path += "/local_cpulist";
-        std::FILE* f = std::fopen(path.c_str(), "r");
-        if (f == nullptr)
-        {
-            return false;
-        }
-        char text[4096] = {};
-        const size_t got = std::fread(text, 1, sizeof(text) - 1, f);
-        std::fclose(f);
-        text[got] = 0;
-        CPU_ZERO(out);
-        int count = 0;
-        for (char* c = text; *c;) // "0-31,64-95"
-        {
-            if (*c < '0' || *c > '9')
-            {
-                ++c;
-                continue;
-            }
-            long first = std::strtol(c, &c, 10), last = first;
-            if (*c == '-')
-            {
-                last = std::strtol(c + 1, &c, 10);
-            }
-            for (long cpu = first; cpu <= last && cpu < CPU_SETSIZE; ++cpu)
-            {
-                CPU_SET(static_cast<int>(cpu), out);
-                ++count;
-            }
-        }
-        return count > 0;
-    }
-    cpu_set_t previous;
-#endif
-    bool active = false;
-};
 
 struct avifgpu_context
 {
@@ -515,7 +421,6 @@ struct avifgpu_context
             b.bytes = 0;
         }
         const size_t rounded = ((bytes + (1u << 20) - 1) >> 20) << 20;
-        GpuLocalAffinity nearTheGpu(device);
         const int status = Cuda(cudaHostAlloc(&b.ptr, rounded, cudaHostAllocDefault), "cudaHostAlloc");
         if (status == AVIFGPU_OK)
         {
@@ -730,7 +635,6 @@ AVIFGPU_EXPORT int avifgpu_host_alloc(avifgpu_context* ctx, size_t bytes, void**
     }
     DeviceGuard guard(ctx->device);
     *out_ptr = nullptr;
-    GpuLocalAffinity nearTheGpu(ctx->device);
     return ctx->Cuda(cudaHostAlloc(out_ptr, bytes ? bytes : 1, cudaHostAllocDefault), "cudaHostAlloc");
 }
 
