@@ -11,6 +11,7 @@
 //                              thread converts 8 pixels (x 2 rows for 4:2:0).
 #include "group_walk.cuh"
 #include "kernel_params.h"
+#include "packed_f32x2.cuh"
 #include "../../include/avifgpu.h"
 
 #include <cuda_runtime.h>
@@ -296,67 +297,90 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
             }
         }
 
-        float cb[kRows][8], cr[kRows][8];
+        // The matrix runs on pixel pairs (2j, 2j + 1) in the two-lane FP32 instructions (packed_f32x2.cuh; its rule: a product
+        // is never the operand of a packed add, so the three luma products and the chroma sums are added as scalars).  The
+        // operations per pixel, and their roundings, are pixel_math.cuh's ForwardPixelFloat.
+        using namespace avifx2;
+        const F32x2 half2 = Splat(0.5f), bias2 = Splat(kTwo23), offset2 = Splat(p.chromaOffset);
+        const F32x2 kr2 = Splat(p.matrix.kr), kg2 = Splat(p.matrix.kg), kb2 = Splat(p.matrix.kb);
+        const F32x2 cbScale2 = Splat(p.matrix.cbScale), crScale2 = Splat(p.matrix.crScale);
+        // 2^23 + trunc(v + 0.5) for both halves: BiasedToCode of either is the code (no upper clamp here)
+        const auto biasedPair = [&](F32x2 v, float& lo, float& hi) { Unpack(AddRz2(Add2(v, half2), bias2), lo, hi); };
+        const auto chromaClamp = [&](float biased) -> uint32_t { return BiasedToCode(fminf(biased, p.biasedMax)); }; // H.273: 2^depth -> 2^depth - 1
+
+        F32x2 cb[kRows][4], cr[kRows][4]; // [row][pair]
 #pragma unroll
         for (int r = 0; r < kRows; ++r)
         {
             uint32_t yCodes[8];
             uint32_t aCodes[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 4; ++j)
             {
-                // sample k of the row sits in half-word (byte) k of the loaded words
-                auto sample = [&](int k) -> uint32_t
+                float rf[2], gf[2], bf[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
                 {
-                    if (sizeof(HostT) == 2)
+                    const int i = 2 * j + h;
+                    // sample k of the row sits in half-word (byte) k of the loaded words
+                    auto sample = [&](int k) -> uint32_t
                     {
-                        const uint32_t w = words[r][k >> 1];
-                        return (k & 1) ? (w >> 16) : (w & 0xffffu);
+                        if (sizeof(HostT) == 2)
+                        {
+                            const uint32_t w = words[r][k >> 1];
+                            return (k & 1) ? (w >> 16) : (w & 0xffffu);
+                        }
+                        return (words[r][k >> 2] >> (8 * (k & 3))) & 0xffu;
+                    };
+                    if (PREMULTIPLY)
+                    {
+                        const float af = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 3), p, hostLut) - kTwo23;
+                        rf[h] = FastPremultiplyBiased(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 0), p, hostLut) - kTwo23, af, p.maxCodeFloat, p.maxReciprocal) - kTwo23;
+                        gf[h] = FastPremultiplyBiased(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 1), p, hostLut) - kTwo23, af, p.maxCodeFloat, p.maxReciprocal) - kTwo23;
+                        bf[h] = FastPremultiplyBiased(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 2), p, hostLut) - kTwo23, af, p.maxCodeFloat, p.maxReciprocal) - kTwo23;
                     }
-                    return (words[r][k >> 2] >> (8 * (k & 3))) & 0xffu;
-                };
-                float rf, gf, bf;
-                if (PREMULTIPLY)
-                {
-                    const float af = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 3), p, hostLut) - kTwo23;
-                    rf = FastPremultiplyBiased(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 0), p, hostLut) - kTwo23, af, p.maxCodeFloat, p.maxReciprocal) - kTwo23;
-                    gf = FastPremultiplyBiased(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 1), p, hostLut) - kTwo23, af, p.maxCodeFloat, p.maxReciprocal) - kTwo23;
-                    bf = FastPremultiplyBiased(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 2), p, hostLut) - kTwo23, af, p.maxCodeFloat, p.maxReciprocal) - kTwo23;
+                    else if (sizeof(HostT) == 1 && sizeof(PlaneT) == 1)
+                    {
+                        // 8-bit host into an 8-bit image: the sample is the code.  Byte -> float is one conversion instruction
+                        // (it takes the byte lane as an operand modifier).
+                        rf[h] = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 0)));
+                        gf[h] = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 1)));
+                        bf[h] = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 2)));
+                    }
+                    else
+                    {
+                        rf[h] = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 0), p, hostLut) - kTwo23;
+                        gf[h] = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 1), p, hostLut) - kTwo23;
+                        bf[h] = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 2), p, hostLut) - kTwo23;
+                    }
+                    if (CHANNELS == 4)
+                    {
+                        aCodes[i] = (sizeof(HostT) == 1 && sizeof(PlaneT) == 1) ? sample(i * CHANNELS + 3)
+                                                                                : BiasedToCode(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 3), p, hostLut));
+                    }
                 }
-                else if (sizeof(HostT) == 1 && sizeof(PlaneT) == 1)
-                {
-                    // 8-bit host into an 8-bit image: the sample is the code.  Byte -> float is one conversion instruction
-                    // (it takes the byte lane as an operand modifier); at 4.5 bytes per pixel this kernel is bound by
-                    // instruction issue, not by the conversion pipe that config 4's 14 bytes per pixel has to avoid.
-                    rf = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 0)));
-                    gf = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 1)));
-                    bf = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 2)));
-                }
-                else
-                {
-                    rf = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 0), p, hostLut) - kTwo23;
-                    gf = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 1), p, hostLut) - kTwo23;
-                    bf = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 2), p, hostLut) - kTwo23;
-                }
-                float yf;
+                const F32x2 red = Pack(rf[0], rf[1]), green = Pack(gf[0], gf[1]), blue = Pack(bf[0], bf[1]);
+                F32x2 luma;
                 if (p.matrix.identity)
                 {
-                    yf = gf;
-                    cb[r][i] = bf;
-                    cr[r][i] = rf;
+                    luma = green;
+                    cb[r][j] = blue;
+                    cr[r][j] = red;
                 }
                 else
                 {
-                    yf = ((p.matrix.kr * rf) + (p.matrix.kg * gf)) + (p.matrix.kb * bf);
-                    cb[r][i] = (bf - yf) * p.matrix.cbScale;
-                    cr[r][i] = (rf - yf) * p.matrix.crScale;
+                    float r0, r1, g0, g1, b0, b1;
+                    Unpack(Mul2(red, kr2), r0, r1);
+                    Unpack(Mul2(green, kg2), g0, g1);
+                    Unpack(Mul2(blue, kb2), b0, b1);
+                    luma = Pack(__fadd_rn(__fadd_rn(r0, g0), b0), __fadd_rn(__fadd_rn(r1, g1), b1)); // (kr R + kg G) + kb B
+                    cb[r][j] = Mul2(Sub2(blue, luma), cbScale2);
+                    cr[r][j] = Mul2(Sub2(red, luma), crScale2);
                 }
-                yCodes[i] = BiasedToCode(__fadd_rz(yf + 0.5f, kTwo23)); // no upper clamp: ForwardMatrixStaysInRange (launcher)
-                if (CHANNELS == 4)
-                {
-                    aCodes[i] = (sizeof(HostT) == 1 && sizeof(PlaneT) == 1) ? sample(i * CHANNELS + 3)
-                                                                            : BiasedToCode(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 3), p, hostLut));
-                }
+                float luma0, luma1;
+                biasedPair(luma, luma0, luma1); // no upper clamp: ForwardMatrixStaysInRange (launcher)
+                yCodes[2 * j] = BiasedToCode(luma0);
+                yCodes[2 * j + 1] = BiasedToCode(luma1);
             }
             StoreEight<PlaneT>(p.plane[0] + (y0 + r) * p.stride[0] + static_cast<long long>(column) * (8 * kPlaneBytes), yCodes);
             if (CHANNELS == 4)
@@ -365,9 +389,14 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
             }
         }
 
-        // chroma: down-filter in float, then quantise (the offset is 0 for the identity matrix)
-        // upper clamp: with the H.273 offset a saturated red / blue reaches 2^depth exactly
-        auto quantise = [&](float c) -> uint32_t { return BiasedToCode(fminf(__fadd_rz((c + p.chromaOffset) + 0.5f, kTwo23), p.biasedMax)); };
+        // chroma: down-filter in float, then quantise (the offset is 0 for the identity matrix); chroma values are products
+        // (or, for the identity matrix, plain samples): the offset is added to each half as a scalar, like the sums
+        const auto addOffset = [&](F32x2 product) -> F32x2
+        {
+            float c0, c1;
+            Unpack(product, c0, c1);
+            return Pack(__fadd_rn(c0, p.chromaOffset), __fadd_rn(c1, p.chromaOffset));
+        };
         if (XS == 0)
         {
 #pragma unroll
@@ -375,10 +404,15 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
             {
                 uint32_t cbCode[8], crCode[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int j = 0; j < 4; ++j)
                 {
-                    cbCode[i] = quantise(cb[r][i]);
-                    crCode[i] = quantise(cr[r][i]);
+                    float b0, b1, r0, r1;
+                    biasedPair(addOffset(cb[r][j]), b0, b1);
+                    biasedPair(addOffset(cr[r][j]), r0, r1);
+                    cbCode[2 * j] = chromaClamp(b0);
+                    cbCode[2 * j + 1] = chromaClamp(b1);
+                    crCode[2 * j] = chromaClamp(r0);
+                    crCode[2 * j + 1] = chromaClamp(r1);
                 }
                 const long long offset = static_cast<long long>(column) * (8 * kPlaneBytes);
                 StoreEight<PlaneT>(p.plane[1] + (y0 + r) * p.stride[1] + offset, cbCode);
@@ -387,28 +421,49 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
         }
         else
         {
+            // site s = pixels 2s, 2s + 1 (of both rows for 4:2:0) = the two halves of pair s; two sites per packed value
             uint32_t cbCode[4], crCode[4];
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
+            for (int s = 0; s < 4; s += 2)
             {
-                float cbv, crv;
+                F32x2 cbBiased, crBiased; // chroma + offset for sites s, s + 1
                 if (p.topLeft)
                 {
-                    cbv = cb[0][2 * s];
-                    crv = cr[0][2 * s];
-                }
-                else if (YS == 1)
-                {
-                    cbv = ((cb[0][2 * s] + cb[0][2 * s + 1]) + (cb[kRows - 1][2 * s] + cb[kRows - 1][2 * s + 1])) * 0.25f;
-                    crv = ((cr[0][2 * s] + cr[0][2 * s + 1]) + (cr[kRows - 1][2 * s] + cr[kRows - 1][2 * s + 1])) * 0.25f;
+                    float b0, b1, r0, r1, unused;
+                    Unpack(cb[0][s], b0, unused);
+                    Unpack(cb[0][s + 1], b1, unused);
+                    Unpack(cr[0][s], r0, unused);
+                    Unpack(cr[0][s + 1], r1, unused);
+                    cbBiased = Pack(__fadd_rn(b0, p.chromaOffset), __fadd_rn(b1, p.chromaOffset));
+                    crBiased = Pack(__fadd_rn(r0, p.chromaOffset), __fadd_rn(r1, p.chromaOffset));
                 }
                 else
                 {
-                    cbv = (cb[0][2 * s] + cb[0][2 * s + 1]) * 0.5f;
-                    crv = (cr[0][2 * s] + cr[0][2 * s + 1]) * 0.5f;
+                    const auto siteSum = [&](const F32x2 (&plane)[kRows][4], int site) -> float
+                    {
+                        float top0, top1;
+                        Unpack(plane[0][site], top0, top1);
+                        const float top = __fadd_rn(top0, top1);
+                        if (YS == 0)
+                        {
+                            return top;
+                        }
+                        float bottom0, bottom1;
+                        Unpack(plane[kRows - 1][site], bottom0, bottom1);
+                        return __fadd_rn(top, __fadd_rn(bottom0, bottom1)); // (c00 + c01) + (c10 + c11)
+                    };
+                    // * 0.25f (0.5f) is exact, so the fused multiply-add with the offset is the two-step number
+                    const F32x2 scale2 = Splat(YS == 1 ? 0.25f : 0.5f);
+                    cbBiased = Fma2(Pack(siteSum(cb, s), siteSum(cb, s + 1)), scale2, offset2);
+                    crBiased = Fma2(Pack(siteSum(cr, s), siteSum(cr, s + 1)), scale2, offset2);
                 }
-                cbCode[s] = quantise(cbv);
-                crCode[s] = quantise(crv);
+                float b0, b1, r0, r1;
+                biasedPair(cbBiased, b0, b1);
+                biasedPair(crBiased, r0, r1);
+                cbCode[s] = chromaClamp(b0);
+                cbCode[s + 1] = chromaClamp(b1);
+                crCode[s] = chromaClamp(r0);
+                crCode[s + 1] = chromaClamp(r1);
             }
             const long long offset = static_cast<long long>(column) * (4 * kPlaneBytes);
             const long long chromaRow = YS ? rowPair : y0;

@@ -43,6 +43,14 @@ __device__ __forceinline__ F32x2 Add2(F32x2 a, F32x2 b)
     return r;
 }
 
+// a + b rounded toward zero in both lanes (FADD2.RZ): the 2^23-bias truncation of the integer kernels
+__device__ __forceinline__ F32x2 AddRz2(F32x2 a, F32x2 b)
+{
+    F32x2 r;
+    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 __device__ __forceinline__ F32x2 Sub2(F32x2 a, F32x2 b)
 {
     F32x2 r;
