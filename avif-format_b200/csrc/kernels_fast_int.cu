@@ -168,6 +168,18 @@ __device__ __forceinline__ float FastPremultiplyBiased(float colour, float alpha
     return __fadd_rz(__fadd_rn(quotient, 0.5f), kTwo23); // 2^23 + code
 }
 
+// The same six operations on two (colour, alpha) pairs at once (packed_f32x2.cuh): lane for lane the IEEE operations of
+// FastPremultiplyBiased -- fma(-q, d, x) == fma(q, -d, x) -- so VerifyFastPremultiply's enumeration covers it.
+__device__ __forceinline__ avifx2::F32x2 FastPremultiplyBiasedPair(avifx2::F32x2 colour, avifx2::F32x2 alpha, float maxCodeFloat, float maxReciprocal)
+{
+    using namespace avifx2;
+    const F32x2 product = Mul2(colour, alpha);
+    const F32x2 q = Mul2(product, Splat(maxReciprocal));
+    const F32x2 residual = Fma2(q, Splat(-maxCodeFloat), product);
+    const F32x2 quotient = Fma2(residual, Splat(maxReciprocal), q);
+    return AddRz2(Add2(quotient, Splat(0.5f)), Splat(kTwo23)); // 2^23 + code
+}
+
 __global__ void VerifyFastPremultiplyKernel(uint32_t maxCode, unsigned long long* __restrict__ counter)
 {
     const float maxCodeFloat = static_cast<float>(maxCode);
@@ -317,49 +329,68 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
 #pragma unroll
             for (int j = 0; j < 4; ++j)
             {
-                float rf[2], gf[2], bf[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
+                // sample k of the row sits in half-word (byte) k of the loaded words
+                auto sample = [&](int k) -> uint32_t
                 {
-                    const int i = 2 * j + h;
-                    // sample k of the row sits in half-word (byte) k of the loaded words
-                    auto sample = [&](int k) -> uint32_t
+                    if (sizeof(HostT) == 2)
                     {
-                        if (sizeof(HostT) == 2)
+                        const uint32_t w = words[r][k >> 1];
+                        return (k & 1) ? (w >> 16) : (w & 0xffffu);
+                    }
+                    return (words[r][k >> 2] >> (8 * (k & 3))) & 0xffu;
+                };
+                F32x2 red, green, blue;
+                if (PREMULTIPLY)
+                {
+                    // both pixels' codes (2^23-biased), then colour * alpha / max per channel on the pair
+                    float biased[2][4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                    {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
                         {
-                            const uint32_t w = words[r][k >> 1];
-                            return (k & 1) ? (w >> 16) : (w & 0xffffu);
+                            biased[h][c] = SampleToBiasedCode<HostT, PlaneT>(sample((2 * j + h) * CHANNELS + c), p, hostLut);
                         }
-                        return (words[r][k >> 2] >> (8 * (k & 3))) & 0xffu;
-                    };
-                    if (PREMULTIPLY)
-                    {
-                        const float af = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 3), p, hostLut) - kTwo23;
-                        rf[h] = FastPremultiplyBiased(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 0), p, hostLut) - kTwo23, af, p.maxCodeFloat, p.maxReciprocal) - kTwo23;
-                        gf[h] = FastPremultiplyBiased(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 1), p, hostLut) - kTwo23, af, p.maxCodeFloat, p.maxReciprocal) - kTwo23;
-                        bf[h] = FastPremultiplyBiased(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 2), p, hostLut) - kTwo23, af, p.maxCodeFloat, p.maxReciprocal) - kTwo23;
                     }
-                    else if (sizeof(HostT) == 1 && sizeof(PlaneT) == 1)
-                    {
-                        // 8-bit host into an 8-bit image: the sample is the code.  Byte -> float is one conversion instruction
-                        // (it takes the byte lane as an operand modifier).
-                        rf[h] = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 0)));
-                        gf[h] = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 1)));
-                        bf[h] = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 2)));
-                    }
-                    else
-                    {
-                        rf[h] = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 0), p, hostLut) - kTwo23;
-                        gf[h] = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 1), p, hostLut) - kTwo23;
-                        bf[h] = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 2), p, hostLut) - kTwo23;
-                    }
-                    if (CHANNELS == 4)
-                    {
-                        aCodes[i] = (sizeof(HostT) == 1 && sizeof(PlaneT) == 1) ? sample(i * CHANNELS + 3)
-                                                                                : BiasedToCode(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 3), p, hostLut));
-                    }
+                    const F32x2 alpha = Sub2(Pack(biased[0][3], biased[1][3]), bias2);
+                    red = Sub2(FastPremultiplyBiasedPair(Sub2(Pack(biased[0][0], biased[1][0]), bias2), alpha, p.maxCodeFloat, p.maxReciprocal), bias2);
+                    green = Sub2(FastPremultiplyBiasedPair(Sub2(Pack(biased[0][1], biased[1][1]), bias2), alpha, p.maxCodeFloat, p.maxReciprocal), bias2);
+                    blue = Sub2(FastPremultiplyBiasedPair(Sub2(Pack(biased[0][2], biased[1][2]), bias2), alpha, p.maxCodeFloat, p.maxReciprocal), bias2);
+                    aCodes[2 * j] = BiasedToCode(biased[0][3]);
+                    aCodes[2 * j + 1] = BiasedToCode(biased[1][3]);
                 }
-                const F32x2 red = Pack(rf[0], rf[1]), green = Pack(gf[0], gf[1]), blue = Pack(bf[0], bf[1]);
+                else
+                {
+                    float rf[2], gf[2], bf[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                    {
+                        const int i = 2 * j + h;
+                        if (sizeof(HostT) == 1 && sizeof(PlaneT) == 1)
+                        {
+                            // 8-bit host into an 8-bit image: the sample is the code.  Byte -> float is one conversion instruction
+                            // (it takes the byte lane as an operand modifier).
+                            rf[h] = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 0)));
+                            gf[h] = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 1)));
+                            bf[h] = static_cast<float>(static_cast<uint8_t>(sample(i * CHANNELS + 2)));
+                        }
+                        else
+                        {
+                            rf[h] = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 0), p, hostLut) - kTwo23;
+                            gf[h] = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 1), p, hostLut) - kTwo23;
+                            bf[h] = SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 2), p, hostLut) - kTwo23;
+                        }
+                        if (CHANNELS == 4)
+                        {
+                            aCodes[i] = (sizeof(HostT) == 1 && sizeof(PlaneT) == 1) ? sample(i * CHANNELS + 3)
+                                                                                    : BiasedToCode(SampleToBiasedCode<HostT, PlaneT>(sample(i * CHANNELS + 3), p, hostLut));
+                        }
+                    }
+                    red = Pack(rf[0], rf[1]);
+                    green = Pack(gf[0], gf[1]);
+                    blue = Pack(bf[0], bf[1]);
+                }
                 F32x2 luma;
                 if (p.matrix.identity)
                 {
