@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
         const F32x2 half2 = Splat(0.5f), bias2 = Splat(kTwo23), offset2 = Splat(p.chromaOffset);
         const F32x2 kr2 = Splat(p.matrix.kr), kg2 = Splat(p.matrix.kg), kb2 = Splat(p.matrix.kb);
         const F32x2 cbScale2 = Splat(p.matrix.cbScale), crScale2 = Splat(p.matrix.crScale);
+        const F32x2 hostScale2 = Splat(p.maxCodeFloat * (1.0f / 32768.0f)); // exact: max <= 4095 times a power of two
         // 2^23 + trunc(v + 0.5) for both halves: BiasedToCode of either is the code (no upper clamp here)
         const auto biasedPair = [&](F32x2 v, float& lo, float& hi) { Unpack(AddRz2(Add2(v, half2), bias2), lo, hi); };
         const auto chromaClamp = [&](float biased) -> uint32_t { return BiasedToCode(fminf(biased, p.biasedMax)); }; // H.273: 2^depth -> 2^depth - 1
@@ -339,26 +340,49 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
                     }
                     return (words[r][k >> 2] >> (8 * (k & 3))) & 0xffu;
                 };
+                // channel c of pixels 2j and 2j + 1 as 2^23-biased codes in the image's depth
+                const auto biasedCodes = [&](int c) -> F32x2
+                {
+                    const uint32_t v0 = sample((2 * j) * CHANNELS + c), v1 = sample((2 * j + 1) * CHANNELS + c);
+                    if (sizeof(HostT) == 2)
+                    {
+                        // SampleToBiasedCode on the pair: (v / 32768f) * max is ONE rounding (the division is a scaling by 2^-15 and
+                        // max * 2^-15 is exact), so the single packed multiply by that constant is the same number; + 0.5f follows a
+                        // product and stays scalar
+                        float t0, t1;
+                        Unpack(Mul2(Sub2(Pack(__uint_as_float(0x4b000000u | v0), __uint_as_float(0x4b000000u | v1)), bias2), hostScale2), t0, t1);
+                        float b0, b1;
+                        Unpack(AddRz2(Pack(__fadd_rn(t0, 0.5f), __fadd_rn(t1, 0.5f)), bias2), b0, b1);
+                        return Pack(fminf(b0, p.biasedMax), fminf(b1, p.biasedMax));
+                    }
+                    return Pack(SampleToBiasedCode<HostT, PlaneT>(v0, p, hostLut), SampleToBiasedCode<HostT, PlaneT>(v1, p, hostLut));
+                };
                 F32x2 red, green, blue;
                 if (PREMULTIPLY)
                 {
-                    // both pixels' codes (2^23-biased), then colour * alpha / max per channel on the pair
-                    float biased[2][4];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                    // colour * alpha / max per channel on the pair
+                    const F32x2 alphaBiased = biasedCodes(3);
+                    const F32x2 alpha = Sub2(alphaBiased, bias2);
+                    red = Sub2(FastPremultiplyBiasedPair(Sub2(biasedCodes(0), bias2), alpha, p.maxCodeFloat, p.maxReciprocal), bias2);
+                    green = Sub2(FastPremultiplyBiasedPair(Sub2(biasedCodes(1), bias2), alpha, p.maxCodeFloat, p.maxReciprocal), bias2);
+                    blue = Sub2(FastPremultiplyBiasedPair(Sub2(biasedCodes(2), bias2), alpha, p.maxCodeFloat, p.maxReciprocal), bias2);
+                    float a0, a1;
+                    Unpack(alphaBiased, a0, a1);
+                    aCodes[2 * j] = BiasedToCode(a0);
+                    aCodes[2 * j + 1] = BiasedToCode(a1);
+                }
+                else if (sizeof(HostT) == 2)
+                {
+                    red = Sub2(biasedCodes(0), bias2);
+                    green = Sub2(biasedCodes(1), bias2);
+                    blue = Sub2(biasedCodes(2), bias2);
+                    if (CHANNELS == 4)
                     {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                        {
-                            biased[h][c] = SampleToBiasedCode<HostT, PlaneT>(sample((2 * j + h) * CHANNELS + c), p, hostLut);
-                        }
+                        float a0, a1;
+                        Unpack(biasedCodes(3), a0, a1);
+                        aCodes[2 * j] = BiasedToCode(a0);
+                        aCodes[2 * j + 1] = BiasedToCode(a1);
                     }
-                    const F32x2 alpha = Sub2(Pack(biased[0][3], biased[1][3]), bias2);
-                    red = Sub2(FastPremultiplyBiasedPair(Sub2(Pack(biased[0][0], biased[1][0]), bias2), alpha, p.maxCodeFloat, p.maxReciprocal), bias2);
-                    green = Sub2(FastPremultiplyBiasedPair(Sub2(Pack(biased[0][1], biased[1][1]), bias2), alpha, p.maxCodeFloat, p.maxReciprocal), bias2);
-                    blue = Sub2(FastPremultiplyBiasedPair(Sub2(Pack(biased[0][2], biased[1][2]), bias2), alpha, p.maxCodeFloat, p.maxReciprocal), bias2);
-                    aCodes[2 * j] = BiasedToCode(biased[0][3]);
-                    aCodes[2 * j + 1] = BiasedToCode(biased[1][3]);
                 }
                 else
                 {
