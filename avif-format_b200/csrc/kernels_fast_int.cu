@@ -266,7 +266,9 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeRgbIntPlanarKernel(const Rg
     constexpr int kVectorWords = (kWordsPerRow % 4 == 0) ? 4 : 2;                 // 128-bit loads where the row chunk allows
     constexpr int kPlaneBytes = static_cast<int>(sizeof(PlaneT));
     // (one copy: a copy per shared-memory bank makes the look-up conflict-free but costs every CTA 32 KB and 8192 table
-    // entries to fill -- measured slower, 724 -> 694 Gpx/s for RGB8 -> 10-bit 4:2:0 and 1711 -> 1377 for Gray8 -> 10-bit)
+    // entries to fill -- measured slower, 724 -> 694 Gpx/s for RGB8 -> 10-bit 4:2:0 and 1711 -> 1377 for Gray8 -> 10-bit;
+    // computing the entry instead -- division by 255 through a verified reciprocal step, packed -- is slower too, 727 -> 641:
+    // the look-up's shared-memory pipe is the lesser evil next to six more instructions per sample)
     __shared__ float hostLut[(sizeof(HostT) == 1 && sizeof(PlaneT) == 2) ? 256 : 1];
     if (sizeof(HostT) == 1 && sizeof(PlaneT) == 2)
     {
