@@ -960,7 +960,10 @@ namespace
         CopyPool()
         {
             const unsigned cores = std::thread::hardware_concurrency();
-            const int count = static_cast<int>(std::min<unsigned>(cores > 1 ? cores - 1 : 0, 15)); // 16 copying threads with the caller: ~60 GB/s, past the PCIe link they feed
+            // 8 copying threads with the caller.  More is worse, measured (profiles/r2_shuttle_pipeline.md): with 16 an 8K frame
+            // with pageable planes took 10.1 ms against 7.9 ms with 8 or 4 -- the copies then disturb the DMA they run beside --
+            // while fewer than 4 cannot keep up with config 4's 1.6 GB of planes or with first-touch page faults.
+            const int count = static_cast<int>(std::min<unsigned>(cores > 1 ? cores - 1 : 0, 7));
             for (int i = 0; i < count; ++i)
             {
                 workers.emplace_back([this] { Run(); });
