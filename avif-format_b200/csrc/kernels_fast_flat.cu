@@ -1,18 +1,21 @@
 // kernels_fast_flat.cu -- the float RGB -> planar YCbCr encode kernel for curves whose step table has the flat
 // form (curve_tables.h): BASELINE config 2, 7680x4320 RGB32f -> 12-bit PQ 4:2:0.
 //
-//   * one CTA per SM, kFlatWarps warps; the 128 KB flat table sits in shared memory next to one 3 KB staging
-//     buffer per warp.  Measured on the 8K PQ frame (Gpx/s): 16 warps 238 | 20: 251 | 24: 273 | 28: 278 | 30: 267
-//     (30 leaves 64 registers); the kernel is bound by instruction issue and shared-memory wavefronts, so resident
-//     warps matter, and the copy engine keeps the per-warp register cost of a fetch at zero;
-//   * a warp converts tiles of 2 rows x 128 pixels.  The two 1536-byte row segments of a tile are fetched by the
-//     copy engine (cp.async.bulk, completion on the warp's own mbarrier) straight into the staging buffer, so the
-//     fetch of tile i+1 costs the warp two instructions and no registers and overlaps the matrix and the stores of
-//     tile i; the lanes then read their 48 bytes per row with three conflict-free LDS.128;
-//   * float -> code: one 64-bit table look-up per sample (LookupCurveFlat); samples inside a fuzzy band (~1.5 %)
-//     are resolved by one bit of the L2-resident band bitmap, fetched for up to two samples of a lane at a time;
-//     +inf / NaN take the exact glibc-identical evaluation;
-//   * forward matrix, quantisation, chroma down-filter and stores: StoreTile (kernels_fast_common.cuh).
+//   * one CTA per SM, kFlatWarps warps; the step table (compact one-word entries + first_k, 67 KB at 12 bits; or the
+//     128 KB 64-bit flat table / the two-level table where the compact form does not apply) sits in shared memory next to
+//     one 3 KB staging buffer per warp.  The compact table's image is brought in by the copy engine (table_staging.cuh).
+//     Measured on the 8K PQ frame (Gpx/s, round 1): 16 warps 238 | 20: 251 | 24: 273 | 28: 278 | 30: 267 (30 leaves 64
+//     registers); the kernel is bound by instruction issue and shared-memory wavefronts, so resident warps matter, and
+//     the copy engine keeps the per-warp register cost of a fetch at zero;
+//   * a warp converts tiles of 2 rows x 128 pixels, walking straight down one tile column (FlatSchedule).  The two
+//     1536-byte row segments of a tile are fetched by the copy engine (cp.async.bulk, completion on the warp's own
+//     mbarrier) straight into the staging buffer, so the fetch of tile i+1 costs the warp two instructions and no
+//     registers and overlaps the matrix and the stores of tile i; the lanes then read their 48 bytes per row with three
+//     conflict-free LDS.128;
+//   * float -> code: one table look-up per sample (LookupCurveCompact: a 32-bit gather, 12 instructions); samples the
+//     look-up flags as possibly inside a fuzzy band (~1.5 %) are resolved by first_k and one bit of the L2-resident band
+//     bitmap, up to two samples of a lane at a time; +inf / NaN take the exact glibc-identical evaluation;
+//   * forward matrix, quantisation, chroma down-filter and stores: StoreTile (kernels_fast_common.cuh, packed FP32).
 #include "kernels_fast_common.cuh"
 #include "table_staging.cuh"
 #include "../../include/avifgpu.h"
