@@ -55,3 +55,27 @@ def test_bench_byte_accounting_matches_the_survey():
         wl = bench.Workload(key)
         assert wl.pixels == pixels, key
         assert wl.algorithmic_bytes == algorithmic_bytes, key
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference runs without a GPU (it is the CPU arm) and prints ONE JSON line with the keys the driver reads,
+    the same `config` object as the GPU arm's, and a cpu_baseline that says which library ran which stage."""
+    import json
+    import subprocess
+    env = dict(os.environ, AVIFGPU_BENCH_REFERENCE_BUDGET_S="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [line for line in out.stdout.splitlines() if line.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "Gpx/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["e2e"] == {"value": line["value"], "unit": "Gpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.common_config(bench.Workload("c2"))
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1 and "stages" in line["cpu_baseline"]
+
