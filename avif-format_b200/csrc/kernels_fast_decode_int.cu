@@ -453,6 +453,15 @@ __global__ void __launch_bounds__(kStreamThreads) StreamDecodeKernel(const Strea
     // one group: 8 samples per plane -> 8 host pixels at `target`
     const auto convertGroup = [&](const Raw8<SampleT>(&raw)[CHANNELS], uint8_t* target)
     {
+        if (MONO && kHost8 && CHANNELS == 1)
+        {
+            if (identityLuma)
+            {
+                // the 8 bytes as they are: unpacking and repacking them made this path instruction-bound (76 % of the issue slots)
+                __stcs(reinterpret_cast<uint2*>(target), make_uint2(raw[0].w[0], raw[0].w[1]));
+                return;
+            }
+        }
         uint32_t samples[8 * CHANNELS];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
