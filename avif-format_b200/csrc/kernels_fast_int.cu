@@ -547,12 +547,8 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeGrayIntKernel(const Rgb16Pa
         }
         __syncthreads();
     }
-    for (GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.groupsPerRow, p.rowCount);
-         walk.Inside(p.rowCount); walk.Advance(p.rowCount))
+    const auto loadGroup = [&](uint32_t (&words)[kWordsPerRow], long long row, long long column)
     {
-        const long long row = walk.row;
-        const long long column = walk.column;
-        uint32_t words[kWordsPerRow];
         const uint8_t* source = p.rows + row * p.rowStride + column * (kWordsPerRow * 4);
 #pragma unroll
         for (int q = 0; q < kWordsPerRow / kVectorWords; ++q)
@@ -571,6 +567,15 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeGrayIntKernel(const Rgb16Pa
                 words[2 * q + 0] = w.x;
                 words[2 * q + 1] = w.y;
             }
+        }
+    };
+    const auto convertGroup = [&](const uint32_t (&words)[kWordsPerRow], long long row, long long column)
+    {
+        if (sizeof(HostT) == 1 && sizeof(PlaneT) == 1 && CHANNELS == 1)
+        {
+            // Gray8 into an 8-bit image: the sample is the code (WriteHeifImage.cpp:224-240) -- the 8 bytes as they are
+            __stcs(reinterpret_cast<uint2*>(p.plane[0] + row * p.stride[0] + column * 8), make_uint2(words[0], words[1]));
+            return;
         }
         auto sample = [&](int k) -> uint32_t
         {
@@ -595,6 +600,46 @@ __global__ void __launch_bounds__(kRgbThreads) EncodeGrayIntKernel(const Rgb16Pa
         if (CHANNELS == 2)
         {
             StoreEight<PlaneT>(p.plane[3] + row * p.stride[3] + column * (8 * kPlaneBytes), aCodes);
+        }
+    };
+    // 8-bit hosts: a group is 8 or 16 bytes -- four groups' loads in flight before the first is converted (the launch is bound
+    // by memory latency otherwise: 28 % of the issue slots used, every warp on long_scoreboard); 16-bit hosts one at a time
+    constexpr int kInFlight = sizeof(HostT) == 1 ? 4 : 1;
+    GroupWalk walk(static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x, p.groupsPerRow, p.rowCount);
+    if (kInFlight == 1)
+    {
+        for (; walk.Inside(p.rowCount); walk.Advance(p.rowCount))
+        {
+            uint32_t words[kWordsPerRow];
+            loadGroup(words, walk.row, walk.column);
+            convertGroup(words, walk.row, walk.column);
+        }
+        return;
+    }
+    while (walk.Inside(p.rowCount))
+    {
+        uint32_t wordsAll[kInFlight][kWordsPerRow];
+        int rowOf[kInFlight], columnOf[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u)
+        {
+            rowOf[u] = -1;
+            columnOf[u] = 0;
+            if (walk.Inside(p.rowCount))
+            {
+                rowOf[u] = walk.row;
+                columnOf[u] = walk.column;
+                loadGroup(wordsAll[u], walk.row, walk.column);
+            }
+            walk.Advance(p.rowCount);
+        }
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u)
+        {
+            if (rowOf[u] >= 0)
+            {
+                convertGroup(wordsAll[u], rowOf[u], columnOf[u]);
+            }
         }
     }
 }
