@@ -31,6 +31,7 @@ int LaunchEncodeFastInteger(const EncodeParams& params, int hostDepth, void* str
 int LaunchEncodeFastGray32(const EncodeParams& params, int hostDepth, void* stream);  // 0 = not applicable
 cudaError_t BuildGray16Lut(uint16_t* deviceLut, int smpte428, uint32_t maxCode, void* stream);
 long long VerifyHlgDivisions(void* stream);
+long long VerifyPqRatio(void* stream);
 long long VerifyFastPremultiply(uint32_t maxCode, void* stream);
 long long VerifyGreenDivision(const DecodeParams& params, void* stream);
 int LaunchDecodeFast(const DecodeParams& params, void* stream);                  // 0 = not applicable
@@ -201,6 +202,20 @@ struct avifgpu_context
             launches += 1;
         }
         return hlgDivisionState;
+    }
+
+    // The quotient inside PQToLinear (ColorTransfer.cpp:110-112): the tuned float decode kernel uses a branch-free division
+    // once it has been compared with the IEEE one for every value the quotient's operands can take, on this device.
+    int pqRatioState = -1;
+    int VerifiedPqRatio()
+    {
+        if (pqRatioState < 0)
+        {
+            const long long disagreements = VerifyPqRatio(streams[0]);
+            pqRatioState = disagreements == 0 ? 1 : 0;
+            launches += 1;
+        }
+        return pqRatioState;
     }
 
     // YuvDecode.cpp:308 divides by the per-image constant kg; the tuned decode kernels use a 3-instruction form after
@@ -834,6 +849,7 @@ AVIFGPU_EXPORT int avifgpu_decode_rows_device(avifgpu_context* ctx, const avifgp
     DeviceGuard deviceGuardForTables(ctx->device);
     p.verifiedHlgDivisions = (desc->host_depth == 32 && transfer == AVIFGPU_TRANSFER_HLG) ? ctx->VerifiedHlgDivisions() : 0;
     p.verifiedGreenDivision = ctx->VerifiedGreenDivision(p);
+    p.verifiedPqRatio = (desc->host_depth == 32 && transfer == AVIFGPU_TRANSFER_PQ && desc->colorspace == AVIFGPU_COLORSPACE_YCBCR) ? ctx->VerifiedPqRatio() : 0;
     for (int k = 0; k < AVIFGPU_MAX_PLANES; ++k)
     {
         const PlaneGeometry g = DecodePlaneGeometry(*desc, k);
@@ -1347,6 +1363,7 @@ static int DecodeRowsHost(avifgpu_context* ctx, const avifgpu_decode_desc* desc,
 
     base.verifiedHlgDivisions = (desc->host_depth == 32 && transfer == AVIFGPU_TRANSFER_HLG) ? ctx->VerifiedHlgDivisions() : 0;
     base.verifiedGreenDivision = ctx->VerifiedGreenDivision(base);
+    base.verifiedPqRatio = (desc->host_depth == 32 && transfer == AVIFGPU_TRANSFER_PQ && desc->colorspace == AVIFGPU_COLORSPACE_YCBCR) ? ctx->VerifiedPqRatio() : 0;
     const int64_t rowPayload = static_cast<int64_t>(desc->width) * DecodeHostColBytes(*desc);
     const int64_t deviceRowStride = (rowPayload + 255) & ~255ll;
     const int sliceRows = SliceRows(nrows, rowPayload);

@@ -27,8 +27,10 @@
 
 #if defined(__CUDACC__)
 #define AVIF_HD __host__ __device__ __forceinline__
+#define AVIF_CONSTEXPR_HD __host__ __device__ constexpr
 #else
 #define AVIF_HD inline
+#define AVIF_CONSTEXPR_HD constexpr
 #endif
 
 namespace avifmath
@@ -109,6 +111,119 @@ __device__ __forceinline__ LibmTables StageLibmTables(uint64_t* storage, int thr
     t.powfLog2 = reinterpret_cast<const double*>(storage + 32);
     t.logf = reinterpret_cast<const double*>(storage + 64);
     return t;
+}
+#endif
+
+// Table reads go through these accessors so that a kernel can hand the functions below a table set of its own kind.
+AVIF_HD uint64_t TableExp2f(const LibmTables& t, uint32_t index) { return t.exp2f[index]; }
+AVIF_HD void TablePowfLog2(const LibmTables& t, uint32_t index, double& invc, double& logc)
+{
+    invc = t.powfLog2[2 * index];
+    logc = t.powfLog2[2 * index + 1];
+}
+
+// powf's log2 table with the exponent folded in.  glibc's log2_inline splits x = 2^k z, z in [OFF, 2 OFF), reads
+// { invc, logc } for z's top four fraction bits and forms y0 = logc + (double)k before the polynomial.  Both k and the
+// table index come from the same 13 bits of ix - OFF, so { invc, logc + (double)k } can be tabulated over (k, index): the
+// very same binary64 addition, done once per entry instead of once per call (two FP64 instructions and three integer ones
+// fewer per powf, a sixth of its cost).  An entry is 16 bytes; a table for k in [lowestExponent, 1] has
+// (2 - lowestExponent) * 16 entries (PQ / SMPTE 428 bases are +0 or at least 2^-77: 25 KB for -96; every float down to the
+// smallest subnormal after glibc's normalisation: 39 KB for -152).
+struct PowfLog2Wide
+{
+    static constexpr uint32_t kOff = 0x3f330000u;
+    // ix - BiasedOffset has the table index (in entries) in bits 19..31, counted from the entry of lowestExponent
+    static AVIF_CONSTEXPR_HD uint32_t BiasedOffset(int lowestExponent) { return kOff - (static_cast<uint32_t>(-lowestExponent) << 23); }
+    static AVIF_CONSTEXPR_HD uint32_t Entries(int lowestExponent) { return static_cast<uint32_t>(2 - lowestExponent) * 16u; }
+};
+
+// Entry `entry` of the wide table for `lowestExponent`: { invc, logc + (double)k } -- e_powf.c's `y0 = logc + (double) k`.
+AVIF_HD void PowfLog2WideEntry(const double* narrowTable, int lowestExponent, uint32_t entry, double& invc, double& y0)
+{
+    const uint32_t i = entry % 16u;
+    const int32_t k = static_cast<int32_t>(entry / 16u) + lowestExponent;
+    invc = narrowTable[2 * i];
+    y0 = narrowTable[2 * i + 1] + static_cast<double>(k);
+}
+
+// Host-side form of a staged wide table (the tests run the identical function bodies on the CPU).
+struct LibmTablesWideHost
+{
+    LibmTables narrow;
+    const double* wide; // Entries(lowestExponent) x { invc, y0 }
+    uint32_t wideBiasedOffset;
+    uint32_t wideLastEntry; // byte offset
+};
+
+AVIF_HD uint64_t TableExp2f(const LibmTablesWideHost& t, uint32_t index) { return t.narrow.exp2f[index]; }
+AVIF_HD void TablePowfLog2(const LibmTablesWideHost& t, uint32_t index, double& invc, double& logc) { TablePowfLog2(t.narrow, index, invc, logc); }
+AVIF_HD uint32_t WideBiasedOffset(const LibmTablesWideHost& t) { return t.wideBiasedOffset; }
+AVIF_HD uint32_t WideLastEntry(const LibmTablesWideHost& t) { return t.wideLastEntry; }
+AVIF_HD void TablePowfLog2Wide(const LibmTablesWideHost& t, uint32_t byteOffset, double& invc, double& y0)
+{
+    invc = t.wide[byteOffset / 8u];
+    y0 = t.wide[byteOffset / 8u + 1u];
+}
+
+#if defined(__CUDACC__)
+// The same tables named by their shared-STATE-SPACE addresses.  A generic pointer into shared memory costs an extra
+// add per look-up on sm_100 (the shared window's base, rebuilt from the CTA's rank in its cluster, is added to every
+// index before the LDS); an ld.shared on a 32-bit address lets the base sit in the instruction's uniform-register
+// operand.  One add per look-up is 4 % of the float decode kernel's instructions.
+struct LibmTablesShared
+{
+    uint32_t exp2f;
+    uint32_t powfLog2;
+    uint32_t logf;
+    // the exponent-folded log2 table (PowfLog2Wide below), when a kernel has staged one
+    uint32_t powfLog2Wide;     // address of its first entry
+    uint32_t wideBiasedOffset; // PowfLog2Wide::BiasedOffset(lowestExponent)
+    uint32_t wideLastEntry;    // byte offset of its last entry
+};
+
+__device__ __forceinline__ LibmTablesShared SharedSpace(const LibmTables& t)
+{
+    LibmTablesShared s;
+    s.exp2f = static_cast<uint32_t>(__cvta_generic_to_shared(t.exp2f));
+    s.powfLog2 = static_cast<uint32_t>(__cvta_generic_to_shared(t.powfLog2));
+    s.logf = static_cast<uint32_t>(__cvta_generic_to_shared(t.logf));
+    return s;
+}
+
+__device__ __forceinline__ uint64_t TableExp2f(const LibmTablesShared& t, uint32_t index)
+{
+    unsigned long long bits;
+    asm("ld.shared.b64 %0, [%1];" : "=l"(bits) : "r"(t.exp2f + index * 8u)); // the tables never change once staged
+    return bits;
+}
+
+__device__ __forceinline__ uint32_t WideBiasedOffset(const LibmTablesShared& t) { return t.wideBiasedOffset; }
+__device__ __forceinline__ uint32_t WideLastEntry(const LibmTablesShared& t) { return t.wideLastEntry; }
+__device__ __forceinline__ void TablePowfLog2Wide(const LibmTablesShared& t, uint32_t byteOffset, double& invc, double& y0)
+{
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(y0) : "r"(t.powfLog2Wide + byteOffset));
+}
+
+// Cooperative fill of a wide table in shared memory (`storage`: Entries(lowestExponent) * 2 doubles) from the staged narrow one.
+__device__ __forceinline__ void StagePowfLog2Wide(double* storage, const LibmTables& narrow, int lowestExponent, int threadIndex, int threadCount,
+                                                  LibmTablesShared* shared)
+{
+    const uint32_t entries = PowfLog2Wide::Entries(lowestExponent);
+    for (uint32_t entry = threadIndex; entry < entries; entry += threadCount)
+    {
+        double invc, y0;
+        PowfLog2WideEntry(narrow.powfLog2, lowestExponent, entry, invc, y0);
+        storage[2 * entry] = invc;
+        storage[2 * entry + 1] = y0;
+    }
+    shared->powfLog2Wide = static_cast<uint32_t>(__cvta_generic_to_shared(storage));
+    shared->wideBiasedOffset = PowfLog2Wide::BiasedOffset(lowestExponent);
+    shared->wideLastEntry = (entries - 1u) * 16u;
+}
+
+__device__ __forceinline__ void TablePowfLog2(const LibmTablesShared& t, uint32_t index, double& invc, double& logc)
+{
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(logc) : "r"(t.powfLog2 + index * 16u));
 }
 #endif
 
@@ -197,7 +312,8 @@ AVIF_HD double ScaleTableEntry(uint64_t tableBits, uint64_t ki)
 
 // 2^xd rounded once to binary32, for |xd| < 126 (callers check).  sign_bias is 0 on every path this library
 // takes (no negative bases), so it is omitted.
-AVIF_HD float Exp2Inline(double xd, const LibmTables& t)
+template <typename Tables>
+AVIF_HD float Exp2Inline(double xd, const Tables& t)
 {
     AVIF_LIBM_COEFFICIENTS(C, 3, kLibmExp2fPolyConst, AVIF_LIBM_EXP2F_POLY);
     // x = k/N + r with r in [-1/(2N), 1/(2N)], N = 32
@@ -206,7 +322,7 @@ AVIF_HD float Exp2Inline(double xd, const LibmTables& t)
     kd -= AVIF_LIBM_EXP2F_SHIFT_SCALED;
     const double r = xd - kd;
     // exp2(x) = 2^(k/N) * 2^r ~= s * (C0*r^3 + C1*r^2 + C2*r + 1)
-    uint64_t bits = t.exp2f[ki % 32];
+    uint64_t bits = TableExp2f(t, static_cast<uint32_t>(ki) % 32u);
     const double s = ScaleTableEntry(bits, ki);
     const double z = fma(C[0], r, C[1]);
     const double r2 = r * r;
@@ -217,17 +333,18 @@ AVIF_HD float Exp2Inline(double xd, const LibmTables& t)
 }
 
 // log2 of the positive normal float whose bits are ix (glibc e_powf.c log2_inline), in binary64.
-AVIF_HD double Log2Inline(uint32_t ix, const LibmTables& t)
+template <typename Tables>
+AVIF_HD double Log2Inline(uint32_t ix, const Tables& t)
 {
     AVIF_LIBM_COEFFICIENTS(A, 5, kLibmPowfLog2PolyConst, AVIF_LIBM_POWF_LOG2_POLY);
     // x = 2^k z; z in [OFF, 2*OFF) with OFF = 0x3f330000; 16 sub-intervals
     const uint32_t tmp = ix - 0x3f330000u;
-    const int i = static_cast<int>((tmp >> (23 - 4)) % 16);
+    const uint32_t i = (tmp >> (23 - 4)) % 16u;
     const uint32_t top = tmp & 0xff800000u;
     const uint32_t iz = ix - top;
     const int32_t k = static_cast<int32_t>(top) >> 23; // arithmetic shift
-    const double invc = t.powfLog2[2 * i];
-    const double logc = t.powfLog2[2 * i + 1];
+    double invc, logc;
+    TablePowfLog2(t, i, invc, logc);
     const double z = NormalFloatBitsToDouble(iz);
 
     // log2(x) = log1p(z/c-1)/ln2 + log2(c) + k
@@ -376,6 +493,93 @@ AVIF_HD float PowfModerateExponent(float x, float y, const LibmTables& t)
     return Exp2Inline(ylogx, t);
 }
 
+// True when PowfStraightLine(x, y) is glibc's powf(x, y) for every x in [+0, limit]: y finite and not zero, and
+// y log2 x can neither overflow (>= 126) nor leave the range the exp2 core handles by itself.  Two cases cover the
+// path: a positive exponent with bases up to 1 (PQ's 1 / m2 and 1 / m1, SMPTE 428's 2.6: y log2 x <= 0, and down to
+// -150 * 2.6 the double result simply rounds to the +0 / subnormal glibc's underflow screen returns), and a moderate
+// exponent with any finite base (the OOTF's gamma - 1).
+inline bool PowfStraightLineCovers(float y, bool basesUpToOneOnly)
+{
+    if (!(y == y) || y == 0.0f) return false;
+    const float magnitude = y < 0.0f ? -y : y;
+    if (magnitude < 0.8f) return true;                        // |y log2 x| < 0.8 * 150 for every finite x > 0
+    return basesUpToOneOnly && y > 0.0f && magnitude <= 6.5f; // y log2 x in [-975, 0]
+}
+
+// powf(x, yd) for a base whose sign bit is clear and that is finite (+0, subnormal or normal), and an exponent the caller
+// has checked with PowfStraightLineCovers -- without a single branch, so that several evaluations interleave (the
+// special-case branches of PowfImpl keep the compiler from overlapping two calls: measured as the float decode kernel's
+// main stall).  x = 0 runs the main path on whatever its bits give (finite garbage, discarded) and selects `zeroResult`
+// (+0 for y > 0, +inf for y < 0: what glibc returns) at the end; a subnormal x is normalised the way glibc does it
+// (x * 2^23, exponent - 23) with two selects instead of a branch when kMaybeSubnormal, and must not occur otherwise.
+// For -150 < y log2 x <= -126 glibc also falls through to the exp2 core; below that its screen returns +0, which is what
+// the core's double result (< 2^-150) rounds to.
+template <bool kMaybeSubnormal, typename Tables>
+AVIF_HD float PowfStraightLine(float x, double yd, float zeroResult, const Tables& t)
+{
+    uint32_t ix = AsUint(x);
+    const bool zero = ix == 0u;
+    if (kMaybeSubnormal)
+    {
+        const bool small = ix < 0x00800000u;
+        const float scaled = x * (small ? 0x1p23f : 1.0f);
+        ix = AsUint(scaled) - (small ? (23u << 23) : 0u);
+    }
+    const double ylogx = yd * Log2Inline(ix, t);
+    const float result = Exp2Inline(ylogx, t);
+    return zero ? zeroResult : result;
+}
+
+// Log2Inline through the exponent-folded table: the same values in every operation (y0 comes out of the table as the sum
+// glibc forms; z's bits are assembled straight from the fraction: iz = (tmp & 0x007fffff) + OFF is ix - top, and OFF has its
+// low three bits clear, so NormalFloatBitsToDouble(iz) is { (fraction >> 3) + ((OFF >> 3) + 0x38000000), fraction << 29 }).
+// An ix outside the table (a base that breaks the caller's promise, or the +0 whose result is selected away) reads the
+// nearest end: finite garbage, never an access outside the table.
+template <typename Tables>
+AVIF_HD double Log2InlineWide(uint32_t ix, const Tables& t)
+{
+    AVIF_LIBM_COEFFICIENTS(A, 5, kLibmPowfLog2PolyConst, AVIF_LIBM_POWF_LOG2_POLY);
+    const uint32_t tmp = ix - WideBiasedOffset(t);
+    uint32_t at = (tmp >> 15) & 0x1fff0u;
+    const uint32_t last = WideLastEntry(t);
+    at = at < last ? at : last;
+    double invc, y0;
+    TablePowfLog2Wide(t, at, invc, y0);
+    const uint32_t fraction = tmp & 0x007fffffu;
+#if defined(__CUDA_ARCH__)
+    const double z = __hiloint2double(static_cast<int>((fraction >> 3) + ((PowfLog2Wide::kOff >> 3) + 0x38000000u)), static_cast<int>(tmp << 29));
+#else
+    const double z = static_cast<double>(AsFloat(fraction + PowfLog2Wide::kOff));
+#endif
+    const double r = fma(z, invc, -1.0);
+    const double r2 = r * r;
+    double y = fma(A[0], r, A[1]);
+    const double p = fma(A[2], r, A[3]);
+    const double r4 = r2 * r2;
+    double q = fma(A[4], r, y0);
+    q = fma(p, r2, q);
+    y = fma(y, r4, q);
+    return y;
+}
+
+// PowfStraightLine on a table set that carries the wide log2 table; the bases must lie inside it (2^lowestExponent * OFF
+// up to 2.8) or be +0.
+template <bool kMaybeSubnormal, typename Tables>
+AVIF_HD float PowfStraightLineWide(float x, double yd, float zeroResult, const Tables& t)
+{
+    uint32_t ix = AsUint(x);
+    const bool zero = ix == 0u;
+    if (kMaybeSubnormal)
+    {
+        const bool small = ix < 0x00800000u;
+        const float scaled = x * (small ? 0x1p23f : 1.0f);
+        ix = AsUint(scaled) - (small ? (23u << 23) : 0u);
+    }
+    const double ylogx = yd * Log2InlineWide(ix, t);
+    const float result = Exp2Inline(ylogx, t);
+    return zero ? zeroResult : result;
+}
+
 AVIF_HD float Powf(float x, float y, const LibmTables& t) { return PowfImpl<false>(x, y, t); }
 
 // Powf for a base whose sign bit is known to be clear.
@@ -424,7 +628,8 @@ AVIF_HD float Expf(float x, const LibmTables& t)
 }
 
 // The body of Expf for arguments known to be finite with |x| < 88 (no overflow / underflow / NaN screening).
-AVIF_HD float ExpfNoScreen(float x, const LibmTables& t)
+template <typename Tables>
+AVIF_HD float ExpfNoScreen(float x, const Tables& t)
 {
     AVIF_LIBM_COEFFICIENTS(C, 3, kLibmExp2fPolyScaledConst, AVIF_LIBM_EXP2F_POLY_SCALED);
     const double xd = static_cast<double>(x);
@@ -433,7 +638,7 @@ AVIF_HD float ExpfNoScreen(float x, const LibmTables& t)
     const uint64_t ki = AsUint64(kd);
     kd -= AVIF_LIBM_EXP2F_SHIFT;
     const double r = z - kd;
-    uint64_t bits = t.exp2f[ki % 32];
+    uint64_t bits = TableExp2f(t, static_cast<uint32_t>(ki) % 32u);
     const double s = ScaleTableEntry(bits, ki);
     const double zz = fma(C[0], r, C[1]);
     const double r2 = r * r;

@@ -109,6 +109,7 @@ struct DecodeParams
     int32_t smCount;              // host-side extra for the launcher
     int32_t verifiedHlgDivisions; // 1 once the context has verified HLGToLinearUnit's fast divisions on this device
     int32_t verifiedGreenDivision; // 1 once the context has verified the fast `/ kg` of YuvDecode.cpp:308 for this matrix, depth, range
+    int32_t verifiedPqRatio;       // 1 once the context has verified the branch-free division inside PQToLinear on this device
 };
 
 // A launcher that sees a CUDA error has already consumed it (cudaGetLastError clears the slot), so it leaves the code

@@ -24,7 +24,7 @@ def test_device_libm_source_matches_system_libm(checker_binary):
     print(out.stdout)
     assert out.returncode == 0, out.stdout + out.stderr
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
-    assert len(lines) == 17
+    assert len(lines) == 26
     for line in lines:
         assert "mismatched=0 " in line + " ", line
 
