@@ -387,6 +387,37 @@ def test_every_10bit_triple_through_the_production_decode_kernel(gpu):
     assert bool(torch.isfinite(fast[:4096]).all().item())
 
 
+def test_every_10bit_triple_through_the_production_pq_decode_kernel(gpu):
+    """The same whole-domain sweep for the PQ sibling of config 3: all 2^30 (Y, Cb, Cr) triples of 10-bit codes, PQ at 1000 nit,
+    through the tuned kernel -- two branch-free powf per channel on the exponent-folded log2 table, the quotient between them by
+    the verified reciprocal-seed division -- and through the generic exact kernel (full powf, IEEE division)."""
+    import torch
+    import avifgpu
+    dev = torch.device("cuda", gpu.device)
+    if torch.cuda.get_device_properties(dev).total_memory < 80 * 2**30:
+        pytest.skip("needs ~45 GB of device memory")
+    w = h = 1 << 15
+    desc = abi.DecodeDesc(w, h, abi.COLORSPACE_YCBCR, abi.CHROMA_444, 10, abi.ALPHA_NONE, 32, cases.NCLX_2020_PQ(1), pq_peak_nits=1000)
+    index = torch.arange(w * h, dtype=torch.int32, device=dev).view(h, w)
+    planes = [(index & 1023).to(torch.int16), ((index >> 10) & 1023).to(torch.int16), (index >> 20).to(torch.int16)]
+    del index
+    struct = avifgpu.planes_from_tensors(planes + [None])
+    fast = torch.empty((h, w * 3), dtype=torch.float32, device=dev)
+    before = gpu.launch_count()
+    gpu.decode_device(desc, struct, fast.data_ptr(), fast.stride(0) * 4)
+    fast_launches = gpu.launch_count() - before
+    backing = torch.empty((h, w * 3 + 4), dtype=torch.float32, device=dev)
+    exact = backing[:, 1:w * 3 + 1]  # 4-byte aligned rows: the launcher takes the generic kernel
+    gpu.decode_device(desc, struct, exact.data_ptr(), exact.stride(0) * 4)
+    torch.cuda.synchronize(dev)
+    assert fast_launches >= 1
+    differing = 0
+    for y in range(0, h, 4096):  # compare in slabs to bound the temporaries
+        differing += int((fast[y:y + 4096].view(torch.int32) != exact[y:y + 4096].view(torch.int32)).sum().item())
+    assert differing == 0, f"{differing} of {fast.numel()} output samples differ"
+    assert bool(torch.isfinite(fast[:4096]).all().item())
+
+
 # ---- integer hosts, decode (kernels_fast_decode_int.cu) -----------------------------------------------------------------
 
 @pytest.mark.parametrize("w,h", [(8, 2), (9, 3), (24, 1), (67, 5), (256, 16), (263, 9), (1031, 6)])
