@@ -3,6 +3,8 @@
 profiles/: duration, DRAM bytes, pipe utilisation, stall reasons, and the hottest source lines.
 
     python profiles/summarize_ncu.py gpurun_out/r1_c2_fast_v8.ncu-rep profiles/r1_c2_encode_v8.ncu.txt [units_per_launch]
+
+NCU_LAUNCH_INDEX=n in the environment picks the n-th captured launch of a report that holds several (default 0).
 """
 import collections
 import csv
@@ -22,7 +24,10 @@ METRICS = [
 
 
 def ncu(args):
-    return subprocess.run(["ncu"] + args, capture_output=True, text=True).stdout
+    import os
+    index = os.environ.get("NCU_LAUNCH_INDEX")
+    pick = ["--launch-skip", index, "--launch-count", "1"] if index is not None else []
+    return subprocess.run(["ncu"] + pick + args, capture_output=True, text=True).stdout
 
 
 def main():
