@@ -24,7 +24,9 @@ planar RGB / monochrome images (per-code EOTF table; was ~45 Gpx/s with six exac
 layout (was 100 Gpx/s) and for Gray(+A) float hosts (was the generic kernel, 95 Gpx/s with the exact powf); the float RGB kernels use the
 compact step table, packed FP32 and a table image staged by the copy engine; the streaming kernels walk (row, column) without a division
 per step and keep four 8-byte groups in flight on 8-bit images.  Tried and dropped (measured slower): a copy of the 8-bit host table per
-shared-memory bank, two 16-byte groups in flight, 20 / 24 warps for the RGBA32f kernel.
+shared-memory bank, two 16-byte groups in flight, 20 / 24 warps for the RGBA32f kernel.  Three rows (8-bit monochrome decode, Gray8
+encodes) were re-measured on their own after the last changes to their kernels (`note` in the raw lines).  The float decode of a YCbCr
+image (config 3 and its PQ sibling) has bench lines of its own: `r2_bench_c3_rowpair_final.json`, `r2_bench_c3pq_rowpair_final.json`.
 """)
 with open(os.path.join(HERE, "r2_other_paths.md"), "w") as f:
     f.write("".join(out))
