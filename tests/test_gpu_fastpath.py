@@ -294,8 +294,8 @@ def test_ycc_to_rgb32_fast_kernel(gpu, port, w, h, chroma):
 
 @pytest.mark.parametrize("gamma,peak", [(1.2, 1000), (0.85, 100), (1.0, 334), (1.79, 25000), (1.8, 27000), (2.5, 100000)])
 def test_hlg_ootf_exponents_on_both_sides_of_the_screen_free_powf(gpu, port, gamma, peak):
-    """The tuned decode kernel's OOTF calls powf without its exponent screens when |gamma - 1| is in (0, 0.8)
-    (device_math.cuh PowfModerateExponent); gamma = 1 (exponent 0), 1.8 and 2.5 go to the generic kernel.  Either way the
+    """The tuned decode kernel's OOTF calls the branch-free powf when |gamma - 1| is in (0, 0.8) (device_math.cuh
+    PowfStraightLineCovers / PowfStraightLineWide); gamma = 1 (exponent 0), 1.8 and 2.5 go to the generic kernel.  Either way the
     float samples are the reference's, bit for bit -- black pixels (luma 0) included."""
     w, h = 260, 8
     nclx = cases.NCLX_2020_HLG(1)
