@@ -79,3 +79,73 @@ def test_reference_arm_prints_the_contract_line():
     assert line["config"] == bench.common_config(bench.Workload("c2"))
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1 and "stages" in line["cpu_baseline"]
 
+
+
+# ---- the premise of the float decode kernel's branch-free powf --------------------------------------------------------------
+
+@pytest.mark.parametrize("bit_depth", [10, 12])
+@pytest.mark.parametrize("nclx_name", ["none", "601lim", "709full", "2020full", "2020lim", "derived2020", "gbr"])
+def test_clamped_channel_sums_are_zero_or_far_from_subnormal(bit_depth, nclx_name):
+    """kernels_fast_decode.cu raises the clamped channel sums R = Y + rGain Cr, B = Y + bGain Cb, G = Y - gTerm(Cb, Cr) to PQ's
+    1 / m2 and SMPTE 428's 2.6 with a powf that takes +0 or NORMAL bases and a log2 table that starts at 2^-96
+    (ChannelSumsStayNormal, LowestWideExponent).  With the CPU checker's own tables and coefficients (YuvLookupTables.cpp:157-184,
+    YUVCoefficiants.cpp), in the reference's float32 expressions (YuvDecode.cpp:306-312): over EVERY (Y, Cr) and (Y, Cb) code pair,
+    and for G over every Y against the green terms nearest to it (the only candidates for a tiny difference), the smallest
+    non-zero clamped sum stays above 2^-40."""
+    import numpy as np
+    import cases
+    import oracle
+
+    nclx = {"none": None, "601lim": cases.NCLX_601(0), "709full": cases.NCLX_709(1), "2020full": cases.NCLX_2020_PQ(1),
+            "2020lim": cases.NCLX_2020_PQ(0), "derived2020": cases.NCLX_DERIVED(), "gbr": cases.NCLX_GBR()}[nclx_name]
+    checker = oracle.load_restatement()
+    kr, kg, kb = (np.float32(v) for v in checker.yuv_coefficients(nclx))
+    table_y, table_uv, _ = checker.yuv_tables(nclx, bit_depth, False)
+    one, two = np.float32(1), np.float32(2)
+    r_gain = two * (one - kr)
+    b_gain = two * (one - kb)
+    # the launcher's own screen (ChannelSumsStayNormal): every H.273 matrix passes it
+    for factor in (r_gain, b_gain, kr * (one - kr), kb * (one - kb), kg):
+        assert np.float32(1 / 65536) <= factor <= np.float32(4)
+
+    def smallest_positive(values):
+        clamped = np.clip(values, np.float32(0), np.float32(1))
+        positive = clamped[clamped > 0]
+        return float(positive.min()) if positive.size else 1.0
+
+    least = 1.0
+    for gain in (r_gain, b_gain):
+        offsets = (gain * table_uv).astype(np.float32)               # one rounding, as in the kernel and the reference
+        sums = (table_y[:, None] + offsets[None, :]).astype(np.float32)
+        least = min(least, smallest_positive(sums))
+    # G = Y - (2 (kr (1 - kr) Cr + kb (1 - kb) Cb)) / kg: all 2^(2 depth) green terms, then per Y the terms nearest to it
+    g_cr = ((kr * (one - kr)) * table_uv).astype(np.float32)
+    g_cb = ((kb * (one - kb)) * table_uv).astype(np.float32)
+    numerators = (two * (g_cr[:, None] + g_cb[None, :]).astype(np.float32)).astype(np.float32)
+    green_terms = np.unique((numerators / kg).astype(np.float32))
+    for y in np.unique(table_y):
+        at = int(np.searchsorted(green_terms, y))
+        near = green_terms[max(0, at - 4):at + 4]
+        least = min(least, smallest_positive((y - near).astype(np.float32)))
+    assert least > 2.0 ** -40, (nclx_name, bit_depth, least)
+
+
+def test_pq_quotient_is_zero_or_far_from_subnormal():
+    """The second powf of PQToLinear (ColorTransfer.cpp:110-112) takes max(x - c1, 0) / (c2 - c3 x) with x = powf(value, 1 / m2) in
+    [0, 1]; the tuned decode kernel evaluates it on +0 or NORMAL bases inside a log2 table that starts at 2^-96.  Over every float
+    x in [c1, 1] (below c1 the numerator is +0), in the reference's float32 expressions: the quotient is 0, or at least 2^-29, and
+    never above 1."""
+    import numpy as np
+    c1 = np.float32(3424.0) / np.float32(4096.0)
+    c2 = np.float32(2413.0) / np.float32(4096.0) * np.float32(32.0)
+    c3 = np.float32(2392.0) / np.float32(4096.0) * np.float32(32.0)
+    first = int(np.array([c1], np.float32).view(np.uint32)[0]) - 8
+    x = np.arange(first, 0x3F800001, dtype=np.uint32).view(np.float32)
+    numerator = np.maximum((x - c1).astype(np.float32), np.float32(0))
+    denominator = (c2 - (c3 * x).astype(np.float32)).astype(np.float32)
+    assert float(denominator.min()) > 0.16 and float(denominator.max()) < 18.9
+    quotient = (numerator / denominator).astype(np.float32)
+    assert float(quotient.max()) <= 1.0
+    positive = quotient[quotient > 0]
+    assert float(positive.min()) >= 2.0 ** -29
+    assert not bool((quotient[:8] != 0).any())  # x < c1
