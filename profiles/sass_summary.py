@@ -2,7 +2,7 @@
 """Per-kernel SASS inventory of avif-format_b200/lib/libavifgpu.so: instruction count and the mnemonics that show how
 a kernel moves data (UBLKCP = cp.async.bulk copy-engine fetch, SYNCS = mbarrier, VIADDMNMX = DPX add-clamp, ...).
 
-    python profiles/sass_summary.py > profiles/r1_sass_summary.txt
+    python profiles/sass_summary.py > profiles/r2_sass_summary.txt
 """
 import collections
 import os
@@ -11,7 +11,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "avif-format_b200", "lib", "libavifgpu.so")
-WATCH = ["UBLKCP", "SYNCS", "LDG", "STG", "LDS", "STS", "VIADDMNMX", "DFMA", "DMUL", "F2F", "MUFU", "R2P", "SHFL", "BAR"]
+WATCH = ["UBLKCP", "SYNCS", "LDG", "STG", "LDS", "STS", "VIADDMNMX", "VIMNMX", "DFMA", "DMUL", "DADD", "F2F", "MUFU", "FCHK", "FFMA2", "FMUL2", "FADD2", "R2P", "SHFL", "BAR", "BSSY", "CALL"]
 
 
 def main():
